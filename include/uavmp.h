@@ -1,0 +1,169 @@
+/* uavmp.h — C-ABI of the B200-native batched trajectory front-end / back-end.
+ *
+ * The reference has no plugin/FFI layer: the two hot paths are plain C++ classes called from ROS test nodes
+ * (SURVEY.md §8(b)).  A maintainer swaps them by calling these entry points from thin C++ shims that keep the
+ * reference signatures (include/uavmp/kino_astar.hpp, include/uavmp/minimum_control.hpp):
+ *
+ *   uavmp_kino_search_batch      replaces  path_searching::KinoAstar::search
+ *                                (src/planner/path_searching/include/path_searching/kino_astar.h:197-198,
+ *                                 src/planner/path_searching/src/kino_astar.cpp:81-272), B queries at once
+ *   uavmp_kino_set_params        replaces  KinoAstar::setParam            (kino_astar.cpp:6-36)
+ *   uavmp_map_set                replaces  KinoAstar::setGridMap + init + localCloudCallback
+ *                                (kino_astar.cpp:38-79) and the GridMap lookups it reads
+ *                                (src/planner/plan_env/include/plan_env/grid_map.h:257-260,350-359,370-385,400-404)
+ *   uavmp_minctrl_solve_batch    replaces  traj_optimization::MinimumControl::solve + getCoef1d
+ *                                (src/planner/traj_optimization/include/traj_optimization/minimum_control.h:34-41,
+ *                                 src/planner/traj_optimization/src/minimum_control.cpp:127-202), B 1-D QPs at once
+ *   uavmp_plan_batch             the search -> waypoints -> 3 x QP pipeline (an extension; the reference never
+ *                                chains the two)
+ *
+ * Conventions: plain pointers and sizes, no exceptions, return 0 on success or a negative UAVMP_E* code
+ * (uavmp_last_error gives the text).  A context is bound to one CUDA device and one stream and is not thread-safe.
+ * Unless a function says otherwise, pointers are HOST memory and the call copies in / out and synchronises.
+ */
+#ifndef UAVMP_H
+#define UAVMP_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UAVMP_OK 0
+#define UAVMP_EINVAL (-1)
+#define UAVMP_ECUDA (-2)
+#define UAVMP_ENOMEM (-3)
+#define UAVMP_ESTATE (-4) /* e.g. search before uavmp_map_set */
+#define UAVMP_ECAP (-5)   /* an output capacity was too small */
+
+/* search return codes, kino_astar.h:155-159 */
+#define UAVMP_REACH_END 1
+#define UAVMP_NO_PATH_FOUND 2
+
+typedef struct uavmp_ctx uavmp_ctx;
+
+/* ROS parameters of KinoAstar::setParam (kino_astar.cpp:8-19), same names */
+typedef struct {
+  int allocated_node_num;
+  int collision_check_type; /* 1: inflated grid, then (switch fall-through) ellipsoid; 2: ellipsoid only */
+  double rou_time;
+  double lambda_heu;
+  double goal_tolerance;
+  double time_step_size;
+  double max_velocity;
+  double max_accelration; /* sic — the reference's parameter name */
+  double acc_resolution;
+  double sample_tau;
+  double robot_r; /* kino_se3/robot_r */
+  double robot_h; /* kino_se3/robot_h */
+} uavmp_kino_params;
+
+/* OSQP settings that MinimumControl::solve leaves at their defaults or overrides
+ * (minimum_control.cpp:160-162; 3rd/osqp/include/public/osqp_api_constants.h:96-153) */
+typedef struct {
+  double rho, sigma, alpha;
+  double eps_abs, eps_rel, eps_prim_inf, eps_dual_inf;
+  int max_iter;
+  int check_termination;
+  int scaling;               /* Ruiz iterations */
+  int adaptive_rho;
+  int adaptive_rho_interval; /* 0 = 4 x check_termination (the deterministic, profiling-off rule) */
+  double adaptive_rho_tolerance;
+} uavmp_osqp_settings;
+
+/* synthetic world generator parameters (host utility; random_forest.cpp:509-535, simulator.xml:16-41) */
+typedef struct {
+  int map_type; /* 0 random pillars + rings, 2 two-slab wall */
+  uint32_t seed;
+  double x_size, y_size, resolution;
+  double init_x, init_y, init_radius;
+  int polar_num, circle_num;
+  double w_l, w_h, h_l, h_h;
+  double radius_l, radius_h, z_l, z_h, theta;
+  double wall_x, wall_y, wall_w;
+} uavmp_mapgen_params;
+
+/* per-call device timings, milliseconds, CUDA events on the context's stream */
+typedef struct {
+  float h2d_ms, search_ms, path_ms, qp_ms, d2h_ms, total_ms;
+  int search_launches, qp_launches, aux_launches;
+} uavmp_timings;
+
+/* counters the search kernel accumulates (summed over the batch); feed SURVEY.md §8(d)'s byte formula */
+typedef struct {
+  long long n_pop, n_occ_lookup, n_cloud_pts_tested, n_hash_probe, n_insert, n_update, n_heuristic, n_shot;
+} uavmp_kino_counters;
+
+/* ---- context ------------------------------------------------------------------------------------- */
+int uavmp_ctx_create(uavmp_ctx** out, int device);
+void uavmp_ctx_destroy(uavmp_ctx* ctx);
+const char* uavmp_last_error(const uavmp_ctx* ctx);
+/* the cudaStream_t every kernel of this context is launched on (for external CUDA events) */
+void* uavmp_ctx_stream(uavmp_ctx* ctx);
+int uavmp_ctx_sync(uavmp_ctx* ctx);
+const char* uavmp_version(void);
+
+/* ---- parameters ------------------------------------------------------------------------------------ */
+void uavmp_kino_params_default(uavmp_kino_params* p); /* the C++ defaults, kino_astar.cpp:8-19 */
+void uavmp_kino_params_launch(uavmp_kino_params* p);  /* test_kino_astar_searching.launch:44-57 */
+void uavmp_osqp_settings_default(uavmp_osqp_settings* s); /* what MinimumControl::solve ends up running with */
+int uavmp_kino_set_params(uavmp_ctx* ctx, const uavmp_kino_params* p);
+
+/* ---- map -------------------------------------------------------------------------------------------- */
+/* occ_inflate: GridMap::md_.occupancy_buffer_inflate_, address = x*ny*nz + y*nz + z (grid_map.h:257-260).
+ * origin / map_size: mp_.map_origin_ / mp_.map_size_ (grid_map.cpp:52-54).  cloud_xyz: the PointCloud2 the
+ * planner subscribed to ("local_cloud", kino_astar.cpp:38-55), n_cloud x 3 float32; may be NULL/0 only when no
+ * search uses the ellipsoid test. */
+int uavmp_map_set(uavmp_ctx* ctx, const int8_t* occ_inflate, int nx, int ny, int nz, const double origin[3],
+                  const double map_size[3], double resolution, const float* cloud_xyz, int n_cloud);
+
+/* ---- hot path (a): batched KinoAstar::search -------------------------------------------------------- */
+/* start_pt/start_vel/end_pt/end_vel: B x 3 f64.  status: 1|2 per query.  use_node_num: KinoAstar::use_node_num_
+ * at return.  path_offsets: B+1 prefix sums of path point counts (the points search() push_back's into `path`).
+ * pop_hash / n_pop (nullable): digest and length of the ordered expansion sequence, for parity checks.
+ * Returns the total number of path points (>= 0) or a negative error.  Fetch the points with uavmp_kino_get_paths. */
+long long uavmp_kino_search_batch(uavmp_ctx* ctx, int B, const double* start_pt, const double* start_vel,
+                                  const double* end_pt, const double* end_vel, int* status, int* use_node_num,
+                                  long long* path_offsets, uint64_t* pop_hash, int* n_pop);
+int uavmp_kino_get_paths(uavmp_ctx* ctx, double* path_xyz, long long cap_points);
+/* ordered popped voxel indices of query q of the last batch (B*pop_cap*3 ints kept on device when tracing is on) */
+int uavmp_kino_set_trace(uavmp_ctx* ctx, int pop_cap);
+int uavmp_kino_get_trace(uavmp_ctx* ctx, int q, int32_t* pop_idx_xyz, int cap);
+int uavmp_kino_get_counters(uavmp_ctx* ctx, uavmp_kino_counters* out);
+
+/* ---- hot path (b): batched MinimumControl::solve ---------------------------------------------------- */
+/* order: 5 (minimum jerk, the reference) or 7 (minimum snap, extension §9.3).  S segments.
+ * pos_1d: B x (S+1) waypoints; bound_vel / bound_acc (/ bound_jerk, order 7 only, else NULL): B x 2 start,end
+ * derivatives; time_vec: B x S.  coef: B x (order+1)*S, segment-major, ascending power, local time
+ * (== MinimumControl::getCoef1d).  solved[b] = 1 iff OSQP status == SOLVED (== the bool solve() returns);
+ * osqp_status / iters are OSQP's status_val / iter. */
+int uavmp_minctrl_solve_batch(uavmp_ctx* ctx, int order, int S, int B, const double* pos_1d,
+                              const double* bound_vel, const double* bound_acc, const double* bound_jerk,
+                              const double* time_vec, const uavmp_osqp_settings* settings, double* coef,
+                              int* solved, int* osqp_status, int* iters);
+
+/* ---- pipeline: search -> waypoints -> QP (extension) ------------------------------------------------ */
+/* For every query whose search reaches the goal, S+1 waypoints are taken from the sampled path at indices
+ * floor(k*(n-1)/S), T_i = seg_time (the reference's convention is 1.0, test_minimum_jerk.cpp:66-71), boundary
+ * derivatives = start_vel / end_vel and zero.  coef: B x 3 x (order+1)*S. */
+int uavmp_plan_batch(uavmp_ctx* ctx, int B, const double* start_pt, const double* start_vel, const double* end_pt,
+                     const double* end_vel, int order, int S, double seg_time, const uavmp_osqp_settings* settings,
+                     int* search_status, int* qp_solved, double* coef);
+/* same, every pointer already in device memory (inputs resident in HBM; outputs stay there) */
+int uavmp_plan_batch_dev(uavmp_ctx* ctx, int B, const double* d_start_pt, const double* d_start_vel,
+                         const double* d_end_pt, const double* d_end_vel, int order, int S, double seg_time,
+                         const uavmp_osqp_settings* settings, int* d_search_status, int* d_qp_solved, double* d_coef);
+
+int uavmp_get_timings(uavmp_ctx* ctx, uavmp_timings* out);
+
+/* ---- host utilities (not on the hot path) ----------------------------------------------------------- */
+void uavmp_mapgen_params_default(uavmp_mapgen_params* p, double x_size, double y_size, uint32_t seed);
+int uavmp_mapgen_cloud(const uavmp_mapgen_params* p, float* cloud_xyz, int cap); /* returns point count */
+int uavmp_grid_inflate_host(const float* cloud_xyz, int n, const double origin[3], const double map_size[3],
+                            double resolution, double obstacles_inflation, int8_t* occ_inflate, int nx, int ny, int nz);
+/* device-evaluated csrc/fpmath.h (op 0 cbrt, 1 acos, 2 cos, 3 powi) for host/device bit-parity tests */
+int uavmp_fpmath_eval(uavmp_ctx* ctx, int op, int n_pow, const double* x, double* y, long long n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UAVMP_H */

@@ -1,0 +1,91 @@
+"""GPU parity: batched CUDA KinoAstar::search vs the CPU oracle, bit-exact (integer / index work and f64 states).
+
+The comparison is the strongest the domain offers: status, use_node_num, the digest of the ORDERED pop sequence
+(voxel index + exact position / velocity / g bits of every expanded node), and every sampled path point bit for bit.
+"""
+import numpy as np
+import pytest
+
+import oracle_lib
+import uav_motion_planning_b200 as u
+
+pytestmark = pytest.mark.gpu
+
+
+def run_case(ctx, world, n_query, seed, ctype, launch=True, min_dist=10.0, allocated=None, trace_on_fail=True):
+    ka = u.KinoAstar(ctx)
+    if launch:
+        ka.setLaunchParams()
+    kw = dict(collision_check_type=ctype)
+    if allocated:
+        kw["allocated_node_num"] = allocated
+    ka.setParam(**kw)
+    ka.setGridMap(world)
+    sp, sv, ep, ev = u.sample_queries(world, n_query, seed=seed, min_dist=min_dist)
+    got = ka.search_batch(sp, sv, ep, ev)
+    orc = oracle_lib.KinoOracle(world, ka.params)
+    bad = []
+    for q in range(n_query):
+        ref = orc.search(sp[q], sv[q], ep[q], ev[q])
+        o0, o1 = got["path_offsets"][q], got["path_offsets"][q + 1]
+        same = (ref["status"] == got["status"][q] and ref["use_node_num"] == got["use_node_num"][q] and
+                ref["n_pop"] == got["n_pop"][q] and ref["pop_hash"] == int(got["pop_hash"][q]) and
+                ref["n_path"] == o1 - o0 and np.array_equal(ref["path"].view(np.uint64), got["paths"][o0:o1].view(np.uint64)))
+        if not same:
+            bad.append((q, ref["status"], int(got["status"][q]), ref["use_node_num"], int(got["use_node_num"][q]),
+                        ref["n_pop"], int(got["n_pop"][q]), ref["n_path"], int(o1 - o0)))
+    return bad, got, ka, orc, (sp, sv, ep, ev)
+
+
+@pytest.fixture(scope="module")
+def world_small():
+    return u.make_world(20, 20, 5, seed=1)
+
+
+@pytest.fixture(scope="module")
+def world_big():
+    return u.make_world(50, 50, 10, seed=1)
+
+
+def test_small_map_grid_and_ellipsoid(gpu_ctx, world_small):
+    bad, got, *_ = run_case(gpu_ctx, world_small, 48, seed=2, ctype=1, min_dist=8.0)
+    assert not bad, bad
+    assert (got["status"] == 1).mean() > 0.5
+
+
+def test_small_map_ellipsoid_only(gpu_ctx, world_small):
+    bad, *_ = run_case(gpu_ctx, world_small, 32, seed=3, ctype=2, min_dist=8.0)
+    assert not bad, bad
+
+
+def test_big_map(gpu_ctx, world_big):
+    bad, got, *_ = run_case(gpu_ctx, world_big, 96, seed=4, ctype=1)
+    assert not bad, bad
+
+
+def test_pool_exhaustion_and_unreachable(gpu_ctx, world_small):
+    # tiny pool: every query hits "reach max node num" (kino_astar.cpp:243-247) -> NO_PATH_FOUND, use_node_num == pool
+    bad, got, *_ = run_case(gpu_ctx, world_small, 16, seed=5, ctype=1, allocated=3000, min_dist=8.0)
+    assert not bad, bad
+    assert (got["status"] == 2).any()
+
+
+def test_code_default_params(gpu_ctx, world_small):
+    # the C++ defaults (kino_astar.cpp:8-19): 125 primitives, tau 0.5 / step 0.1 -> 6 checkpoints
+    bad, *_ = run_case(gpu_ctx, world_small, 24, seed=6, ctype=1, launch=False, min_dist=8.0)
+    assert not bad, bad
+
+
+def test_pop_trace_matches(gpu_ctx, world_small):
+    ka = u.KinoAstar(gpu_ctx)
+    ka.setLaunchParams()
+    ka.setTrace(512)
+    ka.setGridMap(world_small)
+    sp, sv, ep, ev = u.sample_queries(world_small, 8, seed=7, min_dist=8.0)
+    got = ka.search_batch(sp, sv, ep, ev)
+    orc = oracle_lib.KinoOracle(world_small, ka.params)
+    for q in range(8):
+        ref = orc.search(sp[q], sv[q], ep[q], ev[q], pop_cap=512)
+        n = min(ref["n_pop"], 512)
+        assert np.array_equal(ka.pop_trace(q, 512)[:n], ref["trace"][:n])
+    ka.setTrace(0)

@@ -1,0 +1,1259 @@
+// kino_kernel.cu — K1: batched kinodynamic A* (one CTA per query) for sm_100a.
+//
+// Replaces path_searching::KinoAstar::search and its callees
+// (reference: src/planner/path_searching/src/kino_astar.cpp:81-272 search, :651-670 StateTransit,
+//  :312-337 getHeuristicCost, :339-414 cubic/quartic, :416-471 computeShotTraj, :721-758 isCollisionFree,
+//  :473-557 retrievePath/samplePath; plan_env/grid_map.h:350-404 the grid lookups).
+//
+// Execution model.  The search is sequential per query (pop -> expand -> commit) and the open list is a binary
+// heap whose keys the reference mutates in place, so the pop ORDER is only defined by
+// libstdc++'s push_heap/pop_heap.  Each CTA owns one query and an arena in HBM (node records, heap array,
+// open-addressing hash table).  Per expansion:
+//   A. all 256 threads evaluate the (2r+1)^3 motion primitives in parallel: checkpoint integration, in-map,
+//      inflated-grid byte, SE(3) ellipsoid-vs-cloud test (only where a dilated "cloud nearby" bit is set),
+//      velocity limits, end state -> voxel key;
+//   B. keys are de-duplicated inside the expansion (shared-memory table), group leaders probe the global hash
+//      table, the OBVP quartic heuristic is evaluated for every candidate in parallel;
+//   C. new node ids are assigned by an ordered block scan (== the reference's use_node_num_++ order), node
+//      records and hash slots are written in parallel;
+//   D. warp 0 replays the heap pushes / in-place key mutations in lattice order.  The ancestors of all new
+//      leaves are staged in shared memory first ("closure"), so one push costs a ballot, not a chain of
+//      dependent HBM loads.
+// All f64 arithmetic is written with the reference's association and compiled with -fmad=false; cbrt/acos/cos/pow
+// come from fpmath.h, which the CPU oracle shares, so popped-node sequences are bit-identical.
+#include <cub/cub.cuh>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <algorithm>
+#include <numeric>
+
+#include "fpmath.h"
+#include "uavmp_internal.h"
+
+#define KT 256
+#define TAB_SIZE 2048
+#define PUSH_BATCH 256
+#define HC_CAP 608
+#define FULL 0xffffffffu
+#define KEY_BIAS (1 << 17)
+#define EPOCH_BITS 10
+#define EPOCH_MASK ((1u << EPOCH_BITS) - 1u)
+
+namespace {
+
+enum : uint8_t {
+  ST_REJECT = 0, ST_FEASIBLE = 1, ST_CLOSED = 2, ST_NEW = 3, ST_OPEN_CAND = 4, ST_OPEN_NOCAND = 5,
+  ST_FOLLOW_CAND = 6, ST_FOLLOW_NOCAND = 7
+};
+
+struct SearchSmem {
+  unsigned long long key[UAVMP_MAXPRIM];
+  double f[UAVMP_MAXPRIM];
+  double topt[UAVMP_MAXPRIM];
+  double gcur[UAVMP_MAXPRIM];
+  uint32_t id[UAVMP_MAXPRIM];
+  uint32_t tab[TAB_SIZE];
+  HeapSlot hc[HC_CAP];
+  uint16_t list1[UAVMP_MAXPRIM];
+  uint16_t list2[UAVMP_MAXPRIM];
+  uint8_t state[UAVMP_MAXPRIM];
+  int lv_lo[32], lv_off[32], lv_hi[32];
+  double cp[3], cv[3], cg;
+  double gp[3], gv[3];
+  double sp[3], sv[3];
+  double opt_time;
+  double shot[12];
+  unsigned long long pop_hash;
+  unsigned long long cnt[8];
+  uint32_t cur_id, cur_parent, epoch;
+  int heap_len, use_num, n_pop, n1, n2, n_new, status, flag, q, hc_active, hc_total, hc_identity;
+  int wsum[KT / 32];
+};
+
+__device__ __forceinline__ double dot3(double ax, double ay, double az, double bx, double by, double bz) {
+  return (ax * bx + ay * by) + az * bz;  // Eigen fixed-size-3 reduction order
+}
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long h, unsigned long long v) {
+  h ^= v;
+  h *= 0x100000001b3ull;
+  h ^= h >> 29;
+  return h;
+}
+
+// ---- OBVP heuristic (kino_astar.cpp:312-414) ----------------------------------------------------------
+__device__ int d_cubic(double a, double b, double c, double d, double* dts) {
+  int n = 0;
+  double a2 = b / a;
+  double a1 = c / a;
+  double a0 = d / a;
+  double Q = (3 * a1 - a2 * a2) / 9;
+  double R = (9 * a1 * a2 - 27 * a0 - 2 * a2 * a2 * a2) / 54;
+  double D = Q * Q * Q + R * R;
+  if (D > 0) {
+    double S = fpm::cbrt(R + sqrt(D));
+    double T = fpm::cbrt(R - sqrt(D));
+    dts[n++] = -a2 / 3 + (S + T);
+  } else if (D == 0) {
+    double S = fpm::cbrt(R);
+    dts[n++] = -a2 / 3 + S + S;
+    dts[n++] = -a2 / 3 - S;
+  } else {
+    double theta = fpm::acos(R / sqrt(-Q * Q * Q));
+    dts[n++] = 2 * sqrt(-Q) * fpm::cos(theta / 3) - a2 / 3;
+    dts[n++] = 2 * sqrt(-Q) * fpm::cos((theta + 2 * M_PI) / 3) - a2 / 3;
+    dts[n++] = 2 * sqrt(-Q) * fpm::cos((theta + 4 * M_PI) / 3) - a2 / 3;
+  }
+  return n;
+}
+
+__device__ int d_quartic(double a, double b, double c, double d, double e, double* dts) {
+  int n = 0;
+  double a3 = b / a;
+  double a2 = c / a;
+  double a1 = d / a;
+  double a0 = e / a;
+  double ys[3];
+  d_cubic(1, -a2, a1 * a3 - 4 * a0, 4 * a2 * a0 - a1 * a1 - a3 * a3 * a0, ys);
+  double y1 = ys[0];
+  double r = a3 * a3 / 4 - a2 + y1;
+  if (r < 0) return 0;
+  double R = sqrt(r);
+  double D, E;
+  if (R != 0) {
+    D = sqrt(0.75 * a3 * a3 - R * R - 2 * a2 + 0.25 * (4 * a3 * a2 - 8 * a1 - a3 * a3 * a3) / R);
+    E = sqrt(0.75 * a3 * a3 - R * R - 2 * a2 - 0.25 * (4 * a3 * a2 - 8 * a1 - a3 * a3 * a3) / R);
+  } else {
+    D = sqrt(0.75 * a3 * a3 - 2 * a2 + 2 * sqrt(y1 * y1 - 4 * a0));
+    E = sqrt(0.75 * a3 * a3 - 2 * a2 - 2 * sqrt(y1 * y1 - 4 * a0));
+  }
+  if (!(D != D)) {
+    dts[n++] = -a3 / 4 + R / 2 + D / 2;
+    dts[n++] = -a3 / 4 + R / 2 - D / 2;
+  }
+  if (!(E != E)) {
+    dts[n++] = -a3 / 4 - R / 2 + E / 2;
+    dts[n++] = -a3 / 4 - R / 2 - E / 2;
+  }
+  return n;
+}
+
+// returns tie_breaker * optimal_cost; topt < 0 when no root qualified (the reference then leaves
+// optimal_time untouched)
+__device__ double d_heuristic(const KinoParamsDev& P, double x1x, double x1y, double x1z, double v1x, double v1y,
+                              double v1z, double x2x, double x2y, double x2z, double v2x, double v2y, double v2z,
+                              double& topt) {
+  double dpx = x2x - x1x, dpy = x2y - x1y, dpz = x2z - x1z;
+  double optimal_cost = (double)(1 << 30);
+  double a = -36 * dot3(dpx, dpy, dpz, dpx, dpy, dpz);
+  double b = 24 * dot3(dpx, dpy, dpz, v1x + v2x, v1y + v2y, v1z + v2z);
+  double c = -4 * (dot3(v1x, v1y, v1z, v1x, v1y, v1z) + dot3(v1x, v1y, v1z, v2x, v2y, v2z) +
+                   dot3(v2x, v2y, v2z, v2x, v2y, v2z));
+  double d = 0;
+  double e = P.rou;
+  double dts[4];
+  int n = d_quartic(e, d, c, b, a, dts);
+  double T_bar = fmax(fmax(fabs(x1x - x2x), fabs(x1y - x2y)), fabs(x1z - x2z)) / P.vmax;
+  topt = -1.0;
+  for (int i = 0; i < n; i++) {
+    double t = dts[i];
+    double tmp_cost = a / (-3 * t * t * t) + b / (-2 * t * t) + c / (-1 * t) + e * t;
+    if (tmp_cost < optimal_cost && t > T_bar && tmp_cost > 0) {
+      optimal_cost = tmp_cost;
+      topt = t;
+    }
+  }
+  return P.tie * optimal_cost;
+}
+
+// ---- grid lookups (grid_map.h:350-404) ------------------------------------------------------------------
+__device__ __forceinline__ bool in_map(const MapDev& M, double x, double y, double z) {
+  if (x < M.lox || y < M.loy || z < M.loz) return false;
+  if (x > M.hix || y > M.hiy || z > M.hiz) return false;
+  return true;
+}
+__device__ __forceinline__ void pos_to_index(const MapDev& M, double x, double y, double z, int& ix, int& iy, int& iz) {
+  ix = (int)floor((x - M.ox) * M.inv_res);
+  iy = (int)floor((y - M.oy) * M.inv_res);
+  iz = (int)floor((z - M.oz) * M.inv_res);
+}
+__device__ __forceinline__ unsigned map_flags(const MapDev& M, int ix, int iy, int iz) {
+  return __ldg(M.flags + ((size_t)ix * M.ny + iy) * M.nz + iz);
+}
+
+// kino_astar.cpp:721-758 with the KD-tree replaced by a cell list (any-point-inside semantics, §9.1 Q12)
+__device__ bool ellipsoid_free(const MapDev& M, const KinoParamsDev& P, const double* __restrict__ Ei, double px,
+                               double py, double pz, unsigned& n_tested) {
+  int x0 = max((int)floor((px - P.box_r - M.cox) * M.inv_cell), 0);
+  int x1 = min((int)floor((px + P.box_r - M.cox) * M.inv_cell), M.cnx - 1);
+  int y0 = max((int)floor((py - P.box_r - M.coy) * M.inv_cell), 0);
+  int y1 = min((int)floor((py + P.box_r - M.coy) * M.inv_cell), M.cny - 1);
+  int z0 = max((int)floor((pz - P.box_r - M.coz) * M.inv_cell), 0);
+  int z1 = min((int)floor((pz + P.box_r - M.coz) * M.inv_cell), M.cnz - 1);
+  float sx = (float)px, sy = (float)py, sz = (float)pz;
+  double e00 = Ei[0], e01 = Ei[1], e02 = Ei[2], e10 = Ei[3], e11 = Ei[4], e12 = Ei[5], e20 = Ei[6], e21 = Ei[7],
+         e22 = Ei[8];
+  for (int ix = x0; ix <= x1; ix++)
+    for (int iy = y0; iy <= y1; iy++) {
+      // cells along z are contiguous in the cell list: one range per (ix, iy)
+      int cbase = (ix * M.cny + iy) * M.cnz;
+      int k0 = __ldg(M.cell_start + cbase + z0), k1 = __ldg(M.cell_start + cbase + z1 + 1);
+      for (int k = k0; k < k1; k++) {
+        float4 q = __ldg(M.pts + k);
+        float dx = q.x - sx, dy = q.y - sy, dz = q.z - sz;
+        float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        if (!(d2 <= P.kd_r2)) continue;
+        n_tested++;
+        double ddx = (double)q.x - px, ddy = (double)q.y - py, ddz = (double)q.z - pz;
+        double tx = (e00 * ddx + e01 * ddy) + e02 * ddz;
+        double ty = (e10 * ddx + e11 * ddy) + e12 * ddz;
+        double tz = (e20 * ddx + e21 * ddy) + e22 * ddz;
+        if (sqrt(dot3(tx, ty, tz, tx, ty, tz)) <= 1.0) return false;
+      }
+    }
+  return true;
+}
+
+__device__ __forceinline__ unsigned long long pack_key(int ix, int iy, int iz, bool& ok) {
+  unsigned ux = (unsigned)(ix + KEY_BIAS), uy = (unsigned)(iy + KEY_BIAS), uz = (unsigned)(iz + KEY_BIAS);
+  ok = (ux < (1u << 18)) && (uy < (1u << 18)) && (uz < (1u << 18));
+  return ((unsigned long long)ux << 36) | ((unsigned long long)uy << 18) | (unsigned long long)uz;
+}
+__device__ __forceinline__ uint32_t hash_key(unsigned long long k, int bits) {
+  return (uint32_t)((k * 0x9E3779B97F4A7C15ull) >> (64 - bits));
+}
+
+// ---- open list: libstdc++ heap semantics on cached keys -----------------------------------------------
+// slot i (0-based) is stored at heap[i + 1]
+__device__ void heap_pop_serial(HeapSlot* H, KinoNode* nodes, int& len, HeapSlot& top) {
+  // std::pop_heap + pop_back (bits/stl_heap.h __pop_heap -> __adjust_heap -> __push_heap), comp(a,b) = f[a] > f[b]
+  top = H[1];
+  int old_len = len;
+  len = old_len - 1;
+  if (old_len <= 1) return;
+  HeapSlot value = H[old_len];  // last element
+  int n = len;
+  int hole = 0;
+  int second = 0;
+  while (second < (n - 1) / 2) {
+    second = 2 * (second + 1);
+    HeapSlot r = H[second + 1], l = H[second];  // right child = slot `second`, left = second-1
+    if (r.f > l.f) { second--; r = l; }
+    H[hole + 1] = r;
+    nodes[r.id].heap_pos = (uint32_t)hole;
+    hole = second;
+  }
+  if ((n & 1) == 0 && second == (n - 2) / 2) {
+    second = 2 * (second + 1);
+    HeapSlot l = H[second];  // slot second-1
+    H[hole + 1] = l;
+    nodes[l.id].heap_pos = (uint32_t)hole;
+    hole = second - 1;
+  }
+  int parent = (hole - 1) / 2;
+  while (hole > 0) {
+    HeapSlot pe = H[parent + 1];
+    if (!(pe.f > value.f)) break;
+    H[hole + 1] = pe;
+    nodes[pe.id].heap_pos = (uint32_t)hole;
+    hole = parent;
+    parent = (hole - 1) / 2;
+  }
+  H[hole + 1] = value;
+  nodes[value.id].heap_pos = (uint32_t)hole;
+}
+
+// closure = the ancestors of leaves n0+1 .. n0+m (1-based heap indices), staged in shared memory (warp 0)
+__device__ void closure_load(SearchSmem& s, const HeapSlot* H, int len0, int m, int lane) {
+  int total = 0;
+  bool identity = (m > len0 + 1);
+  for (int d = 0; d < 32; d++) {
+    int lo, hi, off;
+    if (identity) {
+      lo = 1; hi = len0 + m; off = 0;
+    } else {
+      lo = max((len0 + 1) >> d, 1);
+      hi = (len0 + m) >> d;
+      off = total;
+    }
+    int cnt = hi >= lo ? hi - lo + 1 : 0;
+    if (lane == 0) { s.lv_lo[d] = lo; s.lv_hi[d] = hi; s.lv_off[d] = off; }
+    if (!identity) {
+      if (d >= 1)
+        for (int j = lane; j < cnt; j += 32) { HeapSlot e = H[lo + j]; e.dirty = 0; s.hc[off + j] = e; }
+      total += cnt;
+    }
+  }
+  if (identity) {
+    total = len0 + m;
+    for (int j = lane; j < len0; j += 32) { HeapSlot e = H[1 + j]; e.dirty = 0; s.hc[j] = e; }
+  }
+  if (lane == 0) { s.hc_total = total; s.hc_active = 1; s.hc_identity = identity ? 1 : 0; }
+  __syncwarp();
+}
+
+__device__ void closure_flush(SearchSmem& s, HeapSlot* H, int lane) {
+  if (!s.hc_active) return;
+  __syncwarp();
+  if (s.hc_identity) {
+    for (int j = lane; j < s.hc_total; j += 32) { HeapSlot e = s.hc[j]; if (e.dirty) H[1 + j] = e; }
+  } else {
+    for (int d = 0; d < 32; d++) {
+      int lo = s.lv_lo[d], hi = s.lv_hi[d], off = s.lv_off[d];
+      int cnt = hi >= lo ? hi - lo + 1 : 0;
+      for (int j = lane; j < cnt; j += 32) { HeapSlot e = s.hc[off + j]; if (e.dirty) H[lo + j] = e; }
+    }
+  }
+  __syncwarp();
+  if (lane == 0) s.hc_active = 0;
+  __syncwarp();
+}
+
+// std::push_heap of (f, id) as 1-based leaf n1, ancestors read from the closure
+__device__ void closure_push(SearchSmem& s, KinoNode* nodes, int n1, double f, uint32_t id, int lane) {
+  int a = n1 >> lane;
+  bool valid = (lane >= 1) && (a >= 1);
+  HeapSlot e;
+  e.f = 0; e.id = 0; e.dirty = 0;
+  if (valid) e = s.hc[s.lv_off[lane] + (a - s.lv_lo[lane])];
+  bool gt = valid && (e.f > f);
+  unsigned m = __ballot_sync(FULL, gt);
+  unsigned cont = m >> 1;            // bit j: level j+1 moves down
+  int L = __ffs(~cont) - 1;          // number of consecutive moves
+  if (lane >= 1 && lane <= L) {
+    int tgt = n1 >> (lane - 1);
+    e.dirty = 1;
+    s.hc[s.lv_off[lane - 1] + (tgt - s.lv_lo[lane - 1])] = e;
+    nodes[e.id].heap_pos = (uint32_t)(tgt - 1);
+  }
+  if (lane == 0) {
+    int tgt = n1 >> L;
+    HeapSlot ne; ne.f = f; ne.id = id; ne.dirty = 1;
+    s.hc[s.lv_off[L] + (tgt - s.lv_lo[L])] = ne;
+    nodes[id].heap_pos = (uint32_t)(tgt - 1);
+  }
+  __syncwarp();
+}
+
+// in-place key mutation of an element that is inside the open list (kino_astar.cpp:251-265)
+__device__ void heap_set_key(SearchSmem& s, HeapSlot* H, KinoNode* nodes, uint32_t id, double f, int lane) {
+  __syncwarp();
+  uint32_t slot = *((volatile uint32_t*)&nodes[id].heap_pos);
+  int n1 = (int)slot + 1;
+  int where = -1;
+  if (s.hc_active) {
+    bool hit = (n1 >= s.lv_lo[lane]) && (n1 <= s.lv_hi[lane]);
+    unsigned m = __ballot_sync(FULL, hit);
+    if (m) where = __ffs(m) - 1;
+  }
+  if (lane == 0) {
+    if (where >= 0) {
+      HeapSlot& e = s.hc[s.lv_off[where] + (n1 - s.lv_lo[where])];
+      e.f = f;
+      e.dirty = 1;
+    } else {
+      H[n1].f = f;
+    }
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void end_state(const SearchSmem& s, const KinoParamsDev& P, double ux, double uy,
+                                          double uz, double* x) {
+  // StateTransit(x0, xt, ut, sample_tau) — kino_astar.cpp:216,651-670
+  x[0] = (s.cp[0] + P.tau * s.cv[0]) + P.htau * ux;
+  x[1] = (s.cp[1] + P.tau * s.cv[1]) + P.htau * uy;
+  x[2] = (s.cp[2] + P.tau * s.cv[2]) + P.htau * uz;
+  x[3] = s.cv[0] + P.tau * ux;
+  x[4] = s.cv[1] + P.tau * uy;
+  x[5] = s.cv[2] + P.tau * uz;
+}
+
+__device__ void shot_pos(const double* c, double t, double& x, double& y, double& z) {
+  // shot_coef_ * [1 t t^2 t^3]^T with pow(t, i) (kino_astar.cpp:441-446)
+  double t0 = fpm::powi(t, 0), t1 = fpm::powi(t, 1), t2 = fpm::powi(t, 2), t3 = fpm::powi(t, 3);
+  x = ((c[0] * t0 + c[1] * t1) + c[2] * t2) + c[3] * t3;
+  y = ((c[4] * t0 + c[5] * t1) + c[6] * t2) + c[7] * t3;
+  z = ((c[8] * t0 + c[9] * t1) + c[10] * t2) + c[11] * t3;
+}
+
+// =====================================================================================================
+__global__ void __launch_bounds__(KT) kino_search_kernel(const KinoParamsDev* __restrict__ Pp, LatticeDev lat,
+                                                         const MapDev* __restrict__ Mp, KinoArena* arenas,
+                                                         KinoBatchDev bt, int table_bits) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SearchSmem& s = *reinterpret_cast<SearchSmem*>(smem_raw);
+  const KinoParamsDev& P = *Pp;
+  const MapDev& M = *Mp;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  KinoArena ar = arenas[blockIdx.x];
+  KinoNode* nodes = ar.nodes;
+  HeapSlot* H = ar.heap;
+  HashSlot* table = ar.table;
+  const uint32_t tmask = (1u << table_bits) - 1u;
+
+  for (;;) {
+    // ---- fetch the next query --------------------------------------------------------------------
+    __syncthreads();
+    if (tid == 0) {
+      int w = atomicAdd(bt.next_query, 1);
+      s.q = (w < bt.B) ? (bt.order ? bt.order[w] : w) : -1;
+    }
+    __syncthreads();
+    const int q = s.q;
+    if (q < 0) break;
+
+    if (tid < 8) s.cnt[tid] = 0;
+    if (tid == 0) {
+      uint32_t ep = *ar.epoch + 1;
+      if (ep > EPOCH_MASK) ep = 0;  // wrapped: table must be cleared
+      s.epoch = ep;
+    }
+    __syncthreads();
+    if (s.epoch == 0) {
+      for (size_t i = tid; i <= tmask; i += KT) table[i].key = 0ull;
+      __syncthreads();
+      if (tid == 0) s.epoch = 1;
+      __syncthreads();
+    }
+    const uint32_t epoch = s.epoch;
+    if (tid == 0) {
+      *ar.epoch = epoch;
+      for (int i = 0; i < 3; i++) {
+        s.sp[i] = bt.start_pt[3 * q + i]; s.sv[i] = bt.start_vel[3 * q + i];
+        s.gp[i] = bt.end_pt[3 * q + i];   s.gv[i] = bt.end_vel[3 * q + i];
+      }
+      // start node (kino_astar.cpp:85-97)
+      double topt;
+      double h = d_heuristic(P, s.sp[0], s.sp[1], s.sp[2], s.sv[0], s.sv[1], s.sv[2], s.gp[0], s.gp[1], s.gp[2],
+                             s.gv[0], s.gv[1], s.gv[2], topt);
+      s.opt_time = (topt >= 0.0) ? topt : (double)(1 << 30);
+      KinoNode nd;
+      nd.px = s.sp[0]; nd.py = s.sp[1]; nd.pz = s.sp[2]; nd.vx = s.sv[0]; nd.vy = s.sv[1]; nd.vz = s.sv[2];
+      nd.g = 0.0; nd.parent = UAVMP_NONE; nd.heap_pos = 0; nd.input = 0; nd.closed = 0; nd.pad0 = 0; nd.pad1 = 0;
+      nodes[0] = nd;
+      HeapSlot hs; hs.f = P.lambda * h; hs.id = 0; hs.dirty = 0;
+      H[1] = hs;
+      int ix, iy, iz; bool ok;
+      pos_to_index(M, s.sp[0], s.sp[1], s.sp[2], ix, iy, iz);
+      unsigned long long k = pack_key(ix, iy, iz, ok);
+      if (!ok) atomicOr(bt.error_flag, 1);
+      uint32_t hh = hash_key(k, table_bits);
+      while ((table[hh].key & EPOCH_MASK) == epoch) hh = (hh + 1) & tmask;  // cannot happen on a fresh epoch
+      table[hh].key = (k << EPOCH_BITS) | epoch;
+      table[hh].id = 0;
+      s.heap_len = 1; s.use_num = 1; s.n_pop = 0; s.status = 0; s.hc_active = 0;
+      s.pop_hash = 0xcbf29ce484222325ull;
+      s.cnt[3] += 1; s.cnt[4] += 1; s.cnt[6] += 1;  // hash probe, insert, heuristic of the start node
+    }
+    unsigned my_occ = 0, my_cloud = 0;
+    __syncthreads();
+
+    // ================================ main loop (kino_astar.cpp:101) ===============================
+    for (;;) {
+      // ---- pop --------------------------------------------------------------------------------------
+      if (tid == 0) {
+        if (s.heap_len == 0) {
+          s.status = UAVMP_NO_PATH_FOUND;  // open list exhausted (:270-271)
+        } else {
+          HeapSlot top;
+          int len = s.heap_len;
+          heap_pop_serial(H, nodes, len, top);
+          s.heap_len = len;
+          KinoNode nd = nodes[top.id];
+          nodes[top.id].closed = 1;
+          s.cur_id = top.id; s.cur_parent = nd.parent;
+          s.cp[0] = nd.px; s.cp[1] = nd.py; s.cp[2] = nd.pz; s.cv[0] = nd.vx; s.cv[1] = nd.vy; s.cv[2] = nd.vz;
+          s.cg = nd.g;
+          int ix, iy, iz;
+          pos_to_index(M, nd.px, nd.py, nd.pz, ix, iy, iz);
+          if (nd.parent == UAVMP_NONE) { /* start node keeps its own index */ }
+          // the node's pruning index is the voxel of its (possibly mutated) position?  No: the reference never
+          // updates node->index on mutation (:256 is commented out) but the mutated position lies in the same
+          // voxel by construction (the lookup key), so recomputing it is identical.
+          unsigned long long ph = s.pop_hash;
+          ph = mix64(ph, (unsigned long long)(uint32_t)ix);
+          ph = mix64(ph, (unsigned long long)(uint32_t)iy);
+          ph = mix64(ph, (unsigned long long)(uint32_t)iz);
+          ph = mix64(ph, fpm::to_bits(nd.px));
+          ph = mix64(ph, fpm::to_bits(nd.vx));
+          ph = mix64(ph, fpm::to_bits(nd.g));
+          s.pop_hash = ph;
+          if (bt.pop_trace && s.n_pop < bt.pop_cap) {
+            int* tr = bt.pop_trace + ((size_t)q * bt.pop_cap + s.n_pop) * 3;
+            tr[0] = ix; tr[1] = iy; tr[2] = iz;
+          }
+          s.n_pop++;
+          double dx = nd.px - s.gp[0], dy = nd.py - s.gp[1], dz = nd.pz - s.gp[2];
+          s.flag = (sqrt(dot3(dx, dy, dz, dx, dy, dz)) < P.goal_tol) ? 1 : 0;
+          s.n1 = 0; s.n2 = 0;
+        }
+      }
+      for (int i = tid; i < TAB_SIZE; i += KT) s.tab[i] = 0;
+      __syncthreads();
+      if (s.status) break;
+
+      // ---- near goal: one-shot trajectory (:112-154, :416-471) ---------------------------------------
+      if (s.flag) {
+        const double td = s.opt_time;  // stale by design (§9.1 Q2)
+        if (tid < 3) {
+          double x1 = s.cp[tid], v1 = s.cv[tid], x2 = s.gp[tid], v2 = s.gv[tid];
+          double dp = x2 - x1, dv = v2 - v1;
+          s.shot[4 * tid + 0] = x1;
+          s.shot[4 * tid + 1] = v1;
+          s.shot[4 * tid + 2] = 0.5 * ((6 / (td * td)) * (dp - v1 * td) - (2 * dv) / td);
+          s.shot[4 * tid + 3] = (1.0 / 6.0) * ((-12 / (td * td * td)) * (dp - v1 * td) + (6 * dv) / (td * td));
+        }
+        __syncthreads();
+        const double segf = floor(td / P.step);
+        const long long seg = (segf < 9.0e18) ? (long long)segf : (long long)9.0e18;
+        bool blocked = false;
+        for (long long base = 0; base <= seg; base += KT) {
+          long long j = base + tid;
+          bool coll = false;
+          if (j <= seg) {
+            double t = (double)j * P.step, x, y, z;
+            shot_pos(s.shot, t, x, y, z);
+            if (!in_map(M, x, y, z)) {
+              coll = true;
+            } else {
+              int ix, iy, iz;
+              pos_to_index(M, x, y, z, ix, iy, iz);
+              my_occ++;
+              coll = (map_flags(M, ix, iy, iz) & 2u) != 0;
+            }
+          }
+          if (__syncthreads_or(coll ? 1 : 0)) { blocked = true; break; }
+        }
+        if (tid == 0) s.cnt[7] += 1;
+        if (!blocked) {
+          // ---- REACH_END: retrievePath + samplePath (:473-557) --------------------------------------
+          if (tid == 0) {
+            int n = 0;
+            uint32_t c = s.cur_id;
+            while (c != UAVMP_NONE && n < UAVMP_MAXPRIM) { s.id[n++] = c; c = nodes[c].parent; }
+            if (c != UAVMP_NONE) atomicOr(bt.error_flag, 2);
+            s.n1 = n;
+          }
+          __syncthreads();
+          const int nn = s.n1;
+          const int segk = P.K - 1;  // floor(duration / step) samples per primitive, duration == sample_tau
+          const long long shot_n = seg + 1;
+          const long long total = (long long)(nn - 1) * segk + shot_n;
+          if (total > bt.path_cap) { if (tid == 0) atomicOr(bt.error_flag, 4); }
+          const long long lim = total < bt.path_cap ? total : bt.path_cap;
+          double* out = bt.path_stage + (size_t)q * bt.path_cap * 3;
+          for (long long i = tid; i < lim; i += KT) {
+            double x, y, z;
+            if (i < (long long)(nn - 1) * segk) {
+              int sgi = (int)(i / segk), j = (int)(i % segk);
+              const KinoNode& cn = nodes[s.id[nn - 1 - sgi]];
+              int inp = nodes[s.id[nn - 2 - sgi]].input;
+              double ux = lat.ux[inp], uy = lat.uy[inp], uz = lat.uz[inp];
+              double t = P.tk[j], h = P.hk[j];
+              x = (cn.px + t * cn.vx) + h * ux;
+              y = (cn.py + t * cn.vy) + h * uy;
+              z = (cn.pz + t * cn.vz) + h * uz;
+            } else {
+              long long j = i - (long long)(nn - 1) * segk;
+              shot_pos(s.shot, (double)j * P.step, x, y, z);
+            }
+            out[3 * i] = x; out[3 * i + 1] = y; out[3 * i + 2] = z;
+          }
+          if (tid == 0) { s.status = UAVMP_REACH_END; bt.n_path[q] = (int)lim; }
+        } else if (s.cur_parent == UAVMP_NONE) {
+          if (tid == 0) s.status = UAVMP_NO_PATH_FOUND;  // :148-152
+        }
+        __syncthreads();
+        if (s.status) break;
+      }
+
+      // ---- A. evaluate the motion primitives (:158-216) ---------------------------------------------
+      for (int p = tid; p < P.nprim; p += KT) {
+        const double ux = lat.ux[p], uy = lat.uy[p], uz = lat.uz[p];
+        bool ok = true;
+        for (int i = 0; i < P.K && ok; i++) {
+          const double t = P.tk[i], h = P.hk[i];
+          const double x = (s.cp[0] + t * s.cv[0]) + h * ux;
+          const double y = (s.cp[1] + t * s.cv[1]) + h * uy;
+          const double z = (s.cp[2] + t * s.cv[2]) + h * uz;
+          if (!in_map(M, x, y, z)) { ok = false; break; }
+          int ix, iy, iz;
+          pos_to_index(M, x, y, z, ix, iy, iz);
+          const unsigned fl = map_flags(M, ix, iy, iz);
+          my_occ++;
+          if (P.ctype == 1 && (fl & 1u)) { ok = false; break; }
+          if ((fl & 4u) && !ellipsoid_free(M, P, lat.Einv + 9 * p, x, y, z, my_cloud)) { ok = false; break; }
+          const double vx = s.cv[0] + t * ux, vy = s.cv[1] + t * uy, vz = s.cv[2] + t * uz;
+          if (vx < -P.vmax || vx > P.vmax || vy < -P.vmax || vy > P.vmax || vz < -P.vmax || vz > P.vmax) ok = false;
+        }
+        uint8_t st = ST_REJECT;
+        if (ok) {
+          double xe[6];
+          end_state(s, P, ux, uy, uz, xe);
+          int ix, iy, iz;
+          pos_to_index(M, xe[0], xe[1], xe[2], ix, iy, iz);
+          bool kok;
+          s.key[p] = pack_key(ix, iy, iz, kok);
+          if (!kok) atomicOr(bt.error_flag, 1);
+          st = ST_FEASIBLE;
+          s.list1[atomicAdd(&s.n1, 1)] = (uint16_t)p;
+        }
+        s.state[p] = st;
+      }
+      __syncthreads();
+      const int n1 = s.n1;
+
+      // ---- B1. group identical voxel keys inside this expansion --------------------------------------
+      for (int e = tid; e < n1; e += KT) {
+        const int p = s.list1[e];
+        const unsigned long long k = s.key[p];
+        uint32_t h = hash_key(k, 11);
+        for (;;) {
+          uint32_t cur = s.tab[h];
+          if (cur == 0) {
+            cur = atomicCAS(&s.tab[h], 0u, (uint32_t)p + 1u);
+            if (cur == 0) break;
+          }
+          if (s.key[cur - 1] == k) { atomicMin(&s.tab[h], (uint32_t)p + 1u); break; }
+          h = (h + 1) & (TAB_SIZE - 1);
+        }
+        s.id[p] = h;
+      }
+      __syncthreads();
+      // ---- B2. leaders probe the global table (:220-225) --------------------------------------------
+      for (int e = tid; e < n1; e += KT) {
+        const int p = s.list1[e];
+        const int leader = (int)s.tab[s.id[p]] - 1;
+        if (leader != p) { s.id[p] = (uint32_t)leader; s.state[p] = ST_FOLLOW_NOCAND; continue; }
+        const unsigned long long k = s.key[p];
+        const double gp = s.cg + lat.ginc[p];
+        uint32_t h = hash_key(k, table_bits);
+        uint8_t st;
+        for (;;) {
+          HashSlot hs = table[h];
+          if ((uint32_t)(hs.key & EPOCH_MASK) != epoch) { st = ST_NEW; s.gcur[p] = gp; break; }
+          if ((hs.key >> EPOCH_BITS) == k) {
+            const KinoNode& nd = nodes[hs.id];
+            if (nd.closed) {
+              st = ST_CLOSED;
+            } else {
+              double gold = nd.g;
+              s.gcur[p] = gold;
+              s.id[p] = hs.id;
+              st = (gp < gold) ? ST_OPEN_CAND : ST_OPEN_NOCAND;
+            }
+            break;
+          }
+          h = (h + 1) & tmask;
+        }
+        s.state[p] = st;
+      }
+      __syncthreads();
+      for (int e = tid; e < n1; e += KT) {
+        const int p = s.list1[e];
+        uint8_t st = s.state[p];
+        if (st == ST_FOLLOW_NOCAND) {
+          const int leader = (int)s.id[p];
+          const uint8_t ls = s.state[leader];
+          if (ls == ST_CLOSED) {
+            st = ST_CLOSED;
+          } else {
+            const double gp = s.cg + lat.ginc[p];
+            if (gp < s.gcur[leader]) st = ST_FOLLOW_CAND;
+          }
+          s.state[p] = st;
+        }
+        if (st == ST_NEW || st == ST_OPEN_CAND || st == ST_FOLLOW_CAND) s.list2[atomicAdd(&s.n2, 1)] = (uint16_t)p;
+      }
+      __syncthreads();
+      const int n2 = s.n2;
+      // ---- B3. heuristic for every candidate (:232,:259) ----------------------------------------------
+      for (int e = tid; e < n2; e += KT) {
+        const int p = s.list2[e];
+        double xe[6];
+        end_state(s, P, lat.ux[p], lat.uy[p], lat.uz[p], xe);
+        double topt;
+        const double h = d_heuristic(P, xe[0], xe[1], xe[2], xe[3], xe[4], xe[5], s.gp[0], s.gp[1], s.gp[2], s.gv[0],
+                                     s.gv[1], s.gv[2], topt);
+        const double gp = s.cg + lat.ginc[p];
+        s.f[p] = gp + P.lambda * h;
+        s.topt[p] = topt;
+      }
+      // ---- C. ordered id assignment for new nodes (== use_node_num_++ in lattice order) ----------------
+      {
+        const int p0 = tid * 3;
+        int c = 0;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          const int p = p0 + j;
+          if (p < P.nprim && s.state[p] == ST_NEW) c++;
+        }
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          int v = __shfl_up_sync(FULL, incl, o);
+          if (lane >= o) incl += v;
+        }
+        if (lane == 31) s.wsum[warp] = incl;
+        __syncthreads();
+        int woff = 0;
+        for (int w = 0; w < warp; w++) woff += s.wsum[w];
+        int excl = woff + incl - c;
+        const int base = s.use_num;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          const int p = p0 + j;
+          if (p < P.nprim && s.state[p] == ST_NEW) s.id[p] = (uint32_t)(base + excl++);
+        }
+        if (tid == KT - 1) s.n_new = woff + incl;
+      }
+      __syncthreads();
+      const int n_new = s.n_new;
+      if (s.use_num + n_new >= P.allocated) {
+        // pool exhausted while committing this expansion (:243-247): the reference returns on the spot
+        if (tid == 0) {
+          s.cnt[3] += n1;  // probes up to the abort are not separable; count the expansion's
+          s.use_num = P.allocated;
+          s.status = UAVMP_NO_PATH_FOUND;
+        }
+        __syncthreads();
+        break;
+      }
+      // ---- C2. node records + hash slots of the new nodes, in parallel -----------------------------------
+      for (int e = tid; e < n2; e += KT) {
+        const int p = s.list2[e];
+        if (s.state[p] != ST_NEW) continue;
+        double xe[6];
+        end_state(s, P, lat.ux[p], lat.uy[p], lat.uz[p], xe);
+        const uint32_t nid = s.id[p];
+        KinoNode nd;
+        nd.px = xe[0]; nd.py = xe[1]; nd.pz = xe[2]; nd.vx = xe[3]; nd.vy = xe[4]; nd.vz = xe[5];
+        nd.g = s.cg + lat.ginc[p];
+        nd.parent = s.cur_id; nd.heap_pos = 0; nd.input = (uint16_t)p; nd.closed = 0; nd.pad0 = 0; nd.pad1 = 0;
+        nodes[nid] = nd;
+        const unsigned long long k = s.key[p];
+        const unsigned long long want = (k << EPOCH_BITS) | epoch;
+        uint32_t h = hash_key(k, table_bits);
+        for (;;) {
+          unsigned long long cur = table[h].key;
+          if ((uint32_t)(cur & EPOCH_MASK) != epoch) {
+            unsigned long long old = atomicCAS(&table[h].key, cur, want);
+            if (old == cur) { table[h].id = nid; break; }
+            continue;  // somebody else claimed it: re-read the same slot
+          }
+          h = (h + 1) & tmask;
+        }
+      }
+      __syncthreads();
+
+      // ---- D. ordered commit: heap pushes and in-place mutations (:225-266) ----------------------------
+      if (warp == 0) {
+        int pushed = 0, len = s.heap_len;
+        double opt_time = s.opt_time;
+        int n_upd = 0;
+        for (int pb = 0; pb < P.nprim; pb += 32) {
+          const int p = pb + lane;
+          const uint8_t st = (p < P.nprim) ? s.state[p] : ST_REJECT;
+          unsigned evm = __ballot_sync(FULL, st == ST_NEW || st == ST_OPEN_CAND || st == ST_FOLLOW_CAND);
+          while (evm) {
+            const int l = __ffs(evm) - 1;
+            evm &= evm - 1;
+            const int pe = pb + l;
+            const uint8_t ste = s.state[pe];
+            if (ste == ST_NEW) {
+              if ((pushed % PUSH_BATCH) == 0) {
+                closure_flush(s, H, lane);
+                closure_load(s, H, len, min(PUSH_BATCH, n_new - pushed), lane);
+              }
+              closure_push(s, nodes, len + 1, s.f[pe], s.id[pe], lane);
+              len++;
+              pushed++;
+              if (s.topt[pe] >= 0.0) opt_time = s.topt[pe];
+            } else {
+              int leader = pe;
+              uint32_t nid;
+              if (ste == ST_FOLLOW_CAND) { leader = (int)s.id[pe]; nid = s.id[leader]; }
+              else nid = s.id[pe];
+              const double gp = s.cg + lat.ginc[pe];
+              if (gp < s.gcur[leader]) {  // tmp_g_cost < old_node->g_cost (:254)
+                __syncwarp();
+                if (lane == 0) s.gcur[leader] = gp;
+                double xe[6];
+                end_state(s, P, lat.ux[pe], lat.uy[pe], lat.uz[pe], xe);
+                KinoNode* nd = nodes + nid;
+                if (lane < 6) (&nd->px)[lane] = xe[lane];
+                if (lane == 6) nd->g = gp;
+                if (lane == 7) nd->parent = s.cur_id;
+                if (lane == 8) nd->input = (uint16_t)pe;
+                heap_set_key(s, H, nodes, nid, s.f[pe], lane);
+                if (s.topt[pe] >= 0.0) opt_time = s.topt[pe];
+                n_upd++;
+              }
+            }
+          }
+        }
+        closure_flush(s, H, lane);
+        if (lane == 0) {
+          s.heap_len = len;
+          s.use_num += n_new;
+          s.opt_time = opt_time;
+          s.cnt[3] += n1; s.cnt[4] += n_new; s.cnt[5] += n_upd; s.cnt[6] += n_new + n_upd;
+        }
+      }
+      __syncthreads();
+    }  // main loop
+
+    // ---- query epilogue ------------------------------------------------------------------------------
+    atomicAdd(&s.cnt[1], (unsigned long long)my_occ);
+    atomicAdd(&s.cnt[2], (unsigned long long)my_cloud);
+    __syncthreads();
+    if (tid == 0) {
+      bt.status[q] = s.status;
+      bt.use_node_num[q] = s.use_num;
+      bt.n_pop[q] = s.n_pop;
+      bt.pop_hash[q] = s.pop_hash;
+      if (s.status != UAVMP_REACH_END) bt.n_path[q] = 0;
+      s.cnt[0] = (unsigned long long)s.n_pop;
+    }
+    __syncthreads();
+    if (tid < 8) atomicAdd(&bt.counters[tid], s.cnt[tid]);
+  }
+}
+
+// ---- map preprocessing -------------------------------------------------------------------------------
+__global__ void k_flags_base(const int8_t* occ, uint8_t* flags, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { int8_t o = occ[i]; flags[i] = (uint8_t)((o == 1 ? 1 : 0) | (o != 0 ? 2 : 0)); }
+}
+__global__ void k_mark_points(const float* cloud, int n, MapDev M, int margin, uint8_t* mark) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double x = (double)cloud[3 * i], y = (double)cloud[3 * i + 1], z = (double)cloud[3 * i + 2];
+  int ix = (int)floor((x - M.ox) * M.inv_res), iy = (int)floor((y - M.oy) * M.inv_res),
+      iz = (int)floor((z - M.oz) * M.inv_res);
+  if (ix < -margin || iy < -margin || iz < -margin || ix >= M.nx + margin || iy >= M.ny + margin ||
+      iz >= M.nz + margin)
+    return;
+  ix = min(max(ix, 0), M.nx - 1); iy = min(max(iy, 0), M.ny - 1); iz = min(max(iz, 0), M.nz - 1);
+  mark[((size_t)ix * M.ny + iy) * M.nz + iz] = 1;
+}
+// out = max over [-r, r] along one axis (stride / extent given)
+__global__ void k_dilate(const uint8_t* in, uint8_t* out, int nx, int ny, int nz, int axis, int r) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t n = (size_t)nx * ny * nz;
+  if (i >= n) return;
+  int z = (int)(i % nz), y = (int)((i / nz) % ny), x = (int)(i / ((size_t)nz * ny));
+  int c = axis == 0 ? x : (axis == 1 ? y : z);
+  int ext = axis == 0 ? nx : (axis == 1 ? ny : nz);
+  size_t stride = axis == 0 ? (size_t)ny * nz : (axis == 1 ? (size_t)nz : 1);
+  uint8_t v = 0;
+  for (int d = -r; d <= r && !v; d++) {
+    int cc = c + d;
+    if (cc >= 0 && cc < ext) v |= in[i + (long long)d * (long long)stride];
+  }
+  out[i] = v;
+}
+__global__ void k_or_near(uint8_t* flags, const uint8_t* near, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flags[i] = (uint8_t)((flags[i] & 3u) | (near[i] ? 4u : 0u));
+}
+__global__ void k_cell_ids(const float* cloud, int n, MapDev M, int* cell, int* idx) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double x = (double)cloud[3 * i], y = (double)cloud[3 * i + 1], z = (double)cloud[3 * i + 2];
+  int cx = (int)floor((x - M.cox) * M.inv_cell), cy = (int)floor((y - M.coy) * M.inv_cell),
+      cz = (int)floor((z - M.coz) * M.inv_cell);
+  int c;
+  if (cx < 0 || cy < 0 || cz < 0 || cx >= M.cnx || cy >= M.cny || cz >= M.cnz) c = M.cnx * M.cny * M.cnz;  // dropped
+  else c = (cx * M.cny + cy) * M.cnz + cz;
+  cell[i] = c;
+  idx[i] = i;
+}
+__global__ void k_gather_pts(const float* cloud, const int* idx_sorted, int n, float4* pts) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int j = idx_sorted[i];
+  pts[i] = make_float4(cloud[3 * j], cloud[3 * j + 1], cloud[3 * j + 2], 0.f);
+}
+__global__ void k_cell_start(const int* cell_sorted, int n, int ncell, int* cell_start) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > ncell) return;
+  int lo = 0, hi = n;  // lower_bound(cell_sorted, c)
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (cell_sorted[mid] < c) lo = mid + 1; else hi = mid;
+  }
+  cell_start[c] = lo;
+}
+
+__global__ void k_pack_paths(const double* stage, const int* n_path, const long long* offsets, int path_cap,
+                             double* out) {
+  int q = blockIdx.x;
+  int n = n_path[q];
+  const double* src = stage + (size_t)q * path_cap * 3;
+  double* dst = out + offsets[q] * 3;
+  for (int i = threadIdx.x; i < 3 * n; i += blockDim.x) dst[i] = src[i];
+}
+__global__ void k_offsets(const int* n_path, int B, long long* offsets) {
+  // single-block exclusive scan (B <= a few 100k): chunked serial-per-thread + block scan
+  __shared__ long long part[1024];
+  int t = threadIdx.x, T = blockDim.x;
+  int per = (B + T - 1) / T;
+  int b0 = t * per, b1 = min(B, b0 + per);
+  long long sum = 0;
+  for (int i = b0; i < b1; i++) sum += n_path[i];
+  part[t] = sum;
+  __syncthreads();
+  if (t == 0) {
+    long long acc = 0;
+    for (int i = 0; i < T; i++) { long long v = part[i]; part[i] = acc; acc += v; }
+    offsets[B] = acc;
+  }
+  __syncthreads();
+  long long acc = part[t];
+  for (int i = b0; i < b1; i++) { offsets[i] = acc; acc += n_path[i]; }
+}
+__global__ void k_dist_keys(const double* sp, const double* ep, int B, float* key, int* idx) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  double dx = sp[3 * i] - ep[3 * i], dy = sp[3 * i + 1] - ep[3 * i + 1], dz = sp[3 * i + 2] - ep[3 * i + 2];
+  key[i] = (float)sqrt(dx * dx + dy * dy + dz * dz);
+  idx[i] = i;
+}
+
+__global__ void k_fpmath(int op, int npow, const double* x, double* y, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v = x[i], r = 0;
+  switch (op) {
+    case 0: r = fpm::cbrt(v); break;
+    case 1: r = fpm::acos(v); break;
+    case 2: r = fpm::cos(v); break;
+    case 3: r = fpm::powi(v, npow); break;
+  }
+  y[i] = r;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+int uavmp_fail(uavmp_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  return code;
+}
+
+// Host f64 below mirrors the reference's expressions; this translation unit's host code is compiled with
+// -ffp-contract=off so the tables are bit-identical to what the oracle computes.
+int kino_upload_params(uavmp_ctx* ctx) {
+  const uavmp_kino_params& kp = ctx->kp;
+  if (kp.allocated_node_num < 2) return uavmp_fail(ctx, UAVMP_EINVAL, "allocated_node_num must be >= 2");
+  if (kp.collision_check_type != 1 && kp.collision_check_type != 2)
+    return uavmp_fail(ctx, UAVMP_EINVAL, "collision_check_type must be 1 or 2");
+  if (!(kp.time_step_size > 0) || !(kp.sample_tau > 0) || !(kp.acc_resolution > 0) || !(kp.max_accelration > 0))
+    return uavmp_fail(ctx, UAVMP_EINVAL, "time_step_size, sample_tau, acc_resolution, max_accelration must be > 0");
+  KinoParamsDev P;
+  memset(&P, 0, sizeof(P));
+  P.allocated = kp.allocated_node_num;
+  P.ctype = kp.collision_check_type;
+  int segment_num = (int)std::floor(kp.sample_tau / kp.time_step_size);  // kino_astar.cpp:169
+  if (segment_num + 1 > UAVMP_MAXK) return uavmp_fail(ctx, UAVMP_EINVAL, "too many checkpoints per primitive");
+  P.K = segment_num + 1;
+  for (int i = 0; i <= segment_num; i++) {
+    double t = i * kp.time_step_size;
+    P.tk[i] = t;
+    P.hk[i] = 0.5 * t * t;
+  }
+  P.rou = kp.rou_time; P.lambda = kp.lambda_heu; P.goal_tol = kp.goal_tolerance; P.step = kp.time_step_size;
+  P.vmax = kp.max_velocity; P.tau = kp.sample_tau; P.htau = 0.5 * kp.sample_tau * kp.sample_tau;
+  P.tie = 1.0 + (3 / 1e4);  // kino_astar.cpp:69
+  P.robot_r = kp.robot_r; P.robot_h = kp.robot_h;
+  P.box_r = std::max(kp.robot_r, kp.robot_h) * 1.001 + 1e-6;
+  float radius = (float)(kp.robot_r + 1e-1);
+  P.kd_r2 = radius * radius;
+
+  // acceleration lattice by float accumulation, ax outer / az inner (kino_astar.cpp:158-160)
+  std::vector<double> ux, uy, uz;
+  const double inv_acc_res = 1.0 / kp.acc_resolution;
+  const double amax = kp.max_accelration;
+  for (double ax = -amax; ax <= amax + 1e-3; ax += inv_acc_res * amax)
+    for (double ay = -amax; ay <= amax + 1e-3; ay += inv_acc_res * amax)
+      for (double az = -amax; az <= amax + 1e-3; az += inv_acc_res * amax) {
+        ux.push_back(ax); uy.push_back(ay); uz.push_back(az);
+        if (ux.size() > UAVMP_MAXPRIM) return uavmp_fail(ctx, UAVMP_EINVAL, "more than %d motion primitives", UAVMP_MAXPRIM);
+      }
+  const int n = (int)ux.size();
+  P.nprim = n;
+  std::vector<double> host((size_t)n * 13);
+  double* hux = host.data(); double* huy = hux + n; double* huz = huy + n; double* hg = huz + n; double* hE = hg + n;
+  for (int p = 0; p < n; p++) {
+    hux[p] = ux[p]; huy[p] = uy[p]; huz[p] = uz[p];
+    double usq = (ux[p] * ux[p] + uy[p] * uy[p]) + uz[p] * uz[p];
+    hg[p] = (usq + kp.rou_time) * kp.sample_tau;  // (ut.dot(ut) + rou_) * sample_tau_ (:231)
+    // attitude from thrust direction and E^-1 (kino_astar.cpp:724-752)
+    double a3[3] = {ux[p] + 9.81 * 0.0, uy[p] + 9.81 * 0.0, uz[p] + 9.81 * 1.0};
+    auto nrm = [](const double* v, double* o) {
+      double n2 = std::sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
+      o[0] = v[0] / n2; o[1] = v[1] / n2; o[2] = v[2] / n2;
+    };
+    auto crs = [](const double* a, const double* b, double* o) {
+      o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+    };
+    double b3[3], b2[3], b1[3], t[3], c1[3] = {std::cos(0.0), std::sin(0.0), 0.0};
+    nrm(a3, b3);
+    crs(b3, c1, t); nrm(t, b2);
+    crs(b2, b3, t); nrm(t, b1);
+    double Rot[3][3] = {{b1[0], b2[0], b3[0]}, {b1[1], b2[1], b3[1]}, {b1[2], b2[2], b3[2]}};
+    double Pd[3] = {kp.robot_r, kp.robot_r, kp.robot_h};
+    double RP[3][3], E[3][3];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) RP[i][j] = Rot[i][j] * Pd[j];
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) E[i][j] = (RP[i][0] * Rot[j][0] + RP[i][1] * Rot[j][1]) + RP[i][2] * Rot[j][2];
+    auto cof = [&](int i, int j) {
+      int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      return E[i1][j1] * E[i2][j2] - E[i1][j2] * E[i2][j1];
+    };
+    double cc0 = cof(0, 0), cc1 = cof(1, 0), cc2 = cof(2, 0);
+    double det = (cc0 * E[0][0] + cc1 * E[1][0]) + cc2 * E[2][0];
+    double invdet = 1.0 / det;
+    double* Ei = hE + 9 * p;
+    Ei[0] = cc0 * invdet; Ei[1] = cc1 * invdet; Ei[2] = cc2 * invdet;
+    Ei[3] = cof(0, 1) * invdet; Ei[4] = cof(1, 1) * invdet; Ei[5] = cof(2, 1) * invdet;
+    Ei[6] = cof(0, 2) * invdet; Ei[7] = cof(1, 2) * invdet; Ei[8] = cof(2, 2) * invdet;
+  }
+  if (ctx->d_lattice) cudaFree(ctx->d_lattice);
+  UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_lattice, host.size() * sizeof(double)));
+  UAVMP_CUDA(ctx, cudaMemcpyAsync(ctx->d_lattice, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (!ctx->d_kparams) UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_kparams, sizeof(KinoParamsDev)));
+  UAVMP_CUDA(ctx, cudaMemcpyAsync(ctx->d_kparams, &P, sizeof(P), cudaMemcpyHostToDevice, ctx->stream));
+  UAVMP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->nprim = n;
+  ctx->params_dirty = false;
+  ctx->flags_dirty = true;  // the "cloud nearby" dilation radius depends on robot_r / robot_h
+  return UAVMP_OK;
+}
+
+static inline unsigned nblk(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+int kino_build_map(uavmp_ctx* ctx) {
+  // derived device structures: flag grid (+ dilated "cloud nearby" bit) and the cell list over the cloud
+  const size_t nvox = (size_t)ctx->nx * ctx->ny * ctx->nz;
+  MapDev& M = ctx->map_host;
+  M.nx = ctx->nx; M.ny = ctx->ny; M.nz = ctx->nz;
+  M.ox = ctx->origin[0]; M.oy = ctx->origin[1]; M.oz = ctx->origin[2];
+  // grid_map.cpp:72-73 and grid_map.h:372-379
+  M.lox = ctx->origin[0] + 1e-4; M.loy = ctx->origin[1] + 1e-4; M.loz = ctx->origin[2] + 1e-4;
+  M.hix = (ctx->origin[0] + ctx->map_size[0]) - 1e-4;
+  M.hiy = (ctx->origin[1] + ctx->map_size[1]) - 1e-4;
+  M.hiz = (ctx->origin[2] + ctx->map_size[2]) - 1e-4;
+  M.inv_res = 1.0 / ctx->resolution;
+  const double box_r = std::max(ctx->kp.robot_r, ctx->kp.robot_h) * 1.001 + 1e-6;
+  const double cell = std::max(5.0 * ctx->resolution, 0.25);
+  const double margin = box_r + cell;
+  M.cox = ctx->origin[0] - margin; M.coy = ctx->origin[1] - margin; M.coz = ctx->origin[2] - margin;
+  M.inv_cell = 1.0 / cell;
+  M.cnx = (int)std::ceil((ctx->map_size[0] + 2 * margin) / cell) + 1;
+  M.cny = (int)std::ceil((ctx->map_size[1] + 2 * margin) / cell) + 1;
+  M.cnz = (int)std::ceil((ctx->map_size[2] + 2 * margin) / cell) + 1;
+  M.n_cloud = ctx->n_cloud;
+  const int ncell = M.cnx * M.cny * M.cnz;
+
+  if (!ctx->d_flags) UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_flags, nvox));
+  if (!ctx->d_tmp) UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_tmp, 2 * nvox));
+  uint8_t* t0 = ctx->d_tmp; uint8_t* t1 = ctx->d_tmp + nvox;
+  cudaStream_t st = ctx->stream;
+  k_flags_base<<<nblk(nvox, 256), 256, 0, st>>>(ctx->d_occ, ctx->d_flags, nvox);
+  UAVMP_CUDA(ctx, cudaMemsetAsync(t0, 0, nvox, st));
+  const int dil = (int)std::floor(box_r * M.inv_res) + 2;
+  if (ctx->n_cloud > 0) {
+    k_mark_points<<<nblk(ctx->n_cloud, 256), 256, 0, st>>>(ctx->d_cloud, ctx->n_cloud, M, dil, t0);
+    k_dilate<<<nblk(nvox, 256), 256, 0, st>>>(t0, t1, M.nx, M.ny, M.nz, 2, dil);
+    k_dilate<<<nblk(nvox, 256), 256, 0, st>>>(t1, t0, M.nx, M.ny, M.nz, 1, dil);
+    k_dilate<<<nblk(nvox, 256), 256, 0, st>>>(t0, t1, M.nx, M.ny, M.nz, 0, dil);
+    k_or_near<<<nblk(nvox, 256), 256, 0, st>>>(ctx->d_flags, t1, nvox);
+  }
+  // cell list
+  if (ctx->d_cell_start) cudaFree(ctx->d_cell_start);
+  if (ctx->d_pts) cudaFree(ctx->d_pts);
+  ctx->d_cell_start = nullptr; ctx->d_pts = nullptr;
+  UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_cell_start, (size_t)(ncell + 2) * sizeof(int)));
+  const int n = ctx->n_cloud;
+  UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_pts, (size_t)std::max(n, 1) * sizeof(float4)));
+  if (n > 0) {
+    int *ck, *ci, *cks, *cis;
+    UAVMP_CUDA(ctx, cudaMalloc(&ck, (size_t)4 * n * sizeof(int)));
+    ci = ck + n; cks = ci + n; cis = cks + n;
+    k_cell_ids<<<nblk(n, 256), 256, 0, st>>>(ctx->d_cloud, n, M, ck, ci);
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, ck, cks, ci, cis, n, 0, 32, st);
+    void* tmp;
+    UAVMP_CUDA(ctx, cudaMalloc(&tmp, tb));
+    cub::DeviceRadixSort::SortPairs(tmp, tb, ck, cks, ci, cis, n, 0, 32, st);
+    k_gather_pts<<<nblk(n, 256), 256, 0, st>>>(ctx->d_cloud, cis, n, ctx->d_pts);
+    k_cell_start<<<nblk(ncell + 1, 256), 256, 0, st>>>(cks, n, ncell, ctx->d_cell_start);
+    UAVMP_CUDA(ctx, cudaStreamSynchronize(st));
+    cudaFree(tmp);
+    cudaFree(ck);
+  } else {
+    UAVMP_CUDA(ctx, cudaMemsetAsync(ctx->d_cell_start, 0, (size_t)(ncell + 2) * sizeof(int), st));
+  }
+  M.flags = ctx->d_flags;
+  M.cell_start = ctx->d_cell_start;
+  M.pts = ctx->d_pts;
+  if (!ctx->d_map) UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_map, sizeof(MapDev)));
+  UAVMP_CUDA(ctx, cudaMemcpyAsync(ctx->d_map, &M, sizeof(M), cudaMemcpyHostToDevice, st));
+  UAVMP_CUDA(ctx, cudaStreamSynchronize(st));
+  UAVMP_CUDA(ctx, cudaGetLastError());
+  ctx->flags_dirty = false;
+  return UAVMP_OK;
+}
+
+static int kino_ctas_per_sm() {
+  int n = 0;
+  cudaFuncSetAttribute(kino_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SearchSmem));
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kino_search_kernel, KT, sizeof(SearchSmem));
+  return n;
+}
+
+int kino_ensure_arenas(uavmp_ctx* ctx) {
+  const int nodes = ctx->kp.allocated_node_num;
+  int per_sm = kino_ctas_per_sm();
+  if (per_sm < 1) return uavmp_fail(ctx, UAVMP_ECUDA, "search kernel does not fit on an SM");
+  int want = ctx->sm_count * per_sm;
+  int bits = 1;
+  while ((1 << bits) < 2 * nodes) bits++;
+  if (bits < 12) bits = 12;
+  const int tsize = 1 << bits;
+  if (ctx->d_arenas && ctx->n_arenas == want && ctx->arena_nodes == nodes && ctx->table_size == tsize) return UAVMP_OK;
+  if (ctx->d_arena_mem) { cudaFree(ctx->d_arena_mem); ctx->d_arena_mem = nullptr; }
+  if (ctx->d_arenas) { cudaFree(ctx->d_arenas); ctx->d_arenas = nullptr; }
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t sz_nodes = up((size_t)nodes * sizeof(KinoNode));
+  const size_t sz_heap = up((size_t)(nodes + 4) * sizeof(HeapSlot));
+  const size_t sz_tab = up((size_t)tsize * sizeof(HashSlot));
+  const size_t sz_ep = 256;
+  const size_t per = sz_nodes + sz_heap + sz_tab + sz_ep;
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  while (want > ctx->sm_count && per * (size_t)want > free_b / 2) want -= ctx->sm_count;
+  if (per * (size_t)want > free_b) return uavmp_fail(ctx, UAVMP_ENOMEM, "not enough device memory for search arenas");
+  UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_arena_mem, per * (size_t)want));
+  std::vector<KinoArena> ha(want);
+  char* base = (char*)ctx->d_arena_mem;
+  for (int i = 0; i < want; i++) {
+    char* b = base + per * (size_t)i;
+    ha[i].nodes = (KinoNode*)b;
+    ha[i].heap = (HeapSlot*)(b + sz_nodes);
+    ha[i].table = (HashSlot*)(b + sz_nodes + sz_heap);
+    ha[i].epoch = (uint32_t*)(b + sz_nodes + sz_heap + sz_tab);
+    // hash tables and epoch words start at zero (epoch 0 == never used)
+    UAVMP_CUDA(ctx, cudaMemsetAsync(b + sz_nodes + sz_heap, 0, sz_tab + sz_ep, ctx->stream));
+  }
+  UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_arenas, sizeof(KinoArena) * want));
+  UAVMP_CUDA(ctx, cudaMemcpyAsync(ctx->d_arenas, ha.data(), sizeof(KinoArena) * want, cudaMemcpyHostToDevice, ctx->stream));
+  UAVMP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->n_arenas = want; ctx->arena_nodes = nodes; ctx->table_size = tsize;
+  return UAVMP_OK;
+}
+
+int kino_ensure_batch(uavmp_ctx* ctx, int B) {
+  if (B <= ctx->batch_cap) return UAVMP_OK;
+  auto fr = [](void* p) { if (p) cudaFree(p); };
+  fr(ctx->d_q); fr(ctx->d_order); fr(ctx->d_status); fr(ctx->d_use); fr(ctx->d_npop); fr(ctx->d_hash);
+  fr(ctx->d_npath); fr(ctx->d_path_stage); fr(ctx->d_trace); fr(ctx->d_offsets);
+  ctx->d_trace = nullptr;
+  int cap = B;
+  UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_q, (size_t)cap * 12 * sizeof(double)));
+  UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_order, (size_t)cap * 4 * sizeof(int)));  // idx | idx_sorted | key | key_sorted
+  UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_status, (size_t)cap * sizeof(int)));
+  UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_use, (size_t)cap * sizeof(int)));
+  UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_npop, (size_t)cap * sizeof(int)));
+  UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_hash, (size_t)cap * sizeof(unsigned long long)));
+  UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_npath, (size_t)cap * sizeof(int)));
+  UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_path_stage, (size_t)cap * ctx->path_cap * 3 * sizeof(double)));
+  UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_offsets, (size_t)(cap + 1) * sizeof(long long)));
+  if (ctx->pop_cap > 0) UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_trace, (size_t)cap * ctx->pop_cap * 3 * sizeof(int)));
+  if (!ctx->d_misc) UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_misc, 64));
+  if (!ctx->d_counters) UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)));
+  ctx->batch_cap = cap;
+  return UAVMP_OK;
+}
+
+int kino_launch_search(uavmp_ctx* ctx, int B, const double* d_sp, const double* d_sv, const double* d_ep,
+                       const double* d_ev, bool sort_order) {
+  cudaStream_t st = ctx->stream;
+  int* order = nullptr;
+  if (sort_order && B > 1) {
+    int* idx = ctx->d_order; int* idx_s = idx + B; float* key = (float*)(idx_s + B); float* key_s = key + B;
+    k_dist_keys<<<nblk(B, 256), 256, 0, st>>>(d_sp, d_ep, B, key, idx);
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, key, key_s, idx, idx_s, B, 0, 32, st);
+    if (tb > ctx->cub_tmp_bytes) {
+      if (ctx->d_cub_tmp) cudaFree(ctx->d_cub_tmp);
+      UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_cub_tmp, tb));
+      ctx->cub_tmp_bytes = tb;
+    }
+    cub::DeviceRadixSort::SortPairsDescending(ctx->d_cub_tmp, tb, key, key_s, idx, idx_s, B, 0, 32, st);
+    order = idx_s;
+  }
+  UAVMP_CUDA(ctx, cudaMemsetAsync(ctx->d_misc, 0, 64, st));
+  UAVMP_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), st));
+  KinoBatchDev bt;
+  bt.B = B; bt.start_pt = d_sp; bt.start_vel = d_sv; bt.end_pt = d_ep; bt.end_vel = d_ev; bt.order = order;
+  bt.status = ctx->d_status; bt.use_node_num = ctx->d_use; bt.n_pop = ctx->d_npop; bt.pop_hash = ctx->d_hash;
+  bt.n_path = ctx->d_npath; bt.path_stage = ctx->d_path_stage; bt.path_cap = ctx->path_cap;
+  bt.pop_trace = ctx->d_trace; bt.pop_cap = ctx->pop_cap;
+  bt.error_flag = ctx->d_misc; bt.next_query = ctx->d_misc + 1; bt.counters = ctx->d_counters;
+  LatticeDev lat;
+  const int n = ctx->nprim;
+  lat.ux = ctx->d_lattice; lat.uy = lat.ux + n; lat.uz = lat.uy + n; lat.ginc = lat.uz + n; lat.Einv = lat.ginc + n;
+  int bits = 0;
+  while ((1 << bits) < ctx->table_size) bits++;
+  const int grid = std::min(ctx->n_arenas, B);
+  cudaFuncSetAttribute(kino_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SearchSmem));
+  kino_search_kernel<<<grid, KT, sizeof(SearchSmem), st>>>(ctx->d_kparams, lat, ctx->d_map, ctx->d_arenas, bt, bits);
+  UAVMP_CUDA(ctx, cudaGetLastError());
+  ctx->tm.search_launches = 1;
+  return UAVMP_OK;
+}
+
+int kino_pack_paths(uavmp_ctx* ctx, int B) {
+  cudaStream_t st = ctx->stream;
+  k_offsets<<<1, 1024, 0, st>>>(ctx->d_npath, B, ctx->d_offsets);
+  long long total = 0;
+  UAVMP_CUDA(ctx, cudaMemcpyAsync(&total, ctx->d_offsets + B, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  UAVMP_CUDA(ctx, cudaStreamSynchronize(st));
+  if (total > ctx->path_packed_cap) {
+    if (ctx->d_path_packed) cudaFree(ctx->d_path_packed);
+    ctx->d_path_packed = nullptr;
+    long long cap = std::max(total, (long long)1024);
+    UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_path_packed, (size_t)cap * 3 * sizeof(double)));
+    ctx->path_packed_cap = cap;
+  }
+  if (total > 0) k_pack_paths<<<B, 128, 0, st>>>(ctx->d_path_stage, ctx->d_npath, ctx->d_offsets, ctx->path_cap, ctx->d_path_packed);
+  UAVMP_CUDA(ctx, cudaGetLastError());
+  ctx->last_total_path = total;
+  ctx->tm.aux_launches = 2;
+  return UAVMP_OK;
+}
+
+int kino_fpmath_eval(uavmp_ctx* ctx, int op, int npow, const double* x, double* y, long long n) {
+  double *dx, *dy;
+  UAVMP_CUDA(ctx, cudaMalloc(&dx, n * sizeof(double)));
+  UAVMP_CUDA(ctx, cudaMalloc(&dy, n * sizeof(double)));
+  UAVMP_CUDA(ctx, cudaMemcpyAsync(dx, x, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  k_fpmath<<<nblk(n, 256), 256, 0, ctx->stream>>>(op, npow, dx, dy, n);
+  UAVMP_CUDA(ctx, cudaMemcpyAsync(y, dy, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  UAVMP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(dx); cudaFree(dy);
+  return UAVMP_OK;
+}

@@ -1,0 +1,168 @@
+// uavmp_internal.h — shared declarations of the CUDA library (not installed; include/uavmp.h is the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "uavmp.h"
+
+#define UAVMP_MAXPRIM 736   // (2*acc_resolution+1)^3 <= 729  (acc_resolution <= 4), padded to 23 warps
+#define UAVMP_MAXK 32       // checkpoints per primitive: floor(sample_tau/time_step_size)+1
+#define UAVMP_NONE 0xffffffffu
+
+// ---- device-side views ---------------------------------------------------------------------------
+struct KinoParamsDev {
+  int allocated, ctype, K, nprim;
+  double rou, lambda, goal_tol, step, vmax, tau, tie;
+  double robot_r, robot_h;
+  double box_r;     // conservative half-extent of the ellipsoid bounding cube
+  float kd_r2;      // (float)(robot_r + 0.1) squared: the KD-tree radius filter of kino_astar.cpp:744
+  double tk[UAVMP_MAXK];  // i * step_size
+  double hk[UAVMP_MAXK];  // 0.5 * t * t
+  double htau;            // 0.5 * tau * tau
+};
+
+// per-primitive tables (global memory, read-only)
+struct LatticeDev {
+  const double* ux; const double* uy; const double* uz;  // acceleration lattice in the reference's loop order
+  const double* ginc;                                    // (u.u + rou) * tau
+  const double* Einv;                                    // nprim x 9, row-major inverse of Rot diag(r,r,h) Rot^T
+};
+
+struct MapDev {
+  const uint8_t* flags;  // bit0: inflate==1, bit1: inflate!=0, bit2: a cloud point may lie within the ellipsoid box
+  int nx, ny, nz;
+  double ox, oy, oz;                    // mp_.map_origin_
+  double lox, loy, loz, hix, hiy, hiz;  // map_min_boundary_ + 1e-4, map_max_boundary_ - 1e-4
+  double inv_res;
+  // uniform cell list over the cloud (float4-padded points sorted by cell)
+  const int* cell_start;
+  const float4* pts;
+  double cox, coy, coz, inv_cell;
+  int cnx, cny, cnz, n_cloud;
+};
+
+struct __align__(8) KinoNode {
+  double px, py, pz, vx, vy, vz, g;
+  uint32_t parent;    // node id or UAVMP_NONE
+  uint32_t heap_pos;  // 0-based slot in the open-list array
+  uint16_t input;     // lattice id of the primitive that produced this state
+  uint8_t closed;
+  uint8_t pad0;
+  uint32_t pad1;
+};
+static_assert(sizeof(KinoNode) == 72, "node record is 72 B");
+
+struct __align__(16) HeapSlot {
+  double f;      // cached key; kept equal to the live f_cost (mutations write through heap_pos)
+  uint32_t id;
+  uint32_t dirty;
+};
+struct __align__(16) HashSlot {
+  unsigned long long key;  // (packed voxel index << 10) | epoch
+  uint32_t id;
+  uint32_t pad;
+};
+
+struct KinoArena {           // one per resident CTA, reused across queries
+  KinoNode* nodes;           // allocated
+  HeapSlot* heap;            // allocated + 2 (slot i lives at heap[i+1] so both children share a 32 B sector)
+  HashSlot* table;           // table_size
+  uint32_t* epoch;           // 1 word
+};
+
+struct KinoBatchDev {
+  int B;
+  const double* start_pt; const double* start_vel; const double* end_pt; const double* end_vel;
+  const int* order;          // processing order (longest straight-line distance first) or nullptr
+  int* status; int* use_node_num; int* n_pop; unsigned long long* pop_hash;
+  int* n_path;               // points per query
+  double* path_stage;        // B x path_cap x 3
+  int path_cap;
+  int* pop_trace; int pop_cap;  // optional B x pop_cap x 3
+  int* error_flag;
+  unsigned long long* counters;  // 8 words
+  int* next_query;           // work counter
+};
+
+// ---- host-side context -----------------------------------------------------------------------------
+struct QpPlan;  // qp_symbolic.cpp
+
+struct uavmp_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int sm_count = 0;
+
+  // params
+  uavmp_kino_params kp;
+  bool params_dirty = true;
+  KinoParamsDev* d_kparams = nullptr;
+  double* d_lattice = nullptr;  // ux|uy|uz|ginc|Einv
+  int nprim = 0;
+
+  // map
+  bool have_map = false;
+  int nx = 0, ny = 0, nz = 0;
+  double origin[3], map_size[3], resolution = 0;
+  int8_t* d_occ = nullptr;
+  uint8_t* d_flags = nullptr;
+  uint8_t* d_tmp = nullptr;
+  float* d_cloud = nullptr;
+  int n_cloud = 0;
+  int* d_cell_start = nullptr;
+  float4* d_pts = nullptr;
+  MapDev map_host;
+  MapDev* d_map = nullptr;
+  bool flags_dirty = true;
+
+  // search arenas
+  int n_arenas = 0, arena_nodes = 0, table_size = 0;
+  void* d_arena_mem = nullptr;
+  KinoArena* d_arenas = nullptr;
+
+  // batch buffers
+  int batch_cap = 0, path_cap = 1024, pop_cap = 0;
+  double* d_q = nullptr;  // 4 x B x 3
+  int* d_order = nullptr;
+  int* d_status = nullptr; int* d_use = nullptr; int* d_npop = nullptr; unsigned long long* d_hash = nullptr;
+  int* d_npath = nullptr; double* d_path_stage = nullptr; int* d_trace = nullptr;
+  long long* d_offsets = nullptr; double* d_path_packed = nullptr; long long path_packed_cap = 0;
+  int* d_misc = nullptr;  // [0] error flag, [1] work counter
+  unsigned long long* d_counters = nullptr;
+  long long last_total_path = 0;
+  int last_B = 0;
+  void* d_cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
+
+  // qp
+  std::vector<QpPlan*> qp_plans;
+  void* d_qp_ws = nullptr; size_t qp_ws_bytes = 0;
+  double* d_qp_in = nullptr; size_t qp_in_bytes = 0;
+  double* d_qp_out = nullptr; size_t qp_out_bytes = 0;
+  int* d_qp_int = nullptr; size_t qp_int_bytes = 0;
+  double* d_plan_out = nullptr; size_t plan_out_bytes = 0;
+  int* d_plan_io = nullptr; size_t plan_io_bytes = 0;
+  double* d_wp = nullptr; size_t wp_bytes = 0;
+
+  // timings
+  cudaEvent_t ev[8];
+  uavmp_timings tm;
+};
+
+int uavmp_fail(uavmp_ctx* ctx, int code, const char* fmt, ...);
+#define UAVMP_CUDA(ctx, call)                                                                  \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess) return uavmp_fail(ctx, UAVMP_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+// kino_kernel.cu
+int kino_upload_params(uavmp_ctx* ctx);
+int kino_build_map(uavmp_ctx* ctx);
+int kino_ensure_arenas(uavmp_ctx* ctx);
+int kino_ensure_batch(uavmp_ctx* ctx, int B);
+int kino_launch_search(uavmp_ctx* ctx, int B, const double* d_start_pt, const double* d_start_vel,
+                       const double* d_end_pt, const double* d_end_vel, bool sort_order);
+int kino_pack_paths(uavmp_ctx* ctx, int B);
