@@ -103,3 +103,111 @@ def fp_eval(op, x, n_pow=0):
     y = np.zeros_like(x)
     lib.oracle_fp_eval_n(op, x.ctypes.data, n_pow, y.ctypes.data, x.size)
     return y
+
+
+# ---- QP side ---------------------------------------------------------------------------------------------------
+class OsqpSettings(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("rho", "sigma", "alpha", "eps_abs", "eps_rel", "eps_prim_inf",
+                                          "eps_dual_inf")] + \
+        [(n, C.c_int) for n in ("max_iter", "check_termination", "scaling", "adaptive_rho", "adaptive_rho_interval")] + \
+        [("adaptive_rho_tolerance", C.c_double), ("want_scaling_dump", C.c_int), ("dump_D", C.c_void_p),
+         ("dump_E", C.c_void_p)]
+
+
+class OsqpInfo(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("setup_flag", "solve_flag", "status_val", "iter", "rho_updates",
+                                       "adaptive_rho_interval_used")] + \
+        [(n, C.c_double) for n in ("rho_final", "prim_res", "dual_res", "obj_val", "scaling_c")]
+
+
+def osqp_settings(**kw):
+    """What MinimumControl::solve runs OSQP with (minimum_control.cpp:160-162 over osqp_api_constants.h:96-153)."""
+    s = OsqpSettings(0.1, 1e-6, 1.6, 1e-3, 1e-3, 1e-3, 1e-4, 1000, 25, 10, 1, 0, 5.0, 0, None, None)
+    for k, v in kw.items():
+        setattr(s, k, v)
+    return s
+
+
+def have_ref():
+    return bool(load().oracle_have_ref())
+
+
+def info_dict(info):
+    return {k: getattr(info, k) for k, _ in OsqpInfo._fields_}
+
+
+def _f(a):
+    return None if a is None else np.ascontiguousarray(a, np.float64)
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def minctrl_solve(order, S, pos_1d, bound_vel, bound_acc, T, bound_jerk=None, settings=None, libm_mode=0):
+    lib = load()
+    st = settings or osqp_settings()
+    pos_1d, bound_vel, bound_acc, bound_jerk, T = _f(pos_1d), _f(bound_vel), _f(bound_acc), _f(bound_jerk), _f(T)
+    coef = np.zeros((order + 1) * S)
+    info = OsqpInfo()
+    lib.oracle_minctrl_solve.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.POINTER(OsqpSettings), C.c_int,
+                                                                               C.c_void_p, C.POINTER(OsqpInfo)]
+    ok = lib.oracle_minctrl_solve(order, S, _p(pos_1d), _p(bound_vel), _p(bound_acc), _p(bound_jerk), _p(T),
+                                  C.byref(st), libm_mode, _p(coef), C.byref(info))
+    if ok < 0:
+        raise RuntimeError("oracle/_ref/libosqp_ref.so is not available")
+    return ok, coef, info_dict(info)
+
+
+def minctrl_assemble(order, S, pos_1d, bound_vel, bound_acc, T, bound_jerk=None, libm_mode=0):
+    lib = load()
+    n, m, nnzP, nnzA = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    lib.oracle_minctrl_dims(order, S, C.byref(n), C.byref(m), C.byref(nnzP), C.byref(nnzA))
+    n, m, nnzP, nnzA = n.value, m.value, nnzP.value, nnzA.value
+    pos_1d, bound_vel, bound_acc, bound_jerk, T = _f(pos_1d), _f(bound_vel), _f(bound_acc), _f(bound_jerk), _f(T)
+    Pp, Pi, Px = np.zeros(n + 1, np.int64), np.zeros(nnzP, np.int64), np.zeros(nnzP)
+    Ap, Ai, Ax = np.zeros(n + 1, np.int64), np.zeros(nnzA, np.int64), np.zeros(nnzA)
+    q, l, u = np.zeros(n), np.zeros(m), np.zeros(m)
+    lib.oracle_minctrl_assemble.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 9
+    lib.oracle_minctrl_assemble(order, S, _p(pos_1d), _p(bound_vel), _p(bound_acc), _p(bound_jerk), _p(T), libm_mode,
+                                _p(Pp), _p(Pi), _p(Px), _p(q), _p(Ap), _p(Ai), _p(Ax), _p(l), _p(u))
+    return dict(n=n, m=m, Pp=Pp, Pi=Pi, Px=Px, q=q, Ap=Ap, Ai=Ai, Ax=Ax, l=l, u=u)
+
+
+def _csc(M):
+    i64 = lambda a: np.ascontiguousarray(a, np.int64)
+    return i64(M.indptr), i64(M.indices), np.ascontiguousarray(M.data, np.float64)
+
+
+def osqp_solve(P_triu_csc, q, A_csc, l, u, settings=None):
+    """Generic QP through the reference's OSQP (scipy CSC inputs)."""
+    lib = load()
+    st = settings or osqp_settings(eps_prim_inf=1e-4, max_iter=4000)
+    n, m = P_triu_csc.shape[0], A_csc.shape[0]
+    Pp, Pi, Px = _csc(P_triu_csc)
+    Ap, Ai, Ax = _csc(A_csc)
+    q, l, u = _f(q), _f(l), _f(u)
+    x, y = np.zeros(n), np.zeros(max(m, 1))
+    info = OsqpInfo()
+    lib.oracle_osqp_solve.argtypes = [C.c_longlong, C.c_longlong] + [C.c_void_p] * 9 + \
+        [C.POINTER(OsqpSettings), C.c_void_p, C.c_void_p, C.POINTER(OsqpInfo)]
+    rc = lib.oracle_osqp_solve(n, m, _p(Pp), _p(Pi), _p(Px), _p(q), _p(Ap), _p(Ai), _p(Ax), _p(l), _p(u),
+                               C.byref(st), _p(x), _p(y), C.byref(info))
+    if rc < 0:
+        raise RuntimeError("oracle/_ref/libosqp_ref.so is not available")
+    return x, y[:m], info_dict(info)
+
+
+def kkt_solve(P_triu_csc, A_csc, sigma, rho, rhs):
+    lib = load()
+    n, m = P_triu_csc.shape[0], A_csc.shape[0]
+    Pp, Pi, Px = _csc(P_triu_csc)
+    Ap, Ai, Ax = _csc(A_csc)
+    rhs = _f(rhs)
+    sol = np.zeros(n + m)
+    lib.oracle_osqp_kkt_solve.argtypes = [C.c_longlong, C.c_longlong] + [C.c_void_p] * 6 + \
+        [C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+    rc = lib.oracle_osqp_kkt_solve(n, m, _p(Pp), _p(Pi), _p(Px), _p(Ap), _p(Ai), _p(Ax), sigma, rho, _p(rhs), _p(sol))
+    if rc:
+        raise RuntimeError(f"kkt solve failed ({rc})")
+    return sol

@@ -1,0 +1,78 @@
+"""GPU parity: batched CUDA MinimumControl::solve vs the reference's own OSQP (oracle/_ref) on the same inputs.
+
+Gate (BASELINE.json north_star): segment coefficients within 1e-5 relative of the OSQP solution at the same ADMM
+tolerance; we also require identical OSQP status and iteration count for every problem.
+"""
+import numpy as np
+import pytest
+
+import oracle_lib
+import uav_motion_planning_b200 as u
+from uav_motion_planning_b200.minimum_control import MinimumControl, default_settings
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def make_problems(B, S, seed, unit_time=True):
+    rng = np.random.default_rng(seed)
+    pos = np.cumsum(rng.normal(size=(B, S + 1)), axis=1)
+    bv = rng.normal(size=(B, 2)) * 0.5
+    ba = rng.normal(size=(B, 2)) * 0.2
+    bj = np.zeros((B, 2))
+    T = np.ones((B, S)) if unit_time else rng.uniform(0.5, 2.0, size=(B, S))
+    return pos, bv, ba, bj, T
+
+
+def compare(ctx, order, S, B, seed, unit_time=True, **st_kw):
+    pos, bv, ba, bj, T = make_problems(B, S, seed, unit_time)
+    mc = MinimumControl(ctx, order=order)
+    got = mc.solve_batch(pos, bv, ba, T, bound_jerk=bj, settings=default_settings(**st_kw))
+    worst = 0.0
+    for b in range(B):
+        ok, coef, info = oracle_lib.minctrl_solve(order, S, pos[b], bv[b], ba[b], T[b], bound_jerk=bj[b],
+                                                  settings=oracle_lib.osqp_settings(**st_kw))
+        assert info["status_val"] == got["status"][b], (b, info, got["status"][b], got["iters"][b])
+        assert info["iter"] == got["iters"][b], (b, info, got["iters"][b])
+        assert ok == got["solved"][b]
+        if ok:
+            scale = np.abs(coef).max()
+            err = np.abs(coef - got["coef"][b]).max() / scale
+            worst = max(worst, err)
+            assert err < RTOL, (b, err)
+    return worst
+
+
+def test_reference_fixture_qpsolve(gpu_ctx):
+    # src/planner/test/src/test_qpsolve.cpp:10-18: waypoints 1,2,3,4, v = a = 0, T = 1,1,1
+    mc = MinimumControl(gpu_ctx, order=5)
+    assert mc.solve(np.array([1.0, 2.0, 3.0, 4.0]), np.zeros(2), np.zeros(2), np.ones(3))
+    ok, coef, info = oracle_lib.minctrl_solve(5, 3, [1, 2, 3, 4], [0, 0], [0, 0], [1, 1, 1])
+    assert ok == 1 and mc.last["iters"][0] == info["iter"]
+    assert np.abs(mc.getCoef1d() - coef).max() / np.abs(coef).max() < RTOL
+
+
+@pytest.mark.parametrize("S", [1, 2, 4, 8])
+def test_min_jerk(gpu_ctx, S):
+    compare(gpu_ctx, 5, S, 64, seed=S)
+
+
+@pytest.mark.parametrize("S", [2, 8, 12, 16])
+def test_min_snap_extension(gpu_ctx, S):
+    compare(gpu_ctx, 7, S, 48, seed=100 + S)
+
+
+def test_nonuniform_times(gpu_ctx):
+    compare(gpu_ctx, 5, 4, 64, seed=7, unit_time=False)
+    compare(gpu_ctx, 7, 8, 64, seed=8, unit_time=False)
+
+
+@pytest.mark.parametrize("eps", [1e-3, 1e-4, 1e-5, 1e-6])
+def test_eps_sweep_config5(gpu_ctx, eps):
+    # BASELINE.json configs[4] in miniature: 16-segment snap, eps_abs = eps_rel swept, adaptive rho active
+    compare(gpu_ctx, 7, 16, 24, seed=int(-np.log10(eps)), unit_time=False, eps_abs=eps, eps_rel=eps, max_iter=4000)
+
+
+def test_ragged_batch_sizes(gpu_ctx):
+    for B in (1, 31, 33, 257):
+        compare(gpu_ctx, 5, 3, B, seed=B)

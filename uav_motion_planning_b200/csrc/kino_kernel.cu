@@ -68,7 +68,7 @@ struct SearchSmem {
   unsigned long long pop_hash;
   unsigned long long cnt[8];
   uint32_t cur_id, cur_parent, epoch;
-  int heap_len, use_num, n_pop, n1, n2, n_new, status, flag, q, hc_active, hc_total, hc_identity;
+  int heap_len, use_num, n_pop, n1, n2, n_new, status, flag, q, hc_active, hc_total;
   int wsum[KT / 32];
 };
 
@@ -265,50 +265,41 @@ __device__ void heap_pop_serial(HeapSlot* H, KinoNode* nodes, int& len, HeapSlot
   nodes[value.id].heap_pos = (uint32_t)hole;
 }
 
-// closure = the ancestors of leaves n0+1 .. n0+m (1-based heap indices), staged in shared memory (warp 0)
+// closure = the ancestors of leaves len0+1 .. len0+m (1-based heap indices), staged in shared memory by warp 0.
+// The caller keeps every batch inside ONE level of the tree (all new leaves at the same depth), so the ancestors
+// `d` levels up form the contiguous range [(len0+1) >> d, (len0+m) >> d] and ranges of different d never share a node.
 __device__ void closure_load(SearchSmem& s, const HeapSlot* H, int len0, int m, int lane) {
   int total = 0;
-  bool identity = (m > len0 + 1);
   for (int d = 0; d < 32; d++) {
-    int lo, hi, off;
-    if (identity) {
-      lo = 1; hi = len0 + m; off = 0;
-    } else {
-      lo = max((len0 + 1) >> d, 1);
-      hi = (len0 + m) >> d;
-      off = total;
-    }
-    int cnt = hi >= lo ? hi - lo + 1 : 0;
-    if (lane == 0) { s.lv_lo[d] = lo; s.lv_hi[d] = hi; s.lv_off[d] = off; }
-    if (!identity) {
-      if (d >= 1)
-        for (int j = lane; j < cnt; j += 32) { HeapSlot e = H[lo + j]; e.dirty = 0; s.hc[off + j] = e; }
-      total += cnt;
-    }
+    const int lo = (len0 + 1) >> d, hi = (len0 + m) >> d;
+    const int cnt = (lo >= 1) ? hi - lo + 1 : 0;
+    if (lane == 0) { s.lv_lo[d] = lo; s.lv_hi[d] = (lo >= 1) ? hi : -1; s.lv_off[d] = total; }
+    if (d >= 1)
+      for (int j = lane; j < cnt; j += 32) { HeapSlot e = H[lo + j]; e.dirty = 0; s.hc[total + j] = e; }
+    total += cnt;
   }
-  if (identity) {
-    total = len0 + m;
-    for (int j = lane; j < len0; j += 32) { HeapSlot e = H[1 + j]; e.dirty = 0; s.hc[j] = e; }
-  }
-  if (lane == 0) { s.hc_total = total; s.hc_active = 1; s.hc_identity = identity ? 1 : 0; }
+  if (lane == 0) { s.hc_total = total; s.hc_active = 1; }
   __syncwarp();
 }
 
 __device__ void closure_flush(SearchSmem& s, HeapSlot* H, int lane) {
   if (!s.hc_active) return;
   __syncwarp();
-  if (s.hc_identity) {
-    for (int j = lane; j < s.hc_total; j += 32) { HeapSlot e = s.hc[j]; if (e.dirty) H[1 + j] = e; }
-  } else {
-    for (int d = 0; d < 32; d++) {
-      int lo = s.lv_lo[d], hi = s.lv_hi[d], off = s.lv_off[d];
-      int cnt = hi >= lo ? hi - lo + 1 : 0;
-      for (int j = lane; j < cnt; j += 32) { HeapSlot e = s.hc[off + j]; if (e.dirty) H[lo + j] = e; }
-    }
+  for (int d = 0; d < 32; d++) {
+    const int lo = s.lv_lo[d], hi = s.lv_hi[d], off = s.lv_off[d];
+    const int cnt = hi >= lo ? hi - lo + 1 : 0;
+    for (int j = lane; j < cnt; j += 32) { HeapSlot e = s.hc[off + j]; if (e.dirty) H[lo + j] = e; }
   }
   __syncwarp();
   if (lane == 0) s.hc_active = 0;
   __syncwarp();
+}
+
+// number of leaves that can be pushed from length `len` without leaving the current tree level
+__device__ __forceinline__ int level_room(int len) {
+  const int x = len + 1;                // 1-based index of the next leaf
+  const int depth = 31 - __clz(x);
+  return (2 << depth) - x;              // leaves x .. 2^(depth+1) - 1
 }
 
 // std::push_heap of (f, id) as 1-based leaf n1, ancestors read from the closure
@@ -751,7 +742,7 @@ __global__ void __launch_bounds__(KT) kino_search_kernel(const KinoParamsDev* __
 
       // ---- D. ordered commit: heap pushes and in-place mutations (:225-266) ----------------------------
       if (warp == 0) {
-        int pushed = 0, len = s.heap_len;
+        int pushed = 0, len = s.heap_len, batch_left = 0;
         double opt_time = s.opt_time;
         int n_upd = 0;
         for (int pb = 0; pb < P.nprim; pb += 32) {
@@ -764,13 +755,15 @@ __global__ void __launch_bounds__(KT) kino_search_kernel(const KinoParamsDev* __
             const int pe = pb + l;
             const uint8_t ste = s.state[pe];
             if (ste == ST_NEW) {
-              if ((pushed % PUSH_BATCH) == 0) {
+              if (batch_left == 0) {
                 closure_flush(s, H, lane);
-                closure_load(s, H, len, min(PUSH_BATCH, n_new - pushed), lane);
+                batch_left = min(min(PUSH_BATCH, n_new - pushed), level_room(len));
+                closure_load(s, H, len, batch_left, lane);
               }
               closure_push(s, nodes, len + 1, s.f[pe], s.id[pe], lane);
               len++;
               pushed++;
+              batch_left--;
               if (s.topt[pe] >= 0.0) opt_time = s.topt[pe];
             } else {
               int leader = pe;

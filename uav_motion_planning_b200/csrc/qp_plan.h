@@ -1,0 +1,28 @@
+// qp_plan.h — pattern-only data of one (order, S) QP family, built by qp_symbolic.cpp, consumed by qp_kernel.cu.
+#pragma once
+#include <vector>
+
+struct QpPlanHost {
+  int order, S, k, nc, n, m, N, nnzP, nnzA, nnzK, nnzL;
+  std::vector<int> Pp, Pi, P_seg, P_pow;  std::vector<double> P_coef;   // upper-triangular CSC of P + value recipe
+  std::vector<int> Ap, Ai, A_seg, A_pow;  std::vector<double> A_coef;   // CSC of A + value recipe coef * T[seg]^pow
+  std::vector<int> l_src;                                               // bound source per constraint row (-1: 0.0)
+  std::vector<int> perm;                                                // perm[j] = original KKT index at position j
+  std::vector<int> Kp, Ki, Kkind, Kidx;                                 // permuted upper CSC of the KKT matrix
+  std::vector<int> Lp, Li;                                              // pattern of L (strictly lower, CSC)
+  std::vector<int> Rp, Rc, Rpos;                                        // per row k: reach columns and target slots
+};
+
+QpPlanHost* qp_plan_build(int order, int S);
+
+// device view (all int arrays live in one allocation)
+struct QpPlanDev {
+  int order, S, k, nc, n, m, N, nnzP, nnzA, nnzK, nnzL;
+  const int *Pp, *Pi, *P_seg, *P_pow;
+  const int *Ap, *Ai, *A_seg, *A_pow;
+  const double *P_coef, *A_coef;
+  const int *l_src, *perm, *Kp, *Ki, *Kkind, *Kidx, *Lp, *Li, *Rp, *Rc, *Rpos;
+  // workspace layout (offsets in doubles)
+  int o_Px, o_Ax, o_q, o_l, o_u, o_D, o_Dinv, o_E, o_Einv, o_rho, o_rhoinv, o_Lx, o_Dd, o_Ddinv, o_yw, o_x, o_xprev,
+      o_dx, o_Pxv, o_Aty, o_z, o_zprev, o_y, o_dy, o_Axv, o_xz, o_bp, o_tn, o_tm, ws_doubles;
+};

@@ -1,0 +1,185 @@
+// qp_symbolic.cpp — host-side symbolic analysis for the batched minimum-jerk / minimum-snap QP (K2).
+//
+// Every 1-D QP of a batch has the same sparsity pattern (it depends only on (order, S)), so everything that is
+// pattern-only is computed once here and shared by all threads of the kernel:
+//   * the pattern + value recipe of P (upper triangle) and A
+//     (reference: src/planner/traj_optimization/src/minimum_control.cpp:5-19 getHessian, :26-96 getConstraintMatrix,
+//      generalised to order 7 per SURVEY.md §9.3; the explicit 0.0 entries the reference inserts only influence
+//      OSQP's fill-in / rounding, not the mathematics, and are not stored),
+//   * where each constraint bound comes from (:98-125 getBound),
+//   * the quasi-definite KKT matrix [[P + sigma I, A'], [A, -diag(1/rho)]] (3rd/osqp/algebra/_common/kkt.h:15-21) in a
+//     fill-reducing order (our own minimum-degree ordering; OSQP uses AMD — any symmetric permutation of a
+//     quasi-definite matrix has an LDL' factorisation), its elimination tree, the pattern of L and, for every row of the
+//     up-looking factorisation, the etree reach in topological order (what QDLDL recomputes per call,
+//     qdldl_interface.c:85-134).
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <set>
+#include <vector>
+
+#include "qp_plan.h"
+
+namespace {
+
+double falling(int j, int r) {
+  double v = 1.0;
+  for (int k = 0; k < r; k++) v *= (double)(j - k);
+  return v;
+}
+
+struct Entry { int r, c, seg, pw; double coef; };
+
+}  // namespace
+
+QpPlanHost* qp_plan_build(int order, int S) {
+  QpPlanHost* pl = new QpPlanHost();
+  QpPlanHost& P = *pl;
+  const int k = (order + 1) / 2, nc = order + 1;
+  const int n = nc * S, m = 2 * k + (k + 1) * (S - 1), N = n + m;
+  P.order = order; P.S = S; P.k = k; P.nc = nc; P.n = n; P.m = m; P.N = N;
+
+  // ---- P (upper) ------------------------------------------------------------------------------------------
+  std::vector<Entry> pe;
+  for (int s = 0; s < S; s++)
+    for (int j = k; j < nc; j++)      // column
+      for (int i = k; i <= j; i++) {  // row <= column
+        int e = i + j - 2 * k + 1;
+        pe.push_back({nc * s + i, nc * s + j, s, e, falling(i, k) * falling(j, k) / (double)e});
+      }
+  std::sort(pe.begin(), pe.end(), [](const Entry& a, const Entry& b) { return a.c != b.c ? a.c < b.c : a.r < b.r; });
+  P.Pp.assign(n + 1, 0);
+  for (auto& e : pe) {
+    P.Pp[e.c + 1]++; P.Pi.push_back(e.r); P.P_seg.push_back(e.seg); P.P_pow.push_back(e.pw); P.P_coef.push_back(e.coef);
+  }
+  for (int c = 0; c < n; c++) P.Pp[c + 1] += P.Pp[c];
+  P.nnzP = (int)pe.size();
+
+  // ---- A -----------------------------------------------------------------------------------------------------
+  std::vector<Entry> ae;
+  for (int r = 0; r < k; r++) ae.push_back({r, r, 0, 0, falling(r, r)});
+  auto deriv_row = [&](int row, int s, int r) {
+    for (int j = r; j < nc; j++) ae.push_back({row, nc * s + j, s, j - r, falling(j, r)});
+  };
+  for (int s = 0; s + 1 < S; s++) {
+    int base = k + (k + 1) * s;
+    deriv_row(base, s, 0);
+    for (int r = 0; r < k; r++) {
+      deriv_row(base + 1 + r, s, r);
+      ae.push_back({base + 1 + r, nc * (s + 1) + r, 0, 0, -falling(r, r)});
+    }
+  }
+  {
+    int base = k + (k + 1) * (S - 1);
+    for (int r = 0; r < k; r++) deriv_row(base + r, S - 1, r);
+  }
+  std::sort(ae.begin(), ae.end(), [](const Entry& a, const Entry& b) { return a.c != b.c ? a.c < b.c : a.r < b.r; });
+  P.Ap.assign(n + 1, 0);
+  for (auto& e : ae) {
+    P.Ap[e.c + 1]++; P.Ai.push_back(e.r); P.A_seg.push_back(e.seg); P.A_pow.push_back(e.pw); P.A_coef.push_back(e.coef);
+  }
+  for (int c = 0; c < n; c++) P.Ap[c + 1] += P.Ap[c];
+  P.nnzA = (int)ae.size();
+
+  // ---- bounds: index into [pos_1d (S+1) | bound_vel (2) | bound_acc (2) | bound_jerk (2)], -1 -> 0.0 ------------
+  P.l_src.assign(m, -1);
+  P.l_src[0] = 0;
+  for (int r = 1; r < k; r++) P.l_src[r] = (S + 1) + 2 * (r - 1);
+  int eb = k + (k + 1) * (S - 1);
+  P.l_src[eb] = S;
+  for (int r = 1; r < k; r++) P.l_src[eb + r] = (S + 1) + 2 * (r - 1) + 1;
+  for (int s = 0; s + 1 < S; s++) P.l_src[k + (k + 1) * s] = s + 1;
+
+  // ---- KKT pattern (original order), as an undirected graph ---------------------------------------------------------
+  // entry sources: kind 0 P off-diagonal, 1 P diagonal (+sigma), 2 sigma only, 3 A, 4 -1/rho
+  struct KE { int i, j, kind, idx; };
+  std::vector<KE> ke;
+  std::vector<char> has_diag(n, 0);
+  for (int c = 0; c < n; c++)
+    for (int p = P.Pp[c]; p < P.Pp[c + 1]; p++) {
+      int r = P.Pi[p];
+      if (r == c) { ke.push_back({r, c, 1, p}); has_diag[c] = 1; }
+      else ke.push_back({r, c, 0, p});
+    }
+  for (int c = 0; c < n; c++) if (!has_diag[c]) ke.push_back({c, c, 2, 0});
+  for (int c = 0; c < n; c++)
+    for (int p = P.Ap[c]; p < P.Ap[c + 1]; p++) ke.push_back({c, n + P.Ai[p], 3, p});  // A' block: (var c, con row)
+  for (int r = 0; r < m; r++) ke.push_back({n + r, n + r, 4, r});
+
+  // ---- minimum-degree ordering on the elimination graph ----------------------------------------------------------------
+  std::vector<std::set<int>> adj(N);
+  for (auto& e : ke) if (e.i != e.j) { adj[e.i].insert(e.j); adj[e.j].insert(e.i); }
+  std::vector<int> perm(N), inv(N, -1);
+  std::vector<char> done(N, 0);
+  for (int step = 0; step < N; step++) {
+    int best = -1; size_t bd = (size_t)-1;
+    for (int v = 0; v < N; v++) if (!done[v] && adj[v].size() < bd) { bd = adj[v].size(); best = v; }
+    perm[step] = best; inv[best] = step; done[best] = 1;
+    std::vector<int> nb(adj[best].begin(), adj[best].end());
+    for (int a : nb) adj[a].erase(best);
+    for (size_t x = 0; x < nb.size(); x++)
+      for (size_t y = x + 1; y < nb.size(); y++) { adj[nb[x]].insert(nb[y]); adj[nb[y]].insert(nb[x]); }
+    adj[best].clear();
+  }
+  P.perm = perm;
+
+  // ---- permuted upper CSC of the KKT matrix -------------------------------------------------------------------------------
+  struct PK { int r, c, kind, idx; };
+  std::vector<PK> pk;
+  for (auto& e : ke) {
+    int a = inv[e.i], b = inv[e.j];
+    pk.push_back({std::min(a, b), std::max(a, b), e.kind, e.idx});
+  }
+  std::sort(pk.begin(), pk.end(), [](const PK& a, const PK& b) { return a.c != b.c ? a.c < b.c : a.r < b.r; });
+  P.Kp.assign(N + 1, 0);
+  for (auto& e : pk) { P.Kp[e.c + 1]++; P.Ki.push_back(e.r); P.Kkind.push_back(e.kind); P.Kidx.push_back(e.idx); }
+  for (int c = 0; c < N; c++) P.Kp[c + 1] += P.Kp[c];
+  P.nnzK = (int)pk.size();
+
+  // ---- elimination tree + column counts of L (same algorithm QDLDL_etree runs per setup) ---------------------------------------
+  std::vector<int> etree(N, -1), work(N, 0), Lnz(N, 0);
+  for (int j = 0; j < N; j++) {
+    work[j] = j;
+    for (int p = P.Kp[j]; p < P.Kp[j + 1]; p++) {
+      int i = P.Ki[p];
+      while (work[i] != j) {
+        if (etree[i] == -1) etree[i] = j;
+        Lnz[i]++;
+        work[i] = j;
+        i = etree[i];
+      }
+    }
+  }
+  P.Lp.assign(N + 1, 0);
+  for (int i = 0; i < N; i++) P.Lp[i + 1] = P.Lp[i] + Lnz[i];
+  P.nnzL = P.Lp[N];
+  P.Li.assign(P.nnzL, 0);
+  // ---- row-by-row reach (topological) and the slot every new L entry lands in ---------------------------------------------------
+  std::vector<int> next(N);
+  for (int i = 0; i < N; i++) next[i] = P.Lp[i];
+  std::vector<char> mark(N, 0);
+  P.Rp.assign(N + 1, 0);
+  for (int kk = 0; kk < N; kk++) {
+    std::vector<int> yidx;
+    for (int p = P.Kp[kk]; p < P.Kp[kk + 1]; p++) {
+      int b = P.Ki[p];
+      if (b == kk) continue;
+      if (!mark[b]) {
+        std::vector<int> chain;
+        int nx = b;
+        while (nx != -1 && nx < kk && !mark[nx]) { mark[nx] = 1; chain.push_back(nx); nx = etree[nx]; }
+        for (int q = (int)chain.size() - 1; q >= 0; q--) yidx.push_back(chain[q]);
+      }
+    }
+    for (int q = (int)yidx.size() - 1; q >= 0; q--) {  // visited back to front == topological order
+      int c = yidx[q];
+      P.Rc.push_back(c);
+      P.Rpos.push_back(next[c]);
+      P.Li[next[c]] = kk;
+      next[c]++;
+      mark[c] = 0;
+    }
+    P.Rp[kk + 1] = (int)P.Rc.size();
+  }
+  return pl;
+}
