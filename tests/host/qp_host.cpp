@@ -1,0 +1,29 @@
+// tests/host/qp_host.cpp — TEST HARNESS (never part of libuavmp.so): compiles the product's K2 body
+// (uav_motion_planning_b200/csrc/qp_body.h) and symbolic plan (qp_symbolic.cpp) for the HOST, so that the restated
+// OSQP algorithm and the fill-reducing plan can be compared with the reference OSQP (oracle/_ref) without a GPU.
+// Build: g++ -O2 -ffp-contract=off -shared -fPIC (tests/host_qp.py does it on demand).
+#include <vector>
+
+#include "../../uav_motion_planning_b200/csrc/qp_body.h"
+
+extern "C" int host_qp_solve(int order, int S, int B, const double* pos, const double* bv, const double* ba,
+                             const double* bj, const double* T, const uavmp_osqp_settings* st, double* coef,
+                             int* solved, int* status, int* iters, int* stats6) {
+  QpPlanHost* H = qp_plan_build(order, S);
+  std::vector<int> ints;
+  std::vector<double> dbls;
+  QpPlanOffsets off;
+  QpPlanDev D;
+  qp_plan_pack(*H, ints, dbls, off);
+  qp_plan_bind(*H, off, ints.data(), dbls.data(), D);
+  if (stats6) { stats6[0] = H->n; stats6[1] = H->m; stats6[2] = H->nnzP; stats6[3] = H->nnzA; stats6[4] = H->nnzK; stats6[5] = H->nnzL; }
+  const int stride = (B + 31) & ~31;
+  // poison the workspace: any read-before-write inside the body shows up as NaN coefficients
+  std::vector<double> ws((size_t)D.ws_doubles * stride, fpm::from_bits(0x7ff8000000000000ull));
+  QpIo io;
+  io.pos = pos; io.bv = bv; io.ba = ba; io.bj = bj ? bj : ba; io.T = T;
+  io.coef = coef; io.solved = solved; io.status = status; io.iters = iters; io.B = B; io.stride = stride;
+  for (int b = 0; b < B; b++) qp_solve_one(D, io, *st, ws.data(), b);
+  delete H;
+  return 0;
+}

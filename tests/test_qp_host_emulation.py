@@ -1,0 +1,60 @@
+"""CPU test of the product's QP kernel BODY: uav_motion_planning_b200/csrc/qp_body.h is compiled for the host by
+tests/host/qp_host.cpp (identical statements to the device instantiation, workspace poisoned with NaN) and compared with
+the committed golden vectors and, where oracle/_ref exists, with the reference's own OSQP.  This covers the host logic
+(qp_symbolic.cpp: pattern, ordering, etree, reach lists) and the OSQP restatement without a GPU; the GPU run of the same
+source is checked by tests/test_qp_parity.py (-m gpu)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import host_qp
+import oracle_lib
+from uav_motion_planning_b200.minimum_control import default_settings
+
+RTOL = 1e-5
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "minctrl_golden.json")))
+
+
+@pytest.mark.parametrize("case", GOLD, ids=lambda c: f"order{c['order']}_S{c['S']}")
+def test_against_golden(case):
+    pr = case["problems"]
+    arr = lambda k: np.array([p[k] for p in pr])
+    got = host_qp.solve_batch(case["order"], arr("pos"), arr("bound_vel"), arr("bound_acc"), arr("T"), arr("bound_jerk"),
+                              settings=default_settings(**case["settings"]))
+    for b, p in enumerate(pr):
+        assert (got["solved"][b], got["status"][b], got["iters"][b]) == (p["solved"], p["status_val"], p["iter"])
+        ref = np.array(p["coef"])
+        assert np.abs(ref - got["coef"][b]).max() / np.abs(ref).max() < RTOL
+
+
+@pytest.mark.skipif(not oracle_lib.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("order,S,eps", [(5, 1, 1e-3), (5, 2, 1e-3), (5, 6, 1e-4), (7, 2, 1e-3), (7, 16, 1e-4),
+                                         (7, 16, 1e-6)])
+def test_against_reference_osqp(order, S, eps):
+    rng = np.random.default_rng(order * 100 + S)
+    B = 6
+    pos = np.cumsum(rng.normal(size=(B, S + 1)), axis=1)
+    bv, ba, bj = rng.normal(size=(B, 2)) * 0.5, rng.normal(size=(B, 2)) * 0.2, np.zeros((B, 2))
+    T = rng.uniform(0.5, 2.0, size=(B, S))
+    kw = dict(eps_abs=eps, eps_rel=eps, max_iter=4000)
+    got = host_qp.solve_batch(order, pos, bv, ba, T, bj, settings=default_settings(**kw))
+    for b in range(B):
+        ok, coef, info = oracle_lib.minctrl_solve(order, S, pos[b], bv[b], ba[b], T[b], bound_jerk=bj[b],
+                                                  settings=oracle_lib.osqp_settings(**kw))
+        assert (ok, info["status_val"], info["iter"]) == (got["solved"][b], got["status"][b], got["iters"][b])
+        assert np.abs(coef - got["coef"][b]).max() / np.abs(coef).max() < RTOL
+
+
+def test_max_iter_status():
+    # max_iter below the first termination check: OSQP reports MAX_ITER_REACHED (7) or SOLVED_INACCURATE (2); solve() -> false
+    pos = np.array([[0.0, 1.0, -1.0, 2.0]])
+    z = np.zeros((1, 2))
+    got = host_qp.solve_batch(5, pos, z, z, np.ones((1, 3)), settings=default_settings(max_iter=10))
+    assert got["solved"][0] == 0 and got["status"][0] in (2, 7) and got["iters"][0] == 10
+    if oracle_lib.have_ref():
+        ok, coef, info = oracle_lib.minctrl_solve(5, 3, pos[0], z[0], z[0], np.ones(3),
+                                                  settings=oracle_lib.osqp_settings(max_iter=10))
+        assert (ok, info["status_val"], info["iter"]) == (0, got["status"][0], 10)
+        assert np.abs(coef - got["coef"][0]).max() / np.abs(coef).max() < RTOL

@@ -19,6 +19,15 @@ int qp_scatter_plan_outputs(uavmp_ctx* ctx, int B, int order, int S, const int* 
                             int* d_qp_solved, double* d_coef);
 void qp_free_plans(uavmp_ctx* ctx);
 
+int ensure_bytes(uavmp_ctx* ctx, void** p, size_t* have, size_t want) {
+  if (*have >= want) return UAVMP_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr; *have = 0;
+  UAVMP_CUDA(ctx, cudaMalloc(p, want));
+  *have = want;
+  return UAVMP_OK;
+}
+
 extern "C" {
 
 const char* uavmp_version(void) { return "uavmp-b200 0.1 (sm_100a)"; }
@@ -224,6 +233,16 @@ int uavmp_kino_get_counters(uavmp_ctx* ctx, uavmp_kino_counters* out) {
 
 int uavmp_get_timings(uavmp_ctx* ctx, uavmp_timings* out) {
   if (!ctx || !out) return UAVMP_EINVAL;
+  if (ctx->tm_pending_dev) {
+    // uavmp_plan_batch_dev is asynchronous: resolve its events (search start / search end / pipeline end) now
+    cudaSetDevice(ctx->device);
+    UAVMP_CUDA(ctx, cudaEventSynchronize(ctx->ev[7]));
+    cudaEventElapsedTime(&ctx->tm.search_ms, ctx->ev[5], ctx->ev[6]);
+    cudaEventElapsedTime(&ctx->tm.qp_ms, ctx->ev[6], ctx->ev[7]);
+    cudaEventElapsedTime(&ctx->tm.total_ms, ctx->ev[5], ctx->ev[7]);
+    ctx->tm.h2d_ms = 0; ctx->tm.d2h_ms = 0; ctx->tm.path_ms = 0;
+    ctx->tm_pending_dev = false;
+  }
   *out = ctx->tm;
   return UAVMP_OK;
 }
@@ -235,14 +254,6 @@ int uavmp_fpmath_eval(uavmp_ctx* ctx, int op, int n_pow, const double* x, double
 }
 
 // ---- hot path (b) --------------------------------------------------------------------------------------
-int ensure_bytes(uavmp_ctx* ctx, void** p, size_t* have, size_t want) {
-  if (*have >= want) return UAVMP_OK;
-  if (*p) cudaFree(*p);
-  *p = nullptr; *have = 0;
-  UAVMP_CUDA(ctx, cudaMalloc(p, want));
-  *have = want;
-  return UAVMP_OK;
-}
 
 int uavmp_minctrl_solve_batch(uavmp_ctx* ctx, int order, int S, int B, const double* pos_1d, const double* bound_vel,
                               const double* bound_acc, const double* bound_jerk, const double* time_vec,
@@ -319,6 +330,8 @@ int uavmp_plan_batch_dev(uavmp_ctx* ctx, int B, const double* d_sp, const double
   UAVMP_CUDA(ctx, cudaMemcpyAsync(d_search_status, ctx->d_status, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, st));
   cudaEventRecord(ctx->ev[7], st);
   ctx->last_B = B;
+  ctx->tm_pending_dev = true;
+  ctx->tm.aux_launches = 3;  // k_dist_keys, k_waypoints, k_scatter_plan (+ cub's radix-sort kernels, library code)
   return UAVMP_OK;
 }
 
@@ -357,6 +370,7 @@ int uavmp_plan_batch(uavmp_ctx* ctx, int B, const double* start_pt, const double
   cudaEventElapsedTime(&ctx->tm.d2h_ms, ctx->ev[7], ctx->ev[4]);
   cudaEventElapsedTime(&ctx->tm.total_ms, ctx->ev[0], ctx->ev[4]);
   ctx->tm.path_ms = 0;
+  ctx->tm_pending_dev = false;
   return check_error_flag(ctx);
 }
 

@@ -1,0 +1,460 @@
+// qp_body.h — the per-problem body of K2 (batched minimum-jerk / minimum-snap QP), written once and compiled twice:
+//   * by nvcc as the device code of qp_solve_kernel (qp_kernel.cu) — the product;
+//   * by g++ (-ffp-contract=off) inside tests/host/qp_host.cpp — a TEST harness that runs the identical statements
+//     on the host so the symbolic plan (qp_symbolic.cpp) and the ADMM restatement can be checked without a GPU.
+// The product never runs the host instantiation: libuavmp.so only contains the __global__ wrapper.
+//
+// Restates the algorithm of the reference's vendored OSQP 1.0.0.beta0 (file:line in the comments below).
+#pragma once
+#include <math.h>
+#include <stddef.h>
+
+#include "fpmath.h"
+#include "qp_plan.h"
+#include "uavmp.h"
+
+#if defined(__CUDACC__)
+#define QP_HD __device__ __forceinline__
+#define QP_LDG(p) __ldg(p)
+#else
+#define QP_HD static inline
+#define QP_LDG(p) (*(p))
+#endif
+
+#define OSQP_INFTY_ 1e30
+#define OSQP_MIN_SCALING_ 1e-4
+#define OSQP_MAX_SCALING_ 1e4
+#define OSQP_RHO_MIN_ 1e-6
+#define OSQP_RHO_MAX_ 1e6
+#define OSQP_RHO_TOL_ 1e-4
+#define OSQP_RHO_EQ_OVER_RHO_INEQ_ 1e3
+#define OSQP_DIVISION_TOL_ (1.0 / OSQP_INFTY_)
+
+enum { ST_SOLVED = 1, ST_SOLVED_INACC = 2, ST_PINF = 3, ST_PINF_INACC = 4, ST_DINF = 5, ST_DINF_INACC = 6,
+       ST_MAXITER = 7, ST_NONCVX = 9, ST_UNSOLVED = 11 };
+
+
+QP_HD double limit_scaling(double v) {
+  v = v < OSQP_MIN_SCALING_ ? 1.0 : v;
+  v = v > OSQP_MAX_SCALING_ ? OSQP_MAX_SCALING_ : v;
+  return v;
+}
+
+#define W(off, i) ws[((size_t)((off) + (i))) * stride + b]
+
+// numeric LDL' of the permuted KKT matrix (up-looking, static reach lists) — QDLDL_factor's arithmetic
+QP_HD int qp_factor(const QpPlanDev& pl, double* ws, size_t stride, int b, double sigma) {
+  const int N = pl.N;
+  int positive = 0;
+  for (int k = 0; k < N; k++) {
+    double Dk = 0.0;
+    for (int p = QP_LDG(pl.Kp + k); p < QP_LDG(pl.Kp + k + 1); p++) {
+      const int i = QP_LDG(pl.Ki + p), kind = QP_LDG(pl.Kkind + p), idx = QP_LDG(pl.Kidx + p);
+      double v;
+      if (kind == 0) v = W(pl.o_Px, idx);
+      else if (kind == 1) v = W(pl.o_Px, idx) + sigma;
+      else if (kind == 2) v = sigma;
+      else if (kind == 3) v = W(pl.o_Ax, idx);
+      else v = -W(pl.o_rhoinv, idx);
+      if (i == k) Dk = v; else W(pl.o_yw, i) = v;
+    }
+    for (int e = QP_LDG(pl.Rp + k); e < QP_LDG(pl.Rp + k + 1); e++) {
+      const int c = QP_LDG(pl.Rc + e), pos = QP_LDG(pl.Rpos + e);
+      const double yc = W(pl.o_yw, c);
+      for (int j = QP_LDG(pl.Lp + c); j < pos; j++) {
+        const int r = QP_LDG(pl.Li + j);
+        W(pl.o_yw, r) = W(pl.o_yw, r) - W(pl.o_Lx, j) * yc;
+      }
+      const double lv = yc * W(pl.o_Ddinv, c);
+      W(pl.o_Lx, pos) = lv;
+      Dk -= yc * lv;
+      W(pl.o_yw, c) = 0.0;
+    }
+    if (Dk == 0.0) return -1;
+    if (Dk > 0.0) positive++;
+    W(pl.o_Dd, k) = Dk;
+    W(pl.o_Ddinv, k) = 1.0 / Dk;
+  }
+  return positive;
+}
+
+// xz <- K^-1 xz  (qdldl_interface.c:394-415: permute, L solve, D^-1, L' solve, permute back)
+QP_HD void qp_kkt_solve(const QpPlanDev& pl, double* ws, size_t stride, int b) {
+  const int N = pl.N;
+  for (int j = 0; j < N; j++) W(pl.o_bp, j) = W(pl.o_xz, QP_LDG(pl.perm + j));
+  for (int i = 0; i < N; i++) {
+    const double val = W(pl.o_bp, i);
+    for (int j = QP_LDG(pl.Lp + i); j < QP_LDG(pl.Lp + i + 1); j++) {
+      const int r = QP_LDG(pl.Li + j);
+      W(pl.o_bp, r) = W(pl.o_bp, r) - W(pl.o_Lx, j) * val;
+    }
+  }
+  for (int i = 0; i < N; i++) W(pl.o_bp, i) = W(pl.o_bp, i) * W(pl.o_Ddinv, i);
+  for (int i = N - 1; i >= 0; i--) {
+    double val = W(pl.o_bp, i);
+    for (int j = QP_LDG(pl.Lp + i); j < QP_LDG(pl.Lp + i + 1); j++) val -= W(pl.o_Lx, j) * W(pl.o_bp, QP_LDG(pl.Li + j));
+    W(pl.o_bp, i) = val;
+  }
+  for (int j = 0; j < N; j++) W(pl.o_xz, QP_LDG(pl.perm + j)) = W(pl.o_bp, j);
+}
+
+// out(m) = A * v(n)
+QP_HD void qp_A_mul(const QpPlanDev& pl, double* ws, size_t stride, int b, int o_v, int o_out) {
+  for (int i = 0; i < pl.m; i++) W(o_out, i) = 0.0;
+  for (int c = 0; c < pl.n; c++) {
+    const double vc = W(o_v, c);
+    for (int p = QP_LDG(pl.Ap + c); p < QP_LDG(pl.Ap + c + 1); p++) {
+      const int r = QP_LDG(pl.Ai + p);
+      W(o_out, r) = W(o_out, r) + W(pl.o_Ax, p) * vc;
+    }
+  }
+}
+// out(n) = A' * v(m)
+QP_HD void qp_At_mul(const QpPlanDev& pl, double* ws, size_t stride, int b, int o_v, int o_out) {
+  for (int c = 0; c < pl.n; c++) {
+    double acc = 0.0;
+    for (int p = QP_LDG(pl.Ap + c); p < QP_LDG(pl.Ap + c + 1); p++) acc += W(pl.o_Ax, p) * W(o_v, QP_LDG(pl.Ai + p));
+    W(o_out, c) = acc;
+  }
+}
+// out(n) = P * v(n), P stored as its upper triangle
+QP_HD void qp_P_mul(const QpPlanDev& pl, double* ws, size_t stride, int b, int o_v, int o_out) {
+  for (int i = 0; i < pl.n; i++) W(o_out, i) = 0.0;
+  for (int c = 0; c < pl.n; c++) {
+    const double vc = W(o_v, c);
+    for (int p = QP_LDG(pl.Pp + c); p < QP_LDG(pl.Pp + c + 1); p++) {
+      const int r = QP_LDG(pl.Pi + p);
+      const double a = W(pl.o_Px, p);
+      W(o_out, r) = W(o_out, r) + a * vc;
+      if (r != c) W(o_out, c) = W(o_out, c) + a * W(o_v, r);
+    }
+  }
+}
+QP_HD double qp_norm_inf(double* ws, size_t stride, int b, int o_v, int len) {
+  double r = 0.0;
+  for (int i = 0; i < len; i++) r = fmax(r, fabs(W(o_v, i)));
+  return r;
+}
+QP_HD double qp_scaled_norm_inf(double* ws, size_t stride, int b, int o_s, int o_v, int len) {
+  double r = 0.0;
+  for (int i = 0; i < len; i++) r = fmax(r, fabs(W(o_s, i) * W(o_v, i)));
+  return r;
+}
+
+struct QpResid {
+  double prim_res, dual_res, scaled_prim, scaled_dual;
+};
+
+// update_info (auxil.c:615-690): residuals of (x, z, y); leaves Ax, Px, A'y in the workspace
+QP_HD void qp_update_info(const QpPlanDev& pl, double* ws, size_t stride, int b, double cinv, QpResid& R) {
+  const int n = pl.n, m = pl.m;
+  qp_A_mul(pl, ws, stride, b, pl.o_x, pl.o_Axv);
+  double sp = 0.0, up = 0.0;
+  for (int i = 0; i < m; i++) {
+    const double d = W(pl.o_Axv, i) - W(pl.o_z, i);
+    sp = fmax(sp, fabs(d));
+    up = fmax(up, fabs(W(pl.o_Einv, i) * d));
+  }
+  R.scaled_prim = sp; R.prim_res = up;
+  qp_P_mul(pl, ws, stride, b, pl.o_x, pl.o_Pxv);
+  qp_At_mul(pl, ws, stride, b, pl.o_y, pl.o_Aty);
+  double sd = 0.0, ud = 0.0;
+  for (int i = 0; i < n; i++) {
+    const double d = (W(pl.o_q, i) + W(pl.o_Pxv, i)) + W(pl.o_Aty, i);
+    sd = fmax(sd, fabs(d));
+    ud = fmax(ud, fabs(W(pl.o_Dinv, i) * d));
+  }
+  R.scaled_dual = sd; R.dual_res = cinv * ud;
+}
+
+// check_termination (auxil.c:736-851).  Returns the new status or 0.
+QP_HD int qp_check_termination(const QpPlanDev& pl, double* ws, size_t stride, int b, const uavmp_osqp_settings& S,
+                                    double c, double cinv, const QpResid& R, bool approximate) {
+  const int n = pl.n, m = pl.m;
+  double eps_abs = S.eps_abs, eps_rel = S.eps_rel, eps_pinf = S.eps_prim_inf, eps_dinf = S.eps_dual_inf;
+  if (R.prim_res > OSQP_INFTY_ || R.dual_res > OSQP_INFTY_) return ST_NONCVX;
+  if (approximate) { eps_abs *= 10; eps_rel *= 10; eps_pinf *= 10; eps_dinf *= 10; }
+  bool prim_ok = false, dual_ok = false, pinf = false, dinf = false;
+  {
+    double mx = fmax(qp_scaled_norm_inf(ws, stride, b, pl.o_Einv, pl.o_z, m),
+                     qp_scaled_norm_inf(ws, stride, b, pl.o_Einv, pl.o_Axv, m));
+    const double eps_prim = eps_abs + eps_rel * mx;
+    if (R.prim_res < eps_prim) {
+      prim_ok = true;
+    } else {
+      // is_primal_infeasible (auxil.c:399-448); bounds are finite here so the polar-cone projection is the identity
+      for (int i = 0; i < m; i++) {
+        const double l = W(pl.o_l, i), u = W(pl.o_u, i);
+        double dy = W(pl.o_dy, i);
+        if (u > OSQP_INFTY_ * OSQP_MIN_SCALING_) {
+          if (l < -OSQP_INFTY_ * OSQP_MIN_SCALING_) dy = 0.0; else dy = fmin(dy, 0.0);
+        } else if (l < -OSQP_INFTY_ * OSQP_MIN_SCALING_) {
+          dy = fmax(dy, 0.0);
+        }
+        W(pl.o_dy, i) = dy;
+      }
+      const double norm_dy = qp_scaled_norm_inf(ws, stride, b, pl.o_E, pl.o_dy, m);
+      if (norm_dy > OSQP_DIVISION_TOL_) {
+        double lhs = 0.0, lhs2 = 0.0;
+        for (int i = 0; i < m; i++) { const double dy = W(pl.o_dy, i); lhs += W(pl.o_u, i) * fmax(dy, 0.0); }
+        for (int i = 0; i < m; i++) { const double dy = W(pl.o_dy, i); lhs2 += W(pl.o_l, i) * fmin(dy, 0.0); }
+        lhs += lhs2;
+        if (lhs < 0.0) {
+          qp_At_mul(pl, ws, stride, b, pl.o_dy, pl.o_tn);
+          pinf = qp_scaled_norm_inf(ws, stride, b, pl.o_Dinv, pl.o_tn, n) < eps_pinf * norm_dy;
+        }
+      }
+    }
+  }
+  {
+    double mx = fmax(fmax(qp_scaled_norm_inf(ws, stride, b, pl.o_Dinv, pl.o_q, n),
+                          qp_scaled_norm_inf(ws, stride, b, pl.o_Dinv, pl.o_Aty, n)),
+                     qp_scaled_norm_inf(ws, stride, b, pl.o_Dinv, pl.o_Pxv, n));
+    mx *= cinv;
+    const double eps_dual = eps_abs + eps_rel * mx;
+    if (R.dual_res < eps_dual) {
+      dual_ok = true;
+    } else {
+      // is_dual_infeasible (auxil.c:450-528)
+      const double norm_dx = qp_scaled_norm_inf(ws, stride, b, pl.o_D, pl.o_dx, n);
+      if (norm_dx > OSQP_DIVISION_TOL_) {
+        double qdx = 0.0;
+        for (int i = 0; i < n; i++) qdx += W(pl.o_q, i) * W(pl.o_dx, i);
+        if (qdx < 0.0) {
+          qp_P_mul(pl, ws, stride, b, pl.o_dx, pl.o_tn);
+          if (qp_scaled_norm_inf(ws, stride, b, pl.o_Dinv, pl.o_tn, n) < c * eps_dinf * norm_dx) {
+            qp_A_mul(pl, ws, stride, b, pl.o_dx, pl.o_tm);
+            bool in_cone = true;
+            const double tol = eps_dinf * norm_dx;
+            for (int i = 0; i < m; i++) {
+              const double v = W(pl.o_Einv, i) * W(pl.o_tm, i);
+              if ((W(pl.o_u, i) < OSQP_INFTY_ * OSQP_MIN_SCALING_ && v > tol) ||
+                  (W(pl.o_l, i) > -OSQP_INFTY_ * OSQP_MIN_SCALING_ && v < -tol)) { in_cone = false; break; }
+            }
+            dinf = in_cone;
+          }
+        }
+      }
+    }
+  }
+  if (prim_ok && dual_ok) return approximate ? ST_SOLVED_INACC : ST_SOLVED;
+  if (pinf) return approximate ? ST_PINF_INACC : ST_PINF;
+  if (dinf) return approximate ? ST_DINF_INACC : ST_DINF;
+  return 0;
+}
+
+
+// one problem: assembly -> osqp_setup -> osqp_solve -> store_solution
+QP_HD void qp_solve_one(const QpPlanDev& pl, const QpIo& io, const uavmp_osqp_settings& S, double* ws, int b) {
+  const size_t stride = (size_t)io.stride;
+  const int n = pl.n, m = pl.m, Sg = pl.S, nc = pl.nc;
+
+  // ---- assembly: P, q, A, l, u (minimum_control.cpp:5-125) ---------------------------------------------------
+  const double* T = io.T + (size_t)b * Sg;
+  for (int p = 0; p < pl.nnzP; p++) W(pl.o_Px, p) = QP_LDG(pl.P_coef + p) * fpm::powi(T[QP_LDG(pl.P_seg + p)], QP_LDG(pl.P_pow + p));
+  for (int p = 0; p < pl.nnzA; p++) W(pl.o_Ax, p) = QP_LDG(pl.A_coef + p) * fpm::powi(T[QP_LDG(pl.A_seg + p)], QP_LDG(pl.A_pow + p));
+  for (int i = 0; i < n; i++) W(pl.o_q, i) = 0.0;
+  for (int i = 0; i < m; i++) {
+    const int src = QP_LDG(pl.l_src + i);
+    double v = 0.0;
+    if (src >= 0) {
+      if (src <= Sg) v = io.pos[(size_t)b * (Sg + 1) + src];
+      else {
+        const int r = (src - (Sg + 1)) >> 1, e = (src - (Sg + 1)) & 1;
+        v = (r == 0 ? io.bv : (r == 1 ? io.ba : io.bj))[(size_t)b * 2 + e];
+      }
+    }
+    W(pl.o_l, i) = v;
+    W(pl.o_u, i) = v;
+  }
+
+  // ---- scale_data (scaling.c:49-165) ----------------------------------------------------------------------------
+  double c = 1.0;
+  for (int i = 0; i < n; i++) W(pl.o_D, i) = 1.0;
+  for (int i = 0; i < m; i++) W(pl.o_E, i) = 1.0;
+  for (int it = 0; it < S.scaling; it++) {
+    // column inf-norms of [P; A] — P's stored upper triangle only (csc_col_norm_inf ignores symmetry) — and rows of A
+    for (int j = 0; j < n; j++) {
+      double dn = 0.0;
+      for (int p = QP_LDG(pl.Pp + j); p < QP_LDG(pl.Pp + j + 1); p++) dn = fmax(fabs(W(pl.o_Px, p)), dn);
+      double an = 0.0;
+      for (int p = QP_LDG(pl.Ap + j); p < QP_LDG(pl.Ap + j + 1); p++) an = fmax(fabs(W(pl.o_Ax, p)), an);
+      W(pl.o_tn, j) = fmax(dn, an);
+    }
+    for (int i = 0; i < m; i++) W(pl.o_tm, i) = 0.0;
+    for (int p = 0; p < pl.nnzA; p++) {
+      const int r = QP_LDG(pl.Ai + p);
+      W(pl.o_tm, r) = fmax(fabs(W(pl.o_Ax, p)), W(pl.o_tm, r));
+    }
+    for (int j = 0; j < n; j++) W(pl.o_tn, j) = 1.0 / sqrt(limit_scaling(W(pl.o_tn, j)));
+    for (int i = 0; i < m; i++) W(pl.o_tm, i) = 1.0 / sqrt(limit_scaling(W(pl.o_tm, i)));
+    // P <- D P D, A <- E A D, q <- D q
+    for (int j = 0; j < n; j++) {
+      const double dj = W(pl.o_tn, j);
+      for (int p = QP_LDG(pl.Pp + j); p < QP_LDG(pl.Pp + j + 1); p++) {
+        double v = W(pl.o_Px, p) * W(pl.o_tn, QP_LDG(pl.Pi + p));
+        W(pl.o_Px, p) = v * dj;
+      }
+      for (int p = QP_LDG(pl.Ap + j); p < QP_LDG(pl.Ap + j + 1); p++) {
+        double v = W(pl.o_Ax, p) * W(pl.o_tm, QP_LDG(pl.Ai + p));
+        W(pl.o_Ax, p) = v * dj;
+      }
+      W(pl.o_q, j) = W(pl.o_q, j) * dj;
+      W(pl.o_D, j) = W(pl.o_D, j) * dj;
+    }
+    for (int i = 0; i < m; i++) W(pl.o_E, i) = W(pl.o_E, i) * W(pl.o_tm, i);
+    // cost normalisation
+    double sum = 0.0;
+    for (int j = 0; j < n; j++) {
+      double dn = 0.0;
+      for (int p = QP_LDG(pl.Pp + j); p < QP_LDG(pl.Pp + j + 1); p++) dn = fmax(fabs(W(pl.o_Px, p)), dn);
+      sum += fabs(dn);
+    }
+    double c_temp = sum / n;
+    double inf_q = limit_scaling(qp_norm_inf(ws, stride, b, pl.o_q, n));
+    c_temp = fmax(c_temp, inf_q);
+    c_temp = limit_scaling(c_temp);
+    c_temp = 1.0 / c_temp;
+    for (int p = 0; p < pl.nnzP; p++) W(pl.o_Px, p) = W(pl.o_Px, p) * c_temp;
+    for (int j = 0; j < n; j++) W(pl.o_q, j) = W(pl.o_q, j) * c_temp;
+    c *= c_temp;
+  }
+  const double cinv = 1.0 / c;
+  for (int j = 0; j < n; j++) W(pl.o_Dinv, j) = 1.0 / W(pl.o_D, j);
+  for (int i = 0; i < m; i++) {
+    const double e = W(pl.o_E, i);
+    W(pl.o_Einv, i) = 1.0 / e;
+    W(pl.o_l, i) = W(pl.o_l, i) * e;
+    W(pl.o_u, i) = W(pl.o_u, i) * e;
+  }
+
+  // ---- set_rho_vec (auxil.c:75-104) ----------------------------------------------------------------------------------
+  double rho = fmin(fmax(S.rho, OSQP_RHO_MIN_), OSQP_RHO_MAX_);
+  auto set_rho = [&](double rho_) {
+    for (int i = 0; i < m; i++) {
+      const double l = W(pl.o_l, i), u = W(pl.o_u, i);
+      double r;
+      if (l < -OSQP_INFTY_ * OSQP_MIN_SCALING_ && u > OSQP_INFTY_ * OSQP_MIN_SCALING_) r = OSQP_RHO_MIN_;
+      else if (u - l < OSQP_RHO_TOL_) r = OSQP_RHO_EQ_OVER_RHO_INEQ_ * rho_;
+      else r = rho_;
+      W(pl.o_rho, i) = r;
+      W(pl.o_rhoinv, i) = 1.0 / r;
+    }
+  };
+  set_rho(rho);
+
+  int status = ST_UNSOLVED, iter_out = 0;
+  // the factorisation's scatter vector must start at zero (QDLDL_factor clears yVals the same way); the workspace is
+  // reused across batches and is NOT zeroed by the host
+  for (int i = 0; i < pl.N; i++) W(pl.o_yw, i) = 0.0;
+  // ---- KKT factorisation (init_linsys_solver_qdldl) -----------------------------------------------------------------------
+  if (qp_factor(pl, ws, stride, b, S.sigma) < n) status = ST_NONCVX;  // osqp_setup fails: OSQP_NONCVX_ERROR
+
+  if (status == ST_UNSOLVED) {
+    for (int i = 0; i < n; i++) { W(pl.o_x, i) = 0.0; W(pl.o_xprev, i) = 0.0; }
+    for (int i = 0; i < m; i++) { W(pl.o_z, i) = 0.0; W(pl.o_zprev, i) = 0.0; W(pl.o_y, i) = 0.0; }
+    const int interval = S.adaptive_rho_interval ? S.adaptive_rho_interval
+                                                 : (S.check_termination ? 4 * S.check_termination : 100);
+    const double alpha = S.alpha, sigma = S.sigma, one_m_alpha = 1.0 - S.alpha;
+    QpResid R;
+    R.prim_res = R.dual_res = R.scaled_prim = R.scaled_dual = OSQP_INFTY_;
+    bool checked_last = false;
+    int iter;
+    for (iter = 1; iter <= S.max_iter; iter++) {
+      // x_prev <- x, z_prev <- z (the reference swaps pointers; x and z are fully overwritten below)
+      // compute_rhs (auxil.c:135-157)
+      for (int i = 0; i < n; i++) {
+        const double xv = W(pl.o_x, i);
+        W(pl.o_xprev, i) = xv;
+        W(pl.o_xz, i) = sigma * xv + (-1.0) * W(pl.o_q, i);
+      }
+      for (int i = 0; i < m; i++) {
+        const double zv = W(pl.o_z, i);
+        W(pl.o_zprev, i) = zv;
+        const double t = W(pl.o_rhoinv, i) * W(pl.o_y, i);
+        W(pl.o_xz, n + i) = (-1.0) * t + 1.0 * zv;
+      }
+      // keep the right-hand side of the z block: ztilde = rhs_z + rho^-1 * nu  (qdldl_interface.c:447-450)
+      for (int i = 0; i < m; i++) W(pl.o_tm, i) = W(pl.o_xz, n + i);
+      qp_kkt_solve(pl, ws, stride, b);
+      for (int i = 0; i < m; i++) W(pl.o_xz, n + i) = W(pl.o_tm, i) + W(pl.o_rhoinv, i) * W(pl.o_xz, n + i);
+      // update_x, update_z, update_y (auxil.c:171-228)
+      for (int i = 0; i < n; i++) {
+        const double xp = W(pl.o_xprev, i);
+        const double xn = alpha * W(pl.o_xz, i) + one_m_alpha * xp;
+        W(pl.o_x, i) = xn;
+        W(pl.o_dx, i) = xn - xp;
+      }
+      for (int i = 0; i < m; i++) {
+        const double zt = W(pl.o_xz, n + i), zp = W(pl.o_zprev, i), yv = W(pl.o_y, i);
+        double zn = W(pl.o_rhoinv, i) * yv;
+        zn = (1.0 * zn + alpha * zt) + one_m_alpha * zp;
+        zn = fmin(fmax(zn, W(pl.o_l, i)), W(pl.o_u, i));
+        W(pl.o_z, i) = zn;
+        double dy = (alpha * zt + one_m_alpha * zp) + (-1.0) * zn;
+        dy = dy * W(pl.o_rho, i);
+        W(pl.o_dy, i) = dy;
+        W(pl.o_y, i) = yv + dy;
+      }
+      const bool can_check = S.check_termination && (iter % S.check_termination == 0);
+      checked_last = can_check;
+      if (can_check) {
+        qp_update_info(pl, ws, stride, b, cinv, R);
+        iter_out = iter;
+        int st = qp_check_termination(pl, ws, stride, b, S, c, cinv, R, false);
+        if (st) { status = st; break; }
+      }
+      if (S.adaptive_rho && interval && (iter % interval == 0)) {
+        if (!can_check) { qp_update_info(pl, ws, stride, b, cinv, R); iter_out = iter; }
+        // compute_rho_estimate + adapt_rho (auxil.c:14-73)
+        double pr = R.scaled_prim, dr = R.scaled_dual;
+        double pn = fmax(qp_norm_inf(ws, stride, b, pl.o_z, m), qp_norm_inf(ws, stride, b, pl.o_Axv, m));
+        pr /= (pn + OSQP_DIVISION_TOL_);
+        double dn = fmax(fmax(qp_norm_inf(ws, stride, b, pl.o_q, n), qp_norm_inf(ws, stride, b, pl.o_Aty, n)),
+                         qp_norm_inf(ws, stride, b, pl.o_Pxv, n));
+        dr /= (dn + OSQP_DIVISION_TOL_);
+        double rho_new = rho * sqrt(pr / dr);
+        rho_new = fmin(fmax(rho_new, OSQP_RHO_MIN_), OSQP_RHO_MAX_);
+        if (rho_new > rho * S.adaptive_rho_tolerance || rho_new < rho / S.adaptive_rho_tolerance) {
+          rho = fmin(fmax(rho_new, OSQP_RHO_MIN_), OSQP_RHO_MAX_);  // osqp_update_rho (osqp_api.c:1178-1228)
+          for (int i = 0; i < m; i++) {
+            // constraint classes were fixed at setup (work->constr_type)
+            const double l = W(pl.o_l, i), u = W(pl.o_u, i);
+            double r;
+            if (l < -OSQP_INFTY_ * OSQP_MIN_SCALING_ && u > OSQP_INFTY_ * OSQP_MIN_SCALING_) r = OSQP_RHO_MIN_;
+            else if (u - l < OSQP_RHO_TOL_) r = OSQP_RHO_EQ_OVER_RHO_INEQ_ * rho;
+            else r = rho;
+            W(pl.o_rho, i) = r;
+            W(pl.o_rhoinv, i) = 1.0 / r;
+          }
+          if (qp_factor(pl, ws, stride, b, sigma) < 0) { status = ST_NONCVX; break; }
+        }
+      }
+    }
+    if (status == ST_UNSOLVED) {
+      // osqp_api.c:686-731: loop ran out
+      if (!checked_last) {
+        qp_update_info(pl, ws, stride, b, cinv, R);
+        iter_out = iter - 1;
+        int st = qp_check_termination(pl, ws, stride, b, S, c, cinv, R, false);
+        if (st) status = st;
+      }
+      if (status == ST_UNSOLVED) {
+        int st = qp_check_termination(pl, ws, stride, b, S, c, cinv, R, true);
+        status = st ? st : ST_MAXITER;
+      }
+    }
+  }
+
+  // ---- store_solution (auxil.c:537-613): x = D x_scaled, NaN when there is no solution -------------------------------
+  const bool has_sol = !(status == ST_PINF || status == ST_PINF_INACC || status == ST_DINF || status == ST_DINF_INACC ||
+                         status == ST_NONCVX);
+  double* out = io.coef + (size_t)b * n;
+  for (int i = 0; i < n; i++) out[i] = has_sol ? W(pl.o_D, i) * W(pl.o_x, i) : fpm::from_bits(0x7ff8000000000000ull);
+  io.status[b] = status;
+  io.iters[b] = iter_out;
+  io.solved[b] = (status == ST_SOLVED) ? 1 : 0;  // OsqpEigen::Solver::solve is true only for OSQP_SOLVED
+  (void)nc;
+}
+
+#undef W

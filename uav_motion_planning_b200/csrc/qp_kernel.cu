@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "fpmath.h"
+#include "qp_body.h"
 #include "qp_plan.h"
 #include "uavmp_internal.h"
 
@@ -37,442 +38,10 @@ struct QpPlan {
 
 namespace {
 
-#define OSQP_INFTY_ 1e30
-#define OSQP_MIN_SCALING_ 1e-4
-#define OSQP_MAX_SCALING_ 1e4
-#define OSQP_RHO_MIN_ 1e-6
-#define OSQP_RHO_MAX_ 1e6
-#define OSQP_RHO_TOL_ 1e-4
-#define OSQP_RHO_EQ_OVER_RHO_INEQ_ 1e3
-#define OSQP_DIVISION_TOL_ (1.0 / OSQP_INFTY_)
-
-enum { ST_SOLVED = 1, ST_SOLVED_INACC = 2, ST_PINF = 3, ST_PINF_INACC = 4, ST_DINF = 5, ST_DINF_INACC = 6,
-       ST_MAXITER = 7, ST_NONCVX = 9, ST_UNSOLVED = 11 };
-
-struct QpIo {
-  const double* pos; const double* bv; const double* ba; const double* bj; const double* T;
-  double* coef; int* solved; int* status; int* iters;
-  int B, stride;
-};
-
-__device__ __forceinline__ double limit_scaling(double v) {
-  v = v < OSQP_MIN_SCALING_ ? 1.0 : v;
-  v = v > OSQP_MAX_SCALING_ ? OSQP_MAX_SCALING_ : v;
-  return v;
-}
-
-#define W(off, i) ws[((size_t)((off) + (i))) * stride + b]
-
-// numeric LDL' of the permuted KKT matrix (up-looking, static reach lists) — QDLDL_factor's arithmetic
-__device__ int qp_factor(const QpPlanDev& pl, double* ws, size_t stride, int b, double sigma) {
-  const int N = pl.N;
-  int positive = 0;
-  for (int k = 0; k < N; k++) {
-    double Dk = 0.0;
-    for (int p = __ldg(pl.Kp + k); p < __ldg(pl.Kp + k + 1); p++) {
-      const int i = __ldg(pl.Ki + p), kind = __ldg(pl.Kkind + p), idx = __ldg(pl.Kidx + p);
-      double v;
-      if (kind == 0) v = W(pl.o_Px, idx);
-      else if (kind == 1) v = W(pl.o_Px, idx) + sigma;
-      else if (kind == 2) v = sigma;
-      else if (kind == 3) v = W(pl.o_Ax, idx);
-      else v = -W(pl.o_rhoinv, idx);
-      if (i == k) Dk = v; else W(pl.o_yw, i) = v;
-    }
-    for (int e = __ldg(pl.Rp + k); e < __ldg(pl.Rp + k + 1); e++) {
-      const int c = __ldg(pl.Rc + e), pos = __ldg(pl.Rpos + e);
-      const double yc = W(pl.o_yw, c);
-      for (int j = __ldg(pl.Lp + c); j < pos; j++) {
-        const int r = __ldg(pl.Li + j);
-        W(pl.o_yw, r) = W(pl.o_yw, r) - W(pl.o_Lx, j) * yc;
-      }
-      const double lv = yc * W(pl.o_Ddinv, c);
-      W(pl.o_Lx, pos) = lv;
-      Dk -= yc * lv;
-      W(pl.o_yw, c) = 0.0;
-    }
-    if (Dk == 0.0) return -1;
-    if (Dk > 0.0) positive++;
-    W(pl.o_Dd, k) = Dk;
-    W(pl.o_Ddinv, k) = 1.0 / Dk;
-  }
-  return positive;
-}
-
-// xz <- K^-1 xz  (qdldl_interface.c:394-415: permute, L solve, D^-1, L' solve, permute back)
-__device__ void qp_kkt_solve(const QpPlanDev& pl, double* ws, size_t stride, int b) {
-  const int N = pl.N;
-  for (int j = 0; j < N; j++) W(pl.o_bp, j) = W(pl.o_xz, __ldg(pl.perm + j));
-  for (int i = 0; i < N; i++) {
-    const double val = W(pl.o_bp, i);
-    for (int j = __ldg(pl.Lp + i); j < __ldg(pl.Lp + i + 1); j++) {
-      const int r = __ldg(pl.Li + j);
-      W(pl.o_bp, r) = W(pl.o_bp, r) - W(pl.o_Lx, j) * val;
-    }
-  }
-  for (int i = 0; i < N; i++) W(pl.o_bp, i) = W(pl.o_bp, i) * W(pl.o_Ddinv, i);
-  for (int i = N - 1; i >= 0; i--) {
-    double val = W(pl.o_bp, i);
-    for (int j = __ldg(pl.Lp + i); j < __ldg(pl.Lp + i + 1); j++) val -= W(pl.o_Lx, j) * W(pl.o_bp, __ldg(pl.Li + j));
-    W(pl.o_bp, i) = val;
-  }
-  for (int j = 0; j < N; j++) W(pl.o_xz, __ldg(pl.perm + j)) = W(pl.o_bp, j);
-}
-
-// out(m) = A * v(n)
-__device__ void qp_A_mul(const QpPlanDev& pl, double* ws, size_t stride, int b, int o_v, int o_out) {
-  for (int i = 0; i < pl.m; i++) W(o_out, i) = 0.0;
-  for (int c = 0; c < pl.n; c++) {
-    const double vc = W(o_v, c);
-    for (int p = __ldg(pl.Ap + c); p < __ldg(pl.Ap + c + 1); p++) {
-      const int r = __ldg(pl.Ai + p);
-      W(o_out, r) = W(o_out, r) + W(pl.o_Ax, p) * vc;
-    }
-  }
-}
-// out(n) = A' * v(m)
-__device__ void qp_At_mul(const QpPlanDev& pl, double* ws, size_t stride, int b, int o_v, int o_out) {
-  for (int c = 0; c < pl.n; c++) {
-    double acc = 0.0;
-    for (int p = __ldg(pl.Ap + c); p < __ldg(pl.Ap + c + 1); p++) acc += W(pl.o_Ax, p) * W(o_v, __ldg(pl.Ai + p));
-    W(o_out, c) = acc;
-  }
-}
-// out(n) = P * v(n), P stored as its upper triangle
-__device__ void qp_P_mul(const QpPlanDev& pl, double* ws, size_t stride, int b, int o_v, int o_out) {
-  for (int i = 0; i < pl.n; i++) W(o_out, i) = 0.0;
-  for (int c = 0; c < pl.n; c++) {
-    const double vc = W(o_v, c);
-    for (int p = __ldg(pl.Pp + c); p < __ldg(pl.Pp + c + 1); p++) {
-      const int r = __ldg(pl.Pi + p);
-      const double a = W(pl.o_Px, p);
-      W(o_out, r) = W(o_out, r) + a * vc;
-      if (r != c) W(o_out, c) = W(o_out, c) + a * W(o_v, r);
-    }
-  }
-}
-__device__ double qp_norm_inf(double* ws, size_t stride, int b, int o_v, int len) {
-  double r = 0.0;
-  for (int i = 0; i < len; i++) r = fmax(r, fabs(W(o_v, i)));
-  return r;
-}
-__device__ double qp_scaled_norm_inf(double* ws, size_t stride, int b, int o_s, int o_v, int len) {
-  double r = 0.0;
-  for (int i = 0; i < len; i++) r = fmax(r, fabs(W(o_s, i) * W(o_v, i)));
-  return r;
-}
-
-struct QpResid {
-  double prim_res, dual_res, scaled_prim, scaled_dual;
-};
-
-// update_info (auxil.c:615-690): residuals of (x, z, y); leaves Ax, Px, A'y in the workspace
-__device__ void qp_update_info(const QpPlanDev& pl, double* ws, size_t stride, int b, double cinv, QpResid& R) {
-  const int n = pl.n, m = pl.m;
-  qp_A_mul(pl, ws, stride, b, pl.o_x, pl.o_Axv);
-  double sp = 0.0, up = 0.0;
-  for (int i = 0; i < m; i++) {
-    const double d = W(pl.o_Axv, i) - W(pl.o_z, i);
-    sp = fmax(sp, fabs(d));
-    up = fmax(up, fabs(W(pl.o_Einv, i) * d));
-  }
-  R.scaled_prim = sp; R.prim_res = up;
-  qp_P_mul(pl, ws, stride, b, pl.o_x, pl.o_Pxv);
-  qp_At_mul(pl, ws, stride, b, pl.o_y, pl.o_Aty);
-  double sd = 0.0, ud = 0.0;
-  for (int i = 0; i < n; i++) {
-    const double d = (W(pl.o_q, i) + W(pl.o_Pxv, i)) + W(pl.o_Aty, i);
-    sd = fmax(sd, fabs(d));
-    ud = fmax(ud, fabs(W(pl.o_Dinv, i) * d));
-  }
-  R.scaled_dual = sd; R.dual_res = cinv * ud;
-}
-
-// check_termination (auxil.c:736-851).  Returns the new status or 0.
-__device__ int qp_check_termination(const QpPlanDev& pl, double* ws, size_t stride, int b, const uavmp_osqp_settings& S,
-                                    double c, double cinv, const QpResid& R, bool approximate) {
-  const int n = pl.n, m = pl.m;
-  double eps_abs = S.eps_abs, eps_rel = S.eps_rel, eps_pinf = S.eps_prim_inf, eps_dinf = S.eps_dual_inf;
-  if (R.prim_res > OSQP_INFTY_ || R.dual_res > OSQP_INFTY_) return ST_NONCVX;
-  if (approximate) { eps_abs *= 10; eps_rel *= 10; eps_pinf *= 10; eps_dinf *= 10; }
-  bool prim_ok = false, dual_ok = false, pinf = false, dinf = false;
-  {
-    double mx = fmax(qp_scaled_norm_inf(ws, stride, b, pl.o_Einv, pl.o_z, m),
-                     qp_scaled_norm_inf(ws, stride, b, pl.o_Einv, pl.o_Axv, m));
-    const double eps_prim = eps_abs + eps_rel * mx;
-    if (R.prim_res < eps_prim) {
-      prim_ok = true;
-    } else {
-      // is_primal_infeasible (auxil.c:399-448); bounds are finite here so the polar-cone projection is the identity
-      for (int i = 0; i < m; i++) {
-        const double l = W(pl.o_l, i), u = W(pl.o_u, i);
-        double dy = W(pl.o_dy, i);
-        if (u > OSQP_INFTY_ * OSQP_MIN_SCALING_) {
-          if (l < -OSQP_INFTY_ * OSQP_MIN_SCALING_) dy = 0.0; else dy = fmin(dy, 0.0);
-        } else if (l < -OSQP_INFTY_ * OSQP_MIN_SCALING_) {
-          dy = fmax(dy, 0.0);
-        }
-        W(pl.o_dy, i) = dy;
-      }
-      const double norm_dy = qp_scaled_norm_inf(ws, stride, b, pl.o_E, pl.o_dy, m);
-      if (norm_dy > OSQP_DIVISION_TOL_) {
-        double lhs = 0.0, lhs2 = 0.0;
-        for (int i = 0; i < m; i++) { const double dy = W(pl.o_dy, i); lhs += W(pl.o_u, i) * fmax(dy, 0.0); }
-        for (int i = 0; i < m; i++) { const double dy = W(pl.o_dy, i); lhs2 += W(pl.o_l, i) * fmin(dy, 0.0); }
-        lhs += lhs2;
-        if (lhs < 0.0) {
-          qp_At_mul(pl, ws, stride, b, pl.o_dy, pl.o_tn);
-          pinf = qp_scaled_norm_inf(ws, stride, b, pl.o_Dinv, pl.o_tn, n) < eps_pinf * norm_dy;
-        }
-      }
-    }
-  }
-  {
-    double mx = fmax(fmax(qp_scaled_norm_inf(ws, stride, b, pl.o_Dinv, pl.o_q, n),
-                          qp_scaled_norm_inf(ws, stride, b, pl.o_Dinv, pl.o_Aty, n)),
-                     qp_scaled_norm_inf(ws, stride, b, pl.o_Dinv, pl.o_Pxv, n));
-    mx *= cinv;
-    const double eps_dual = eps_abs + eps_rel * mx;
-    if (R.dual_res < eps_dual) {
-      dual_ok = true;
-    } else {
-      // is_dual_infeasible (auxil.c:450-528)
-      const double norm_dx = qp_scaled_norm_inf(ws, stride, b, pl.o_D, pl.o_dx, n);
-      if (norm_dx > OSQP_DIVISION_TOL_) {
-        double qdx = 0.0;
-        for (int i = 0; i < n; i++) qdx += W(pl.o_q, i) * W(pl.o_dx, i);
-        if (qdx < 0.0) {
-          qp_P_mul(pl, ws, stride, b, pl.o_dx, pl.o_tn);
-          if (qp_scaled_norm_inf(ws, stride, b, pl.o_Dinv, pl.o_tn, n) < c * eps_dinf * norm_dx) {
-            qp_A_mul(pl, ws, stride, b, pl.o_dx, pl.o_tm);
-            bool in_cone = true;
-            const double tol = eps_dinf * norm_dx;
-            for (int i = 0; i < m; i++) {
-              const double v = W(pl.o_Einv, i) * W(pl.o_tm, i);
-              if ((W(pl.o_u, i) < OSQP_INFTY_ * OSQP_MIN_SCALING_ && v > tol) ||
-                  (W(pl.o_l, i) > -OSQP_INFTY_ * OSQP_MIN_SCALING_ && v < -tol)) { in_cone = false; break; }
-            }
-            dinf = in_cone;
-          }
-        }
-      }
-    }
-  }
-  if (prim_ok && dual_ok) return approximate ? ST_SOLVED_INACC : ST_SOLVED;
-  if (pinf) return approximate ? ST_PINF_INACC : ST_PINF;
-  if (dinf) return approximate ? ST_DINF_INACC : ST_DINF;
-  return 0;
-}
-
 __global__ void __launch_bounds__(128) qp_solve_kernel(QpPlanDev pl, QpIo io, uavmp_osqp_settings S, double* ws) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= io.B) return;
-  const size_t stride = (size_t)io.stride;
-  const int n = pl.n, m = pl.m, Sg = pl.S, nc = pl.nc;
-
-  // ---- assembly: P, q, A, l, u (minimum_control.cpp:5-125) ---------------------------------------------------
-  const double* T = io.T + (size_t)b * Sg;
-  for (int p = 0; p < pl.nnzP; p++) W(pl.o_Px, p) = __ldg(pl.P_coef + p) * fpm::powi(T[__ldg(pl.P_seg + p)], __ldg(pl.P_pow + p));
-  for (int p = 0; p < pl.nnzA; p++) W(pl.o_Ax, p) = __ldg(pl.A_coef + p) * fpm::powi(T[__ldg(pl.A_seg + p)], __ldg(pl.A_pow + p));
-  for (int i = 0; i < n; i++) W(pl.o_q, i) = 0.0;
-  for (int i = 0; i < m; i++) {
-    const int src = __ldg(pl.l_src + i);
-    double v = 0.0;
-    if (src >= 0) {
-      if (src <= Sg) v = io.pos[(size_t)b * (Sg + 1) + src];
-      else {
-        const int r = (src - (Sg + 1)) >> 1, e = (src - (Sg + 1)) & 1;
-        v = (r == 0 ? io.bv : (r == 1 ? io.ba : io.bj))[(size_t)b * 2 + e];
-      }
-    }
-    W(pl.o_l, i) = v;
-    W(pl.o_u, i) = v;
-  }
-
-  // ---- scale_data (scaling.c:49-165) ----------------------------------------------------------------------------
-  double c = 1.0;
-  for (int i = 0; i < n; i++) W(pl.o_D, i) = 1.0;
-  for (int i = 0; i < m; i++) W(pl.o_E, i) = 1.0;
-  for (int it = 0; it < S.scaling; it++) {
-    // column inf-norms of [P; A] — P's stored upper triangle only (csc_col_norm_inf ignores symmetry) — and rows of A
-    for (int j = 0; j < n; j++) {
-      double dn = 0.0;
-      for (int p = __ldg(pl.Pp + j); p < __ldg(pl.Pp + j + 1); p++) dn = fmax(fabs(W(pl.o_Px, p)), dn);
-      double an = 0.0;
-      for (int p = __ldg(pl.Ap + j); p < __ldg(pl.Ap + j + 1); p++) an = fmax(fabs(W(pl.o_Ax, p)), an);
-      W(pl.o_tn, j) = fmax(dn, an);
-    }
-    for (int i = 0; i < m; i++) W(pl.o_tm, i) = 0.0;
-    for (int p = 0; p < pl.nnzA; p++) {
-      const int r = __ldg(pl.Ai + p);
-      W(pl.o_tm, r) = fmax(fabs(W(pl.o_Ax, p)), W(pl.o_tm, r));
-    }
-    for (int j = 0; j < n; j++) W(pl.o_tn, j) = 1.0 / sqrt(limit_scaling(W(pl.o_tn, j)));
-    for (int i = 0; i < m; i++) W(pl.o_tm, i) = 1.0 / sqrt(limit_scaling(W(pl.o_tm, i)));
-    // P <- D P D, A <- E A D, q <- D q
-    for (int j = 0; j < n; j++) {
-      const double dj = W(pl.o_tn, j);
-      for (int p = __ldg(pl.Pp + j); p < __ldg(pl.Pp + j + 1); p++) {
-        double v = W(pl.o_Px, p) * W(pl.o_tn, __ldg(pl.Pi + p));
-        W(pl.o_Px, p) = v * dj;
-      }
-      for (int p = __ldg(pl.Ap + j); p < __ldg(pl.Ap + j + 1); p++) {
-        double v = W(pl.o_Ax, p) * W(pl.o_tm, __ldg(pl.Ai + p));
-        W(pl.o_Ax, p) = v * dj;
-      }
-      W(pl.o_q, j) = W(pl.o_q, j) * dj;
-      W(pl.o_D, j) = W(pl.o_D, j) * dj;
-    }
-    for (int i = 0; i < m; i++) W(pl.o_E, i) = W(pl.o_E, i) * W(pl.o_tm, i);
-    // cost normalisation
-    double sum = 0.0;
-    for (int j = 0; j < n; j++) {
-      double dn = 0.0;
-      for (int p = __ldg(pl.Pp + j); p < __ldg(pl.Pp + j + 1); p++) dn = fmax(fabs(W(pl.o_Px, p)), dn);
-      sum += fabs(dn);
-    }
-    double c_temp = sum / n;
-    double inf_q = limit_scaling(qp_norm_inf(ws, stride, b, pl.o_q, n));
-    c_temp = fmax(c_temp, inf_q);
-    c_temp = limit_scaling(c_temp);
-    c_temp = 1.0 / c_temp;
-    for (int p = 0; p < pl.nnzP; p++) W(pl.o_Px, p) = W(pl.o_Px, p) * c_temp;
-    for (int j = 0; j < n; j++) W(pl.o_q, j) = W(pl.o_q, j) * c_temp;
-    c *= c_temp;
-  }
-  const double cinv = 1.0 / c;
-  for (int j = 0; j < n; j++) W(pl.o_Dinv, j) = 1.0 / W(pl.o_D, j);
-  for (int i = 0; i < m; i++) {
-    const double e = W(pl.o_E, i);
-    W(pl.o_Einv, i) = 1.0 / e;
-    W(pl.o_l, i) = W(pl.o_l, i) * e;
-    W(pl.o_u, i) = W(pl.o_u, i) * e;
-  }
-
-  // ---- set_rho_vec (auxil.c:75-104) ----------------------------------------------------------------------------------
-  double rho = fmin(fmax(S.rho, OSQP_RHO_MIN_), OSQP_RHO_MAX_);
-  auto set_rho = [&](double rho_) {
-    for (int i = 0; i < m; i++) {
-      const double l = W(pl.o_l, i), u = W(pl.o_u, i);
-      double r;
-      if (l < -OSQP_INFTY_ * OSQP_MIN_SCALING_ && u > OSQP_INFTY_ * OSQP_MIN_SCALING_) r = OSQP_RHO_MIN_;
-      else if (u - l < OSQP_RHO_TOL_) r = OSQP_RHO_EQ_OVER_RHO_INEQ_ * rho_;
-      else r = rho_;
-      W(pl.o_rho, i) = r;
-      W(pl.o_rhoinv, i) = 1.0 / r;
-    }
-  };
-  set_rho(rho);
-
-  int status = ST_UNSOLVED, iter_out = 0;
-  // ---- KKT factorisation (init_linsys_solver_qdldl) -----------------------------------------------------------------------
-  if (qp_factor(pl, ws, stride, b, S.sigma) < n) status = ST_NONCVX;  // osqp_setup fails: OSQP_NONCVX_ERROR
-
-  if (status == ST_UNSOLVED) {
-    for (int i = 0; i < n; i++) { W(pl.o_x, i) = 0.0; W(pl.o_xprev, i) = 0.0; }
-    for (int i = 0; i < m; i++) { W(pl.o_z, i) = 0.0; W(pl.o_zprev, i) = 0.0; W(pl.o_y, i) = 0.0; }
-    const int interval = S.adaptive_rho_interval ? S.adaptive_rho_interval
-                                                 : (S.check_termination ? 4 * S.check_termination : 100);
-    const double alpha = S.alpha, sigma = S.sigma, one_m_alpha = 1.0 - S.alpha;
-    QpResid R;
-    R.prim_res = R.dual_res = R.scaled_prim = R.scaled_dual = OSQP_INFTY_;
-    bool checked_last = false;
-    int iter;
-    for (iter = 1; iter <= S.max_iter; iter++) {
-      // x_prev <- x, z_prev <- z (the reference swaps pointers; x and z are fully overwritten below)
-      // compute_rhs (auxil.c:135-157)
-      for (int i = 0; i < n; i++) {
-        const double xv = W(pl.o_x, i);
-        W(pl.o_xprev, i) = xv;
-        W(pl.o_xz, i) = sigma * xv + (-1.0) * W(pl.o_q, i);
-      }
-      for (int i = 0; i < m; i++) {
-        const double zv = W(pl.o_z, i);
-        W(pl.o_zprev, i) = zv;
-        const double t = W(pl.o_rhoinv, i) * W(pl.o_y, i);
-        W(pl.o_xz, n + i) = (-1.0) * t + 1.0 * zv;
-      }
-      // keep the right-hand side of the z block: ztilde = rhs_z + rho^-1 * nu  (qdldl_interface.c:447-450)
-      for (int i = 0; i < m; i++) W(pl.o_tm, i) = W(pl.o_xz, n + i);
-      qp_kkt_solve(pl, ws, stride, b);
-      for (int i = 0; i < m; i++) W(pl.o_xz, n + i) = W(pl.o_tm, i) + W(pl.o_rhoinv, i) * W(pl.o_xz, n + i);
-      // update_x, update_z, update_y (auxil.c:171-228)
-      for (int i = 0; i < n; i++) {
-        const double xp = W(pl.o_xprev, i);
-        const double xn = alpha * W(pl.o_xz, i) + one_m_alpha * xp;
-        W(pl.o_x, i) = xn;
-        W(pl.o_dx, i) = xn - xp;
-      }
-      for (int i = 0; i < m; i++) {
-        const double zt = W(pl.o_xz, n + i), zp = W(pl.o_zprev, i), yv = W(pl.o_y, i);
-        double zn = W(pl.o_rhoinv, i) * yv;
-        zn = (1.0 * zn + alpha * zt) + one_m_alpha * zp;
-        zn = fmin(fmax(zn, W(pl.o_l, i)), W(pl.o_u, i));
-        W(pl.o_z, i) = zn;
-        double dy = (alpha * zt + one_m_alpha * zp) + (-1.0) * zn;
-        dy = dy * W(pl.o_rho, i);
-        W(pl.o_dy, i) = dy;
-        W(pl.o_y, i) = yv + dy;
-      }
-      const bool can_check = S.check_termination && (iter % S.check_termination == 0);
-      checked_last = can_check;
-      if (can_check) {
-        qp_update_info(pl, ws, stride, b, cinv, R);
-        iter_out = iter;
-        int st = qp_check_termination(pl, ws, stride, b, S, c, cinv, R, false);
-        if (st) { status = st; break; }
-      }
-      if (S.adaptive_rho && interval && (iter % interval == 0)) {
-        if (!can_check) { qp_update_info(pl, ws, stride, b, cinv, R); iter_out = iter; }
-        // compute_rho_estimate + adapt_rho (auxil.c:14-73)
-        double pr = R.scaled_prim, dr = R.scaled_dual;
-        double pn = fmax(qp_norm_inf(ws, stride, b, pl.o_z, m), qp_norm_inf(ws, stride, b, pl.o_Axv, m));
-        pr /= (pn + OSQP_DIVISION_TOL_);
-        double dn = fmax(fmax(qp_norm_inf(ws, stride, b, pl.o_q, n), qp_norm_inf(ws, stride, b, pl.o_Aty, n)),
-                         qp_norm_inf(ws, stride, b, pl.o_Pxv, n));
-        dr /= (dn + OSQP_DIVISION_TOL_);
-        double rho_new = rho * sqrt(pr / dr);
-        rho_new = fmin(fmax(rho_new, OSQP_RHO_MIN_), OSQP_RHO_MAX_);
-        if (rho_new > rho * S.adaptive_rho_tolerance || rho_new < rho / S.adaptive_rho_tolerance) {
-          rho = fmin(fmax(rho_new, OSQP_RHO_MIN_), OSQP_RHO_MAX_);  // osqp_update_rho (osqp_api.c:1178-1228)
-          for (int i = 0; i < m; i++) {
-            // constraint classes were fixed at setup (work->constr_type)
-            const double l = W(pl.o_l, i), u = W(pl.o_u, i);
-            double r;
-            if (l < -OSQP_INFTY_ * OSQP_MIN_SCALING_ && u > OSQP_INFTY_ * OSQP_MIN_SCALING_) r = OSQP_RHO_MIN_;
-            else if (u - l < OSQP_RHO_TOL_) r = OSQP_RHO_EQ_OVER_RHO_INEQ_ * rho;
-            else r = rho;
-            W(pl.o_rho, i) = r;
-            W(pl.o_rhoinv, i) = 1.0 / r;
-          }
-          if (qp_factor(pl, ws, stride, b, sigma) < 0) { status = ST_NONCVX; break; }
-        }
-      }
-    }
-    if (status == ST_UNSOLVED) {
-      // osqp_api.c:686-731: loop ran out
-      if (!checked_last) {
-        qp_update_info(pl, ws, stride, b, cinv, R);
-        iter_out = iter - 1;
-        int st = qp_check_termination(pl, ws, stride, b, S, c, cinv, R, false);
-        if (st) status = st;
-      }
-      if (status == ST_UNSOLVED) {
-        int st = qp_check_termination(pl, ws, stride, b, S, c, cinv, R, true);
-        status = st ? st : ST_MAXITER;
-      }
-    }
-  }
-
-  // ---- store_solution (auxil.c:537-613): x = D x_scaled, NaN when there is no solution -------------------------------
-  const bool has_sol = !(status == ST_PINF || status == ST_PINF_INACC || status == ST_DINF || status == ST_DINF_INACC ||
-                         status == ST_NONCVX);
-  double* out = io.coef + (size_t)b * n;
-  for (int i = 0; i < n; i++) out[i] = has_sol ? W(pl.o_D, i) * W(pl.o_x, i) : __longlong_as_double(0x7ff8000000000000ll);
-  io.status[b] = status;
-  io.iters[b] = iter_out;
-  io.solved[b] = (status == ST_SOLVED) ? 1 : 0;  // OsqpEigen::Solver::solve is true only for OSQP_SOLVED
-  (void)nc;
+  qp_solve_one(pl, io, S, ws, b);
 }
 
 // ---- pipeline glue: waypoints from the searched paths, outputs back to per-plan layout --------------------------------------
@@ -524,37 +93,15 @@ static QpPlan* get_plan(uavmp_ctx* ctx, int order, int S) {
   p->host = qp_plan_build(order, S);
   const QpPlanHost& H = *p->host;
   std::vector<int> ints;
-  auto push = [&](const std::vector<int>& v) { size_t o = ints.size(); ints.insert(ints.end(), v.begin(), v.end()); return o; };
-  size_t oPp = push(H.Pp), oPi = push(H.Pi), oPs = push(H.P_seg), oPw = push(H.P_pow);
-  size_t oAp = push(H.Ap), oAi = push(H.Ai), oAs = push(H.A_seg), oAw = push(H.A_pow);
-  size_t oL = push(H.l_src), oPerm = push(H.perm), oKp = push(H.Kp), oKi = push(H.Ki), oKk = push(H.Kkind),
-         oKx = push(H.Kidx), oLp = push(H.Lp), oLi = push(H.Li), oRp = push(H.Rp), oRc = push(H.Rc), oRs = push(H.Rpos);
-  std::vector<double> dbl(H.P_coef);
-  dbl.insert(dbl.end(), H.A_coef.begin(), H.A_coef.end());
+  std::vector<double> dbl;
+  QpPlanOffsets off;
+  qp_plan_pack(H, ints, dbl, off);
   if (cudaMalloc(&p->d_ints, ints.size() * sizeof(int)) != cudaSuccess) return nullptr;
   if (cudaMalloc(&p->d_dbls, dbl.size() * sizeof(double)) != cudaSuccess) return nullptr;
   cudaMemcpyAsync(p->d_ints, ints.data(), ints.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
   cudaMemcpyAsync(p->d_dbls, dbl.data(), dbl.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
   cudaStreamSynchronize(ctx->stream);
-  QpPlanDev& D = p->dev;
-  D.order = H.order; D.S = H.S; D.k = H.k; D.nc = H.nc; D.n = H.n; D.m = H.m; D.N = H.N;
-  D.nnzP = H.nnzP; D.nnzA = H.nnzA; D.nnzK = H.nnzK; D.nnzL = H.nnzL;
-  const int* I = p->d_ints;
-  D.Pp = I + oPp; D.Pi = I + oPi; D.P_seg = I + oPs; D.P_pow = I + oPw;
-  D.Ap = I + oAp; D.Ai = I + oAi; D.A_seg = I + oAs; D.A_pow = I + oAw;
-  D.P_coef = p->d_dbls; D.A_coef = p->d_dbls + H.P_coef.size();
-  D.l_src = I + oL; D.perm = I + oPerm; D.Kp = I + oKp; D.Ki = I + oKi; D.Kkind = I + oKk; D.Kidx = I + oKx;
-  D.Lp = I + oLp; D.Li = I + oLi; D.Rp = I + oRp; D.Rc = I + oRc; D.Rpos = I + oRs;
-  int o = 0;
-  auto take = [&](int len) { int r = o; o += len; return r; };
-  const int n = H.n, m = H.m, N = H.N;
-  D.o_Px = take(H.nnzP); D.o_Ax = take(H.nnzA); D.o_q = take(n); D.o_l = take(m); D.o_u = take(m);
-  D.o_D = take(n); D.o_Dinv = take(n); D.o_E = take(m); D.o_Einv = take(m); D.o_rho = take(m); D.o_rhoinv = take(m);
-  D.o_Lx = take(H.nnzL); D.o_Dd = take(N); D.o_Ddinv = take(N); D.o_yw = take(N);
-  D.o_x = take(n); D.o_xprev = take(n); D.o_dx = take(n); D.o_Pxv = take(n); D.o_Aty = take(n);
-  D.o_z = take(m); D.o_zprev = take(m); D.o_y = take(m); D.o_dy = take(m); D.o_Axv = take(m);
-  D.o_xz = take(N); D.o_bp = take(N); D.o_tn = take(n); D.o_tm = take(m);
-  D.ws_doubles = o;
+  qp_plan_bind(H, off, p->d_ints, p->d_dbls, p->dev);
   ctx->qp_plans.push_back(p);
   return p;
 }

@@ -1,5 +1,7 @@
 // qp_plan.h — pattern-only data of one (order, S) QP family, built by qp_symbolic.cpp, consumed by qp_kernel.cu.
 #pragma once
+#include <stddef.h>
+
 #include <vector>
 
 struct QpPlanHost {
@@ -25,4 +27,16 @@ struct QpPlanDev {
   // workspace layout (offsets in doubles)
   int o_Px, o_Ax, o_q, o_l, o_u, o_D, o_Dinv, o_E, o_Einv, o_rho, o_rhoinv, o_Lx, o_Dd, o_Ddinv, o_yw, o_x, o_xprev,
       o_dx, o_Pxv, o_Aty, o_z, o_zprev, o_y, o_dy, o_Axv, o_xz, o_bp, o_tn, o_tm, ws_doubles;
+};
+
+// flattening of a host plan into one int array + one double array (what is uploaded), and the view over it
+struct QpPlanOffsets { size_t Pp, Pi, P_seg, P_pow, Ap, Ai, A_seg, A_pow, l_src, perm, Kp, Ki, Kkind, Kidx, Lp, Li, Rp, Rc, Rpos, A_coef; };
+void qp_plan_pack(const QpPlanHost& H, std::vector<int>& ints, std::vector<double>& dbls, QpPlanOffsets& off);
+void qp_plan_bind(const QpPlanHost& H, const QpPlanOffsets& off, const int* ints, const double* dbls, QpPlanDev& D);
+
+// per-batch I/O of the solve kernel
+struct QpIo {
+  const double* pos; const double* bv; const double* ba; const double* bj; const double* T;
+  double* coef; int* solved; int* status; int* iters;
+  int B, stride;
 };

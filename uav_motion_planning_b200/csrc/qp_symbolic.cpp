@@ -183,3 +183,36 @@ QpPlanHost* qp_plan_build(int order, int S) {
   }
   return pl;
 }
+
+void qp_plan_pack(const QpPlanHost& H, std::vector<int>& ints, std::vector<double>& dbls, QpPlanOffsets& o) {
+  ints.clear();
+  auto push = [&](const std::vector<int>& v) { size_t at = ints.size(); ints.insert(ints.end(), v.begin(), v.end()); return at; };
+  o.Pp = push(H.Pp); o.Pi = push(H.Pi); o.P_seg = push(H.P_seg); o.P_pow = push(H.P_pow);
+  o.Ap = push(H.Ap); o.Ai = push(H.Ai); o.A_seg = push(H.A_seg); o.A_pow = push(H.A_pow);
+  o.l_src = push(H.l_src); o.perm = push(H.perm); o.Kp = push(H.Kp); o.Ki = push(H.Ki); o.Kkind = push(H.Kkind);
+  o.Kidx = push(H.Kidx); o.Lp = push(H.Lp); o.Li = push(H.Li); o.Rp = push(H.Rp); o.Rc = push(H.Rc); o.Rpos = push(H.Rpos);
+  dbls = H.P_coef;
+  o.A_coef = dbls.size();
+  dbls.insert(dbls.end(), H.A_coef.begin(), H.A_coef.end());
+}
+
+void qp_plan_bind(const QpPlanHost& H, const QpPlanOffsets& o, const int* I, const double* Dbl, QpPlanDev& D) {
+  D.order = H.order; D.S = H.S; D.k = H.k; D.nc = H.nc; D.n = H.n; D.m = H.m; D.N = H.N;
+  D.nnzP = H.nnzP; D.nnzA = H.nnzA; D.nnzK = H.nnzK; D.nnzL = H.nnzL;
+  D.Pp = I + o.Pp; D.Pi = I + o.Pi; D.P_seg = I + o.P_seg; D.P_pow = I + o.P_pow;
+  D.Ap = I + o.Ap; D.Ai = I + o.Ai; D.A_seg = I + o.A_seg; D.A_pow = I + o.A_pow;
+  D.P_coef = Dbl; D.A_coef = Dbl + o.A_coef;
+  D.l_src = I + o.l_src; D.perm = I + o.perm; D.Kp = I + o.Kp; D.Ki = I + o.Ki; D.Kkind = I + o.Kkind; D.Kidx = I + o.Kidx;
+  D.Lp = I + o.Lp; D.Li = I + o.Li; D.Rp = I + o.Rp; D.Rc = I + o.Rc; D.Rpos = I + o.Rpos;
+  // workspace layout (offsets in doubles; element e of problem b lives at ws[e * stride + b])
+  int at = 0;
+  auto take = [&](int len) { int r = at; at += len; return r; };
+  const int n = H.n, m = H.m, N = H.N;
+  D.o_Px = take(H.nnzP); D.o_Ax = take(H.nnzA); D.o_q = take(n); D.o_l = take(m); D.o_u = take(m);
+  D.o_D = take(n); D.o_Dinv = take(n); D.o_E = take(m); D.o_Einv = take(m); D.o_rho = take(m); D.o_rhoinv = take(m);
+  D.o_Lx = take(H.nnzL); D.o_Dd = take(N); D.o_Ddinv = take(N); D.o_yw = take(N);
+  D.o_x = take(n); D.o_xprev = take(n); D.o_dx = take(n); D.o_Pxv = take(n); D.o_Aty = take(n);
+  D.o_z = take(m); D.o_zprev = take(m); D.o_y = take(m); D.o_dy = take(m); D.o_Axv = take(m);
+  D.o_xz = take(N); D.o_bp = take(N); D.o_tn = take(n); D.o_tm = take(m);
+  D.ws_doubles = at;
+}

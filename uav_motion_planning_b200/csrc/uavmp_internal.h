@@ -149,6 +149,7 @@ struct uavmp_ctx {
   // timings
   cudaEvent_t ev[8];
   uavmp_timings tm;
+  bool tm_pending_dev = false;
 };
 
 int uavmp_fail(uavmp_ctx* ctx, int code, const char* fmt, ...);
