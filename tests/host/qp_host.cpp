@@ -27,3 +27,18 @@ extern "C" int host_qp_solve(int order, int S, int B, const double* pos, const d
   delete H;
   return 0;
 }
+
+// unpermuted KKT pattern of one (order, S) family, for tests/golden/make_amd_tables.py
+extern "C" int host_qp_kkt_pattern(int order, int S, int* N_out, int* nnz_out, long long* Kp, long long* Ki, int cap,
+                                   int* from_table) {
+  QpPlanHost* H = qp_plan_build(order, S);
+  *N_out = H->N;
+  *nnz_out = (int)H->Ki0.size();
+  if (from_table) *from_table = H->perm_from_table ? 1 : 0;
+  if (Kp && Ki && cap >= (int)H->Ki0.size()) {
+    for (int i = 0; i <= H->N; i++) Kp[i] = H->Kp0[i];
+    for (size_t i = 0; i < H->Ki0.size(); i++) Ki[i] = H->Ki0[i];
+  }
+  delete H;
+  return 0;
+}

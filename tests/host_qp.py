@@ -15,7 +15,7 @@ _lib = None
 def load():
     global _lib
     if _lib is None:
-        deps = [SRC] + [os.path.join(CS, f) for f in ("qp_body.h", "qp_plan.h", "qp_symbolic.cpp", "fpmath.h")]
+        deps = [SRC] + [os.path.join(CS, f) for f in ("qp_body.h", "qp_plan.h", "qp_symbolic.cpp", "fpmath.h", "amd_perm_table.inc")]
         if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
             subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-shared",
                             "-I" + os.path.join(ROOT, "include"), "-I" + CS, "-o", OUT, SRC,

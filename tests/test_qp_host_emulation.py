@@ -27,6 +27,8 @@ def test_against_golden(case):
         assert (got["solved"][b], got["status"][b], got["iters"][b]) == (p["solved"], p["status_val"], p["iter"])
         ref = np.array(p["coef"])
         assert np.abs(ref - got["coef"][b]).max() / np.abs(ref).max() < RTOL
+        # with the tabulated AMD order the restated OSQP follows the reference operation for operation
+        assert np.array_equal(ref, got["coef"][b])
 
 
 @pytest.mark.skipif(not oracle_lib.have_ref(), reason="oracle/_ref not built")
@@ -45,6 +47,20 @@ def test_against_reference_osqp(order, S, eps):
                                                   settings=oracle_lib.osqp_settings(**kw))
         assert (ok, info["status_val"], info["iter"]) == (got["solved"][b], got["status"][b], got["iters"][b])
         assert np.abs(coef - got["coef"][b]).max() / np.abs(coef).max() < RTOL
+        assert np.array_equal(coef, got["coef"][b])
+
+
+def test_fallback_ordering_outside_the_table():
+    """S = 41 is not tabulated: the plan falls back to its own minimum-degree order; agreement is then to rounding."""
+    S, rng = 41, np.random.default_rng(41)
+    pos = np.cumsum(rng.normal(size=(2, S + 1)), axis=1)
+    z = np.zeros((2, 2))
+    got = host_qp.solve_batch(5, pos, z, z, np.ones((2, S)))
+    if oracle_lib.have_ref():
+        for b in range(2):
+            ok, coef, info = oracle_lib.minctrl_solve(5, S, pos[b], z[b], z[b], np.ones(S))
+            assert ok == got["solved"][b]
+            assert np.abs(coef - got["coef"][b]).max() / np.abs(coef).max() < 1e-4
 
 
 def test_max_iter_status():

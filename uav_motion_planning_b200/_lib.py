@@ -54,7 +54,8 @@ SYMBOLS = [
     "uavmp_kino_set_params", "uavmp_map_set", "uavmp_kino_search_batch", "uavmp_kino_get_paths",
     "uavmp_kino_set_trace", "uavmp_kino_get_trace", "uavmp_kino_get_counters", "uavmp_minctrl_solve_batch",
     "uavmp_plan_batch", "uavmp_plan_batch_dev", "uavmp_get_timings", "uavmp_mapgen_params_default",
-    "uavmp_mapgen_cloud", "uavmp_grid_inflate_host", "uavmp_fpmath_eval",
+    "uavmp_mapgen_cloud", "uavmp_grid_inflate_host", "uavmp_fpmath_eval", "uavmp_kino_set_profile",
+    "uavmp_kino_get_profile",
 ]
 
 _lib = None
@@ -103,6 +104,8 @@ def load():
     lib.uavmp_grid_inflate_host.argtypes = [vp, C.c_int, vp, vp, C.c_double, C.c_double, vp, C.c_int, C.c_int,
                                             C.c_int]
     lib.uavmp_fpmath_eval.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_longlong]
+    lib.uavmp_kino_set_profile.argtypes = [vp, C.c_int]
+    lib.uavmp_kino_get_profile.argtypes = [vp, vp, vp, C.c_int, ip]
     _lib = lib
     return lib
 

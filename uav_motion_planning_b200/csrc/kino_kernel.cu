@@ -37,6 +37,8 @@
 #define PUSH_BATCH 256
 #define HC_CAP 608
 #define FULL 0xffffffffu
+// phase timers: thread 0 charges the cycles since the last mark to phase `k`
+#define PH_MARK(k) do { if (prof && tid == 0) { long long t_ = clock64(); s.ph[k] += (unsigned long long)(t_ - s.ph_t); s.ph_t = t_; } } while (0)
 #define KEY_BIAS (1 << 17)
 #define EPOCH_BITS 10
 #define EPOCH_MASK ((1u << EPOCH_BITS) - 1u)
@@ -67,6 +69,8 @@ struct SearchSmem {
   double shot[12];
   unsigned long long pop_hash;
   unsigned long long cnt[8];
+  unsigned long long ph[8];   // per-phase SM cycles of this CTA (thread 0's clock), only when bt.phase_cycles != nullptr
+  long long ph_t;
   uint32_t cur_id, cur_parent, epoch;
   int heap_len, use_num, n_pop, n1, n2, n_new, status, flag, q, hc_active, hc_total;
   int wsum[KT / 32];
@@ -384,6 +388,9 @@ __global__ void __launch_bounds__(KT) kino_search_kernel(const KinoParamsDev* __
   HeapSlot* H = ar.heap;
   HashSlot* table = ar.table;
   const uint32_t tmask = (1u << table_bits) - 1u;
+  const bool prof = bt.phase_cycles != nullptr;
+  if (tid < 8) s.ph[tid] = 0;
+  if (tid == 0) s.ph_t = clock64();
 
   for (;;) {
     // ---- fetch the next query --------------------------------------------------------------------
@@ -441,6 +448,8 @@ __global__ void __launch_bounds__(KT) kino_search_kernel(const KinoParamsDev* __
     }
     unsigned my_occ = 0, my_cloud = 0;
     __syncthreads();
+    PH_MARK(7);
+    long long q_t0 = prof ? clock64() : 0;
 
     // ================================ main loop (kino_astar.cpp:101) ===============================
     for (;;) {
@@ -484,6 +493,7 @@ __global__ void __launch_bounds__(KT) kino_search_kernel(const KinoParamsDev* __
       }
       for (int i = tid; i < TAB_SIZE; i += KT) s.tab[i] = 0;
       __syncthreads();
+      PH_MARK(0);
       if (s.status) break;
 
       // ---- near goal: one-shot trajectory (:112-154, :416-471) ---------------------------------------
@@ -558,6 +568,7 @@ __global__ void __launch_bounds__(KT) kino_search_kernel(const KinoParamsDev* __
           if (tid == 0) s.status = UAVMP_NO_PATH_FOUND;  // :148-152
         }
         __syncthreads();
+        PH_MARK(1);
         if (s.status) break;
       }
 
@@ -595,6 +606,7 @@ __global__ void __launch_bounds__(KT) kino_search_kernel(const KinoParamsDev* __
         s.state[p] = st;
       }
       __syncthreads();
+      PH_MARK(2);
       const int n1 = s.n1;
 
       // ---- B1. group identical voxel keys inside this expansion --------------------------------------
@@ -660,6 +672,7 @@ __global__ void __launch_bounds__(KT) kino_search_kernel(const KinoParamsDev* __
         if (st == ST_NEW || st == ST_OPEN_CAND || st == ST_FOLLOW_CAND) s.list2[atomicAdd(&s.n2, 1)] = (uint16_t)p;
       }
       __syncthreads();
+      PH_MARK(3);
       const int n2 = s.n2;
       // ---- B3. heuristic for every candidate (:232,:259) ----------------------------------------------
       for (int e = tid; e < n2; e += KT) {
@@ -702,6 +715,7 @@ __global__ void __launch_bounds__(KT) kino_search_kernel(const KinoParamsDev* __
         if (tid == KT - 1) s.n_new = woff + incl;
       }
       __syncthreads();
+      PH_MARK(4);
       const int n_new = s.n_new;
       if (s.use_num + n_new >= P.allocated) {
         // pool exhausted while committing this expansion (:243-247): the reference returns on the spot
@@ -739,6 +753,7 @@ __global__ void __launch_bounds__(KT) kino_search_kernel(const KinoParamsDev* __
         }
       }
       __syncthreads();
+      PH_MARK(5);
 
       // ---- D. ordered commit: heap pushes and in-place mutations (:225-266) ----------------------------
       if (warp == 0) {
@@ -797,6 +812,7 @@ __global__ void __launch_bounds__(KT) kino_search_kernel(const KinoParamsDev* __
         }
       }
       __syncthreads();
+      PH_MARK(6);
     }  // main loop
 
     // ---- query epilogue ------------------------------------------------------------------------------
@@ -810,10 +826,14 @@ __global__ void __launch_bounds__(KT) kino_search_kernel(const KinoParamsDev* __
       bt.pop_hash[q] = s.pop_hash;
       if (s.status != UAVMP_REACH_END) bt.n_path[q] = 0;
       s.cnt[0] = (unsigned long long)s.n_pop;
+      if (prof && bt.query_cycles) bt.query_cycles[q] = clock64() - q_t0;
     }
     __syncthreads();
     if (tid < 8) atomicAdd(&bt.counters[tid], s.cnt[tid]);
   }
+  PH_MARK(7);
+  __syncthreads();
+  if (prof && tid < 8) atomicAdd(&bt.phase_cycles[tid], s.ph[tid]);
 }
 
 // ---- map preprocessing -------------------------------------------------------------------------------
@@ -1206,12 +1226,24 @@ int kino_launch_search(uavmp_ctx* ctx, int B, const double* d_sp, const double* 
   bt.n_path = ctx->d_npath; bt.path_stage = ctx->d_path_stage; bt.path_cap = ctx->path_cap;
   bt.pop_trace = ctx->d_trace; bt.pop_cap = ctx->pop_cap;
   bt.error_flag = ctx->d_misc; bt.next_query = ctx->d_misc + 1; bt.counters = ctx->d_counters;
+  bt.phase_cycles = nullptr; bt.query_cycles = nullptr;
+  if (ctx->profile_phases) {
+    if (!ctx->d_phase) UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_phase, 8 * sizeof(unsigned long long)));
+    if (ctx->query_cycles_cap < B) {
+      if (ctx->d_query_cycles) cudaFree(ctx->d_query_cycles);
+      UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_query_cycles, (size_t)B * sizeof(long long)));
+      ctx->query_cycles_cap = B;
+    }
+    UAVMP_CUDA(ctx, cudaMemsetAsync(ctx->d_phase, 0, 8 * sizeof(unsigned long long), st));
+    bt.phase_cycles = ctx->d_phase; bt.query_cycles = ctx->d_query_cycles;
+  }
   LatticeDev lat;
   const int n = ctx->nprim;
   lat.ux = ctx->d_lattice; lat.uy = lat.ux + n; lat.uz = lat.uy + n; lat.ginc = lat.uz + n; lat.Einv = lat.ginc + n;
   int bits = 0;
   while ((1 << bits) < ctx->table_size) bits++;
   const int grid = std::min(ctx->n_arenas, B);
+  ctx->last_grid = grid;
   cudaFuncSetAttribute(kino_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SearchSmem));
   kino_search_kernel<<<grid, KT, sizeof(SearchSmem), st>>>(ctx->d_kparams, lat, ctx->d_map, ctx->d_arenas, bt, bits);
   UAVMP_CUDA(ctx, cudaGetLastError());

@@ -9,6 +9,8 @@ struct QpPlanHost {
   std::vector<int> Pp, Pi, P_seg, P_pow;  std::vector<double> P_coef;   // upper-triangular CSC of P + value recipe
   std::vector<int> Ap, Ai, A_seg, A_pow;  std::vector<double> A_coef;   // CSC of A + value recipe coef * T[seg]^pow
   std::vector<int> l_src;                                               // bound source per constraint row (-1: 0.0)
+  std::vector<int> Kp0, Ki0;                                            // unpermuted upper CSC KKT pattern (form_KKT order)
+  bool perm_from_table = false;                                         // true: the reference AMD's permutation (tabulated)
   std::vector<int> perm;                                                // perm[j] = original KKT index at position j
   std::vector<int> Kp, Ki, Kkind, Kidx;                                 // permuted upper CSC of the KKT matrix
   std::vector<int> Lp, Li;                                              // pattern of L (strictly lower, CSC)

@@ -20,6 +20,9 @@
 
 #include "qp_plan.h"
 
+// amd_perm_table.inc defines: static const int* qp_amd_table_lookup(int order, int S, int N)
+#include "amd_perm_table.inc"
+
 namespace {
 
 double falling(int j, int r) {
@@ -56,16 +59,24 @@ QpPlanHost* qp_plan_build(int order, int S) {
   P.nnzP = (int)pe.size();
 
   // ---- A -----------------------------------------------------------------------------------------------------
+  // The reference inserts explicit 0.0 entries (minimum_control.cpp:55,61,64,65,70,71,83,90,91): every derivative row
+  // stores all nc coefficients of its segment and the continuity rows also store the zeros in front of the -r! entry.
+  // They are kept (value 0 * T^0) because OsqpEigen copies them into OSQP's CSC A, where they shape the KKT pattern,
+  // the AMD ordering and therefore the order of floating-point operations in the LDL' factorisation.
   std::vector<Entry> ae;
   for (int r = 0; r < k; r++) ae.push_back({r, r, 0, 0, falling(r, r)});
   auto deriv_row = [&](int row, int s, int r) {
-    for (int j = r; j < nc; j++) ae.push_back({row, nc * s + j, s, j - r, falling(j, r)});
+    for (int j = 0; j < nc; j++) {
+      if (j < r) ae.push_back({row, nc * s + j, s, 0, 0.0});
+      else ae.push_back({row, nc * s + j, s, j - r, falling(j, r)});
+    }
   };
   for (int s = 0; s + 1 < S; s++) {
     int base = k + (k + 1) * s;
     deriv_row(base, s, 0);
     for (int r = 0; r < k; r++) {
       deriv_row(base + 1 + r, s, r);
+      for (int j = 0; j < r; j++) ae.push_back({base + 1 + r, nc * (s + 1) + j, 0, 0, 0.0});
       ae.push_back({base + 1 + r, nc * (s + 1) + r, 0, 0, -falling(r, r)});
     }
   }
@@ -90,51 +101,77 @@ QpPlanHost* qp_plan_build(int order, int S) {
   for (int r = 1; r < k; r++) P.l_src[eb + r] = (S + 1) + 2 * (r - 1) + 1;
   for (int s = 0; s + 1 < S; s++) P.l_src[k + (k + 1) * s] = s + 1;
 
-  // ---- KKT pattern (original order), as an undirected graph ---------------------------------------------------------
-  // entry sources: kind 0 P off-diagonal, 1 P diagonal (+sigma), 2 sigma only, 3 A, 4 -1/rho
+  // ---- KKT = [[P + sigma I, A'], [A, -diag(1/rho)]], upper-triangular CSC, entries in the order OSQP's form_KKT
+  // writes them (3rd/osqp/algebra/_common/kkt.c:254-291 _kkt_assemble_csc): column c < n holds P's column c and, when P
+  // has no diagonal there, a structural diagonal last; column n + r holds row r of A in increasing variable order, then
+  // the diagonal.  entry sources: kind 0 P off-diagonal, 1 P diagonal (+sigma), 2 sigma only, 3 A, 4 -1/rho
   struct KE { int i, j, kind, idx; };
-  std::vector<KE> ke;
-  std::vector<char> has_diag(n, 0);
-  for (int c = 0; c < n; c++)
+  std::vector<std::vector<KE>> kcol(N);
+  for (int c = 0; c < n; c++) {
+    bool has_diag = false;
     for (int p = P.Pp[c]; p < P.Pp[c + 1]; p++) {
       int r = P.Pi[p];
-      if (r == c) { ke.push_back({r, c, 1, p}); has_diag[c] = 1; }
-      else ke.push_back({r, c, 0, p});
+      if (r == c) { kcol[c].push_back({r, c, 1, p}); has_diag = true; }
+      else kcol[c].push_back({r, c, 0, p});
     }
-  for (int c = 0; c < n; c++) if (!has_diag[c]) ke.push_back({c, c, 2, 0});
-  for (int c = 0; c < n; c++)
-    for (int p = P.Ap[c]; p < P.Ap[c + 1]; p++) ke.push_back({c, n + P.Ai[p], 3, p});  // A' block: (var c, con row)
-  for (int r = 0; r < m; r++) ke.push_back({n + r, n + r, 4, r});
-
-  // ---- minimum-degree ordering on the elimination graph ----------------------------------------------------------------
-  std::vector<std::set<int>> adj(N);
-  for (auto& e : ke) if (e.i != e.j) { adj[e.i].insert(e.j); adj[e.j].insert(e.i); }
-  std::vector<int> perm(N), inv(N, -1);
-  std::vector<char> done(N, 0);
-  for (int step = 0; step < N; step++) {
-    int best = -1; size_t bd = (size_t)-1;
-    for (int v = 0; v < N; v++) if (!done[v] && adj[v].size() < bd) { bd = adj[v].size(); best = v; }
-    perm[step] = best; inv[best] = step; done[best] = 1;
-    std::vector<int> nb(adj[best].begin(), adj[best].end());
-    for (int a : nb) adj[a].erase(best);
-    for (size_t x = 0; x < nb.size(); x++)
-      for (size_t y = x + 1; y < nb.size(); y++) { adj[nb[x]].insert(nb[y]); adj[nb[y]].insert(nb[x]); }
-    adj[best].clear();
+    if (!has_diag) kcol[c].push_back({c, c, 2, 0});
   }
+  for (int c = 0; c < n; c++)
+    for (int p = P.Ap[c]; p < P.Ap[c + 1]; p++) kcol[n + P.Ai[p]].push_back({c, n + P.Ai[p], 3, p});
+  for (int r = 0; r < m; r++) kcol[n + r].push_back({n + r, n + r, 4, r});
+  P.Kp0.assign(N + 1, 0);
+  P.Ki0.clear();
+  for (int c = 0; c < N; c++) {
+    for (auto& e : kcol[c]) P.Ki0.push_back(e.i);
+    P.Kp0[c + 1] = (int)P.Ki0.size();
+  }
+
+  // ---- fill-reducing order -------------------------------------------------------------------------------------------
+  // OSQP orders the KKT matrix with AMD (qdldl_interface.c:137-160 amd_l_order).  For the (order, S) families in
+  // amd_perm_table.inc the permutation AMD returns for exactly this pattern is tabulated (generated by
+  // tests/golden/make_amd_tables.py from the reference's own AMD), which makes the factorisation — and with it every ADMM
+  // iterate — follow the reference operation for operation.  Other families fall back to a plain minimum-degree order
+  // (any symmetric permutation of a quasi-definite matrix has an LDL'; results then agree to rounding only).
+  std::vector<int> perm(N), inv(N, -1);
+  const int* tab = qp_amd_table_lookup(order, S, N);
+  P.perm_from_table = tab != nullptr;
+  if (tab) {
+    for (int i = 0; i < N; i++) perm[i] = tab[i];
+  } else {
+    std::vector<std::set<int>> adj(N);
+    for (int c = 0; c < N; c++)
+      for (auto& e : kcol[c]) if (e.i != e.j) { adj[e.i].insert(e.j); adj[e.j].insert(e.i); }
+    std::vector<char> done(N, 0);
+    for (int step = 0; step < N; step++) {
+      int best = -1; size_t bd = (size_t)-1;
+      for (int v = 0; v < N; v++) if (!done[v] && adj[v].size() < bd) { bd = adj[v].size(); best = v; }
+      perm[step] = best; done[best] = 1;
+      std::vector<int> nb(adj[best].begin(), adj[best].end());
+      for (int a : nb) adj[a].erase(best);
+      for (size_t x = 0; x < nb.size(); x++)
+        for (size_t y = x + 1; y < nb.size(); y++) { adj[nb[x]].insert(nb[y]); adj[nb[y]].insert(nb[x]); }
+      adj[best].clear();
+    }
+  }
+  for (int i = 0; i < N; i++) inv[perm[i]] = i;
   P.perm = perm;
 
-  // ---- permuted upper CSC of the KKT matrix -------------------------------------------------------------------------------
-  struct PK { int r, c, kind, idx; };
-  std::vector<PK> pk;
-  for (auto& e : ke) {
-    int a = inv[e.i], b = inv[e.j];
-    pk.push_back({std::min(a, b), std::max(a, b), e.kind, e.idx});
-  }
-  std::sort(pk.begin(), pk.end(), [](const PK& a, const PK& b) { return a.c != b.c ? a.c < b.c : a.r < b.r; });
+  // ---- permuted upper CSC, entries in the order csc_symperm emits them (csc_utils.c:326-386): original columns in
+  // order, entries in order, each appended to column max(pinv[i], pinv[j]) with row min(...) — rows are NOT sorted
+  // within a column, and QDLDL's reach order (hence the summation order) follows that sequence
+  std::vector<std::vector<KE>> pcol(N);
+  for (int c = 0; c < N; c++)
+    for (auto& e : kcol[c]) {
+      int a = inv[e.i], b = inv[e.j];
+      pcol[std::max(a, b)].push_back({std::min(a, b), std::max(a, b), e.kind, e.idx});
+    }
   P.Kp.assign(N + 1, 0);
-  for (auto& e : pk) { P.Kp[e.c + 1]++; P.Ki.push_back(e.r); P.Kkind.push_back(e.kind); P.Kidx.push_back(e.idx); }
-  for (int c = 0; c < N; c++) P.Kp[c + 1] += P.Kp[c];
-  P.nnzK = (int)pk.size();
+  P.Ki.clear(); P.Kkind.clear(); P.Kidx.clear();
+  for (int c = 0; c < N; c++) {
+    for (auto& e : pcol[c]) { P.Ki.push_back(e.i); P.Kkind.push_back(e.kind); P.Kidx.push_back(e.idx); }
+    P.Kp[c + 1] = (int)P.Ki.size();
+  }
+  P.nnzK = (int)P.Ki.size();
 
   // ---- elimination tree + column counts of L (same algorithm QDLDL_etree runs per setup) ---------------------------------------
   std::vector<int> etree(N, -1), work(N, 0), Lnz(N, 0);

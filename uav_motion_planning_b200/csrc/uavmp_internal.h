@@ -85,6 +85,8 @@ struct KinoBatchDev {
   int* error_flag;
   unsigned long long* counters;  // 8 words
   int* next_query;           // work counter
+  unsigned long long* phase_cycles;  // optional profiling: 8 words, SM cycles per phase summed over CTAs
+  long long* query_cycles;           // optional profiling: B words, SM cycles each query occupied its CTA
 };
 
 // ---- host-side context -----------------------------------------------------------------------------
@@ -135,6 +137,9 @@ struct uavmp_ctx {
   long long last_total_path = 0;
   int last_B = 0;
   void* d_cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
+  bool profile_phases = false;
+  unsigned long long* d_phase = nullptr; long long* d_query_cycles = nullptr; int query_cycles_cap = 0;
+  int last_grid = 0;
 
   // qp
   std::vector<QpPlan*> qp_plans;

@@ -92,3 +92,15 @@ class KinoAstar:
                               np.asarray(end_vel)[None])
         path.extend(np.asarray(p) for p in r["paths"])  # the reference only push_back's (caller clears)
         return int(r["status"][0])
+
+    # -- optional in-kernel profile (uavmp_kino_set_profile / uavmp_kino_get_profile) ---------------------------
+    def setProfile(self, on=True):
+        self.ctx.check(self.lib.uavmp_kino_set_profile(self.ctx.h, int(on)))
+
+    def profile(self, B):
+        ph = np.zeros(8, np.uint64)
+        qc = np.zeros(B, np.int64)
+        grid = C.c_int()
+        self.ctx.check(self.lib.uavmp_kino_get_profile(self.ctx.h, _lib.ptr(ph), _lib.ptr(qc), B, C.byref(grid)))
+        names = ["pop", "shot_path", "primitives", "dedup_probe", "heuristic_scan", "node_write", "heap_commit", "setup"]
+        return dict(phase_cycles=dict(zip(names, ph.tolist())), query_cycles=qc, grid=grid.value)
