@@ -82,7 +82,7 @@ void uavmp_ctx_destroy(uavmp_ctx* ctx) {
                   ctx->d_pts, ctx->d_map, ctx->d_arena_mem, ctx->d_arenas, ctx->d_q, ctx->d_order, ctx->d_status,
                   ctx->d_use, ctx->d_npop, ctx->d_hash, ctx->d_npath, ctx->d_path_stage, ctx->d_trace, ctx->d_offsets,
                   ctx->d_path_packed, ctx->d_misc, ctx->d_counters, ctx->d_cub_tmp, ctx->d_qp_ws, ctx->d_qp_in,
-                  ctx->d_qp_out, ctx->d_qp_int, ctx->d_plan_out, ctx->d_plan_io, ctx->d_wp, ctx->d_phase, ctx->d_query_cycles};
+                  ctx->d_qp_out, ctx->d_qp_int, ctx->d_plan_out, ctx->d_plan_io, ctx->d_wp, ctx->d_phase, ctx->d_query_cycles, ctx->d_flags_pad};
   for (void* p : ptrs) if (p) cudaFree(p);
   qp_free_plans(ctx);
   for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->ev[i]);

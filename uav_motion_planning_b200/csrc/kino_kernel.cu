@@ -22,9 +22,12 @@
 // All f64 arithmetic is written with the reference's association and compiled with -fmad=false; cbrt/acos/cos/pow
 // come from fpmath.h, which the CPU oracle shares, so popped-node sequences are bit-identical.
 #include <cub/cub.cuh>
+#include <cuda.h>
+#include <limits.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <numeric>
@@ -35,7 +38,12 @@
 #define KT 256
 #define TAB_SIZE 2048
 #define PUSH_BATCH 256
-#define HC_CAP 608
+#define HC_CAP 640
+#define TB 32          // x / y edge of the flags box staged per expansion (voxels)
+#define TBZ 48         // z edge: the TMA inner coordinate must be 16 B aligned, so the box starts at z & ~15
+#define PTS_CAP 2048   // cloud points staged per expansion
+#define CS_CAP 1280    // cell_start entries staged per expansion
+#define COL_CAP 128    // cell columns staged per expansion
 #define FULL 0xffffffffu
 // phase timers: thread 0 charges the cycles since the last mark to phase `k`
 #define PH_MARK(k) do { if (prof && tid == 0) { long long t_ = clock64(); s.ph[k] += (unsigned long long)(t_ - s.ph_t); s.ph_t = t_; } } while (0)
@@ -50,17 +58,46 @@ enum : uint8_t {
   ST_FOLLOW_CAND = 6, ST_FOLLOW_NOCAND = 7
 };
 
-struct SearchSmem {
-  unsigned long long key[UAVMP_MAXPRIM];
+struct PhaseA {  // staging buffers of the primitive evaluation
+  uint8_t tile[TB * TB * TBZ];   // flags box, [x][y][z] z fastest (the TMA destination: keep first, 128 B aligned)
+  float4 pts[PTS_CAP];          // cloud points of the cells the expansion can touch, column after column
+  int cstart[CS_CAP];           // their cell_start entries, [column][z]
+  int col_delta[COL_CAP];       // shared-memory index = global point index + col_delta[column]
+};
+struct PhaseB {  // successor classification / commit
   double f[UAVMP_MAXPRIM];
   double topt[UAVMP_MAXPRIM];
   double gcur[UAVMP_MAXPRIM];
-  uint32_t id[UAVMP_MAXPRIM];
+  uint32_t hs[UAVMP_MAXPRIM];    // hash slot of the group's node
+  uint32_t hpos[UAVMP_MAXPRIM];  // its open-list position at probe time
   uint32_t tab[TAB_SIZE];
   HeapSlot hc[HC_CAP];
+  uint16_t win[UAVMP_MAXPRIM];   // last improving primitive of an existing node's group
+  uint8_t inun[UAVMP_MAXPRIM];   // that node is an ancestor of a new leaf: its key was already written in order
+};
+
+struct SearchSmem {
+  union __align__(128) { PhaseA a; PhaseB b; };
+  unsigned long long key[UAVMP_MAXPRIM];
+  uint32_t id[UAVMP_MAXPRIM];
   uint16_t list1[UAVMP_MAXPRIM];
   uint16_t list2[UAVMP_MAXPRIM];
+  uint16_t listT[UAVMP_MAXPRIM];
+  uint16_t need[UAVMP_MAXPRIM];
   uint8_t state[UAVMP_MAXPRIM];
+  // separable tables of one expansion
+  double X[UAVMP_MAXK][3][UAVMP_MAXNA];
+  int XI[UAVMP_MAXK][3][UAVMP_MAXNA];
+  uint8_t XOK[UAVMP_MAXK][3][UAVMP_MAXNA];
+  double EX[3][UAVMP_MAXNA], EV[3][UAVMP_MAXNA];
+  int EI[3][UAVMP_MAXNA];
+  uint8_t axok[3][UAVMP_MAXNA];
+  int aimin[3][UAVMP_MAXNA], aimax[3][UAVMP_MAXNA];
+  double axmin[3][UAVMP_MAXNA], axmax[3][UAVMP_MAXNA];
+  double xlo[3], xhi[3];
+  int to[3], rc0[3], rc1[3];
+  int any_ok, tile_ok, nT, tnext, npts;
+  unsigned long long mbar;
   int lv_lo[32], lv_off[32], lv_hi[32];
   double cp[3], cv[3], cg;
   double gp[3], gv[3];
@@ -184,40 +221,7 @@ __device__ __forceinline__ void pos_to_index(const MapDev& M, double x, double y
   iz = (int)floor((z - M.oz) * M.inv_res);
 }
 __device__ __forceinline__ unsigned map_flags(const MapDev& M, int ix, int iy, int iz) {
-  return __ldg(M.flags + ((size_t)ix * M.ny + iy) * M.nz + iz);
-}
-
-// kino_astar.cpp:721-758 with the KD-tree replaced by a cell list (any-point-inside semantics, §9.1 Q12)
-__device__ bool ellipsoid_free(const MapDev& M, const KinoParamsDev& P, const double* __restrict__ Ei, double px,
-                               double py, double pz, unsigned& n_tested) {
-  int x0 = max((int)floor((px - P.box_r - M.cox) * M.inv_cell), 0);
-  int x1 = min((int)floor((px + P.box_r - M.cox) * M.inv_cell), M.cnx - 1);
-  int y0 = max((int)floor((py - P.box_r - M.coy) * M.inv_cell), 0);
-  int y1 = min((int)floor((py + P.box_r - M.coy) * M.inv_cell), M.cny - 1);
-  int z0 = max((int)floor((pz - P.box_r - M.coz) * M.inv_cell), 0);
-  int z1 = min((int)floor((pz + P.box_r - M.coz) * M.inv_cell), M.cnz - 1);
-  float sx = (float)px, sy = (float)py, sz = (float)pz;
-  double e00 = Ei[0], e01 = Ei[1], e02 = Ei[2], e10 = Ei[3], e11 = Ei[4], e12 = Ei[5], e20 = Ei[6], e21 = Ei[7],
-         e22 = Ei[8];
-  for (int ix = x0; ix <= x1; ix++)
-    for (int iy = y0; iy <= y1; iy++) {
-      // cells along z are contiguous in the cell list: one range per (ix, iy)
-      int cbase = (ix * M.cny + iy) * M.cnz;
-      int k0 = __ldg(M.cell_start + cbase + z0), k1 = __ldg(M.cell_start + cbase + z1 + 1);
-      for (int k = k0; k < k1; k++) {
-        float4 q = __ldg(M.pts + k);
-        float dx = q.x - sx, dy = q.y - sy, dz = q.z - sz;
-        float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-        if (!(d2 <= P.kd_r2)) continue;
-        n_tested++;
-        double ddx = (double)q.x - px, ddy = (double)q.y - py, ddz = (double)q.z - pz;
-        double tx = (e00 * ddx + e01 * ddy) + e02 * ddz;
-        double ty = (e10 * ddx + e11 * ddy) + e12 * ddz;
-        double tz = (e20 * ddx + e21 * ddy) + e22 * ddz;
-        if (sqrt(dot3(tx, ty, tz, tx, ty, tz)) <= 1.0) return false;
-      }
-    }
-  return true;
+  return __ldg(M.flags + ((size_t)ix * M.ny + iy) * M.nzp + iz);
 }
 
 __device__ __forceinline__ unsigned long long pack_key(int ix, int iy, int iz, bool& ok) {
@@ -230,8 +234,11 @@ __device__ __forceinline__ uint32_t hash_key(unsigned long long k, int bits) {
 }
 
 // ---- open list: libstdc++ heap semantics on cached keys -----------------------------------------------
-// slot i (0-based) is stored at heap[i + 1]
-__device__ void heap_pop_serial(HeapSlot* H, KinoNode* nodes, int& len, HeapSlot& top) {
+// slot i (0-based) is stored at heap[i + 1]; every move also records the new position in the node's hash slot
+#define HS_DIRTY 0x80000000u
+#define HS_MASK 0x7fffffffu
+
+__device__ void heap_pop_serial(HeapSlot* H, HashSlot* table, int& len, HeapSlot& top) {
   // std::pop_heap + pop_back (bits/stl_heap.h __pop_heap -> __adjust_heap -> __push_heap), comp(a,b) = f[a] > f[b]
   top = H[1];
   int old_len = len;
@@ -246,14 +253,14 @@ __device__ void heap_pop_serial(HeapSlot* H, KinoNode* nodes, int& len, HeapSlot
     HeapSlot r = H[second + 1], l = H[second];  // right child = slot `second`, left = second-1
     if (r.f > l.f) { second--; r = l; }
     H[hole + 1] = r;
-    nodes[r.id].heap_pos = (uint32_t)hole;
+    table[r.hs].heap_pos = (uint32_t)hole;
     hole = second;
   }
   if ((n & 1) == 0 && second == (n - 2) / 2) {
     second = 2 * (second + 1);
     HeapSlot l = H[second];  // slot second-1
     H[hole + 1] = l;
-    nodes[l.id].heap_pos = (uint32_t)hole;
+    table[l.hs].heap_pos = (uint32_t)hole;
     hole = second - 1;
   }
   int parent = (hole - 1) / 2;
@@ -261,12 +268,12 @@ __device__ void heap_pop_serial(HeapSlot* H, KinoNode* nodes, int& len, HeapSlot
     HeapSlot pe = H[parent + 1];
     if (!(pe.f > value.f)) break;
     H[hole + 1] = pe;
-    nodes[pe.id].heap_pos = (uint32_t)hole;
+    table[pe.hs].heap_pos = (uint32_t)hole;
     hole = parent;
     parent = (hole - 1) / 2;
   }
   H[hole + 1] = value;
-  nodes[value.id].heap_pos = (uint32_t)hole;
+  table[value.hs].heap_pos = (uint32_t)hole;
 }
 
 // closure = the ancestors of leaves len0+1 .. len0+m (1-based heap indices), staged in shared memory by warp 0.
@@ -278,22 +285,40 @@ __device__ void closure_load(SearchSmem& s, const HeapSlot* H, int len0, int m, 
     const int lo = (len0 + 1) >> d, hi = (len0 + m) >> d;
     const int cnt = (lo >= 1) ? hi - lo + 1 : 0;
     if (lane == 0) { s.lv_lo[d] = lo; s.lv_hi[d] = (lo >= 1) ? hi : -1; s.lv_off[d] = total; }
-    if (d >= 1)
-      for (int j = lane; j < cnt; j += 32) { HeapSlot e = H[lo + j]; e.dirty = 0; s.hc[total + j] = e; }
+    if (d >= 1) {
+      for (int j = lane; j < cnt; j += 32) {
+        HeapSlot e;
+        const double2 raw = __ldcg(reinterpret_cast<const double2*>(H + lo + j));
+        e.f = raw.x;
+        const unsigned long long w = (unsigned long long)__double_as_longlong(raw.y);
+        e.id = (uint32_t)w; e.hs = (uint32_t)(w >> 32) & HS_MASK;
+        s.b.hc[total + j] = e;
+      }
+    } else {
+      for (int j = lane; j < cnt; j += 32) { HeapSlot e; e.f = 0; e.id = UAVMP_NONE; e.hs = 0; s.b.hc[total + j] = e; }
+    }
     total += cnt;
   }
   if (lane == 0) { s.hc_total = total; s.hc_active = 1; }
   __syncwarp();
 }
 
-__device__ void closure_flush(SearchSmem& s, HeapSlot* H, int lane) {
+__device__ void closure_flush(SearchSmem& s, HeapSlot* H, HashSlot* table, int lane) {
   if (!s.hc_active) return;
   __syncwarp();
   for (int d = 0; d < 32; d++) {
     const int lo = s.lv_lo[d], hi = s.lv_hi[d], off = s.lv_off[d];
     const int cnt = hi >= lo ? hi - lo + 1 : 0;
-    for (int j = lane; j < cnt; j += 32) { HeapSlot e = s.hc[off + j]; if (e.dirty) H[lo + j] = e; }
+    for (int j = lane; j < cnt; j += 32) {
+      HeapSlot e = s.b.hc[off + j];
+      if (e.hs & HS_DIRTY) {
+        e.hs &= HS_MASK;
+        H[lo + j] = e;
+        table[e.hs].heap_pos = (uint32_t)(lo + j - 1);
+      }
+    }
   }
+  __threadfence_block();
   __syncwarp();
   if (lane == 0) s.hc_active = 0;
   __syncwarp();
@@ -307,63 +332,55 @@ __device__ __forceinline__ int level_room(int len) {
 }
 
 // std::push_heap of (f, id) as 1-based leaf n1, ancestors read from the closure
-__device__ void closure_push(SearchSmem& s, KinoNode* nodes, int n1, double f, uint32_t id, int lane) {
+__device__ void closure_push(SearchSmem& s, int n1, double f, uint32_t id, uint32_t hs, int lane) {
   int a = n1 >> lane;
   bool valid = (lane >= 1) && (a >= 1);
   HeapSlot e;
-  e.f = 0; e.id = 0; e.dirty = 0;
-  if (valid) e = s.hc[s.lv_off[lane] + (a - s.lv_lo[lane])];
+  e.f = 0; e.id = 0; e.hs = 0;
+  if (valid) e = s.b.hc[s.lv_off[lane] + (a - s.lv_lo[lane])];
   bool gt = valid && (e.f > f);
   unsigned m = __ballot_sync(FULL, gt);
   unsigned cont = m >> 1;            // bit j: level j+1 moves down
   int L = __ffs(~cont) - 1;          // number of consecutive moves
   if (lane >= 1 && lane <= L) {
     int tgt = n1 >> (lane - 1);
-    e.dirty = 1;
-    s.hc[s.lv_off[lane - 1] + (tgt - s.lv_lo[lane - 1])] = e;
-    nodes[e.id].heap_pos = (uint32_t)(tgt - 1);
+    e.hs |= HS_DIRTY;
+    s.b.hc[s.lv_off[lane - 1] + (tgt - s.lv_lo[lane - 1])] = e;
   }
   if (lane == 0) {
     int tgt = n1 >> L;
-    HeapSlot ne; ne.f = f; ne.id = id; ne.dirty = 1;
-    s.hc[s.lv_off[L] + (tgt - s.lv_lo[L])] = ne;
-    nodes[id].heap_pos = (uint32_t)(tgt - 1);
+    HeapSlot ne; ne.f = f; ne.id = id; ne.hs = hs | HS_DIRTY;
+    s.b.hc[s.lv_off[L] + (tgt - s.lv_lo[L])] = ne;
   }
   __syncwarp();
 }
 
-// in-place key mutation of an element that is inside the open list (kino_astar.cpp:251-265)
-__device__ void heap_set_key(SearchSmem& s, HeapSlot* H, KinoNode* nodes, uint32_t id, double f, int lane) {
+// in-place key mutation (kino_astar.cpp:251-265) of a node that may sit among the staged ancestors: look for it in the
+// closure; if it is not there, write through its live heap position
+__device__ void heap_set_key_slow(SearchSmem& s, HeapSlot* H, const HashSlot* table, uint32_t id, uint32_t hs, double f,
+                                  int lane) {
   __syncwarp();
-  uint32_t slot = *((volatile uint32_t*)&nodes[id].heap_pos);
-  int n1 = (int)slot + 1;
-  int where = -1;
+  int found = -1;
   if (s.hc_active) {
-    bool hit = (n1 >= s.lv_lo[lane]) && (n1 <= s.lv_hi[lane]);
-    unsigned m = __ballot_sync(FULL, hit);
-    if (m) where = __ffs(m) - 1;
+    const int total = s.hc_total;
+    for (int base = 0; base < total; base += 32) {
+      const int j = base + lane;
+      const bool hit = (j < total) && (s.b.hc[j].id == id);
+      const unsigned m = __ballot_sync(FULL, hit);
+      if (m) { found = base + __ffs(m) - 1; break; }
+    }
   }
   if (lane == 0) {
-    if (where >= 0) {
-      HeapSlot& e = s.hc[s.lv_off[where] + (n1 - s.lv_lo[where])];
-      e.f = f;
-      e.dirty = 1;
+    if (found >= 0) {
+      s.b.hc[found].f = f;
+      s.b.hc[found].hs |= HS_DIRTY;
     } else {
-      H[n1].f = f;
+      __threadfence_block();
+      const uint32_t pos = __ldcg(&table[hs].heap_pos);
+      __stcg(&H[pos + 1].f, f);
     }
   }
   __syncwarp();
-}
-
-__device__ __forceinline__ void end_state(const SearchSmem& s, const KinoParamsDev& P, double ux, double uy,
-                                          double uz, double* x) {
-  // StateTransit(x0, xt, ut, sample_tau) — kino_astar.cpp:216,651-670
-  x[0] = (s.cp[0] + P.tau * s.cv[0]) + P.htau * ux;
-  x[1] = (s.cp[1] + P.tau * s.cv[1]) + P.htau * uy;
-  x[2] = (s.cp[2] + P.tau * s.cv[2]) + P.htau * uz;
-  x[3] = s.cv[0] + P.tau * ux;
-  x[4] = s.cv[1] + P.tau * uy;
-  x[5] = s.cv[2] + P.tau * uz;
 }
 
 __device__ void shot_pos(const double* c, double t, double& x, double& y, double& z) {
@@ -374,11 +391,110 @@ __device__ void shot_pos(const double* c, double t, double& x, double& y, double
   z = ((c[8] * t0 + c[9] * t1) + c[10] * t2) + c[11] * t3;
 }
 
+// ---- TMA / mbarrier primitives (sm_90+ PTX) -------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, int c0, int c1, int c2, void* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---- ellipsoid test of one (primitive, checkpoint) against the cloud points staged in shared memory ---------
+// warp-cooperative: lanes take the points of one cell column at a time; kino_astar.cpp:721-758 semantics
+// ("any cloud point p with || E^-1 (p - pt) || <= 1"; the KD-tree radius r + 0.1 is a pure superset filter, §9.1 Q12)
+__device__ __forceinline__ bool point_in_ellipsoid(const double* e, double px, double py, double pz, float4 q,
+                                                   double cull2) {
+  const double ddx = (double)q.x - px, ddy = (double)q.y - py, ddz = (double)q.z - pz;
+  if ((ddx * ddx + ddy * ddy) + ddz * ddz > cull2) return false;  // farther than the longest semi-axis (+ margin)
+  const double tx = (e[0] * ddx + e[1] * ddy) + e[2] * ddz;
+  const double ty = (e[3] * ddx + e[4] * ddy) + e[5] * ddz;
+  const double tz = (e[6] * ddx + e[7] * ddy) + e[8] * ddz;
+  return sqrt(dot3(tx, ty, tz, tx, ty, tz)) <= 1.0;
+}
+
+__device__ bool warp_ellipsoid_hit(const SearchSmem& s, const MapDev& M, const KinoParamsDev& P, const double* e,
+                                   double px, double py, double pz, int lane, unsigned& n_tested) {
+  // cell range of the bounding cube, relative to the staged region
+  const int x0 = max((int)floor((px - P.box_r - M.cox) * M.inv_cell), s.rc0[0]) - s.rc0[0];
+  const int x1 = min((int)floor((px + P.box_r - M.cox) * M.inv_cell), s.rc1[0]) - s.rc0[0];
+  const int y0 = max((int)floor((py - P.box_r - M.coy) * M.inv_cell), s.rc0[1]) - s.rc0[1];
+  const int y1 = min((int)floor((py + P.box_r - M.coy) * M.inv_cell), s.rc1[1]) - s.rc0[1];
+  const int z0 = max((int)floor((pz - P.box_r - M.coz) * M.inv_cell), s.rc0[2]) - s.rc0[2];
+  const int z1 = min((int)floor((pz + P.box_r - M.coz) * M.inv_cell), s.rc1[2]) - s.rc0[2];
+  if (x1 < x0 || y1 < y0 || z1 < z0) return false;
+  const int ncy = s.rc1[1] - s.rc0[1] + 1, ncz1 = s.rc1[2] - s.rc0[2] + 2;
+  const int wy = y1 - y0 + 1, ncol = (x1 - x0 + 1) * wy;
+  bool hit = false;
+  for (int cb = 0; cb < ncol; cb += 32) {
+    int beg = 0, cnt = 0;
+    if (cb + lane < ncol) {
+      const int lx = x0 + (cb + lane) / wy, ly = y0 + (cb + lane) % wy;
+      const int col = lx * ncy + ly;
+      const int g0 = s.a.cstart[col * ncz1 + z0], g1 = s.a.cstart[col * ncz1 + z1 + 1];
+      beg = g0 + s.a.col_delta[col];
+      cnt = g1 - g0;
+    }
+    unsigned nonempty = __ballot_sync(FULL, cnt > 0);
+    while (nonempty) {
+      const int l = __ffs(nonempty) - 1;
+      nonempty &= nonempty - 1;
+      const int b = __shfl_sync(FULL, beg, l), c = __shfl_sync(FULL, cnt, l);
+      for (int j = lane; j < c + ((32 - (c & 31)) & 31); j += 32) {  // uniform trip count for the ballot
+        bool h = false;
+        if (j < c) { h = point_in_ellipsoid(e, px, py, pz, s.a.pts[b + j], P.cull2); n_tested++; }
+        if (__any_sync(FULL, h)) { hit = true; break; }
+      }
+      if (hit) break;
+    }
+    if (hit) break;
+  }
+  return hit;
+}
+
+// fallback when the region's points do not fit in shared memory: the lane-serial cell-list walk over global memory
+__device__ bool ellipsoid_hit_global(const MapDev& M, const KinoParamsDev& P, const double* e, double px, double py,
+                                     double pz, unsigned& n_tested) {
+  int x0 = max((int)floor((px - P.box_r - M.cox) * M.inv_cell), 0);
+  int x1 = min((int)floor((px + P.box_r - M.cox) * M.inv_cell), M.cnx - 1);
+  int y0 = max((int)floor((py - P.box_r - M.coy) * M.inv_cell), 0);
+  int y1 = min((int)floor((py + P.box_r - M.coy) * M.inv_cell), M.cny - 1);
+  int z0 = max((int)floor((pz - P.box_r - M.coz) * M.inv_cell), 0);
+  int z1 = min((int)floor((pz + P.box_r - M.coz) * M.inv_cell), M.cnz - 1);
+  for (int ix = x0; ix <= x1; ix++)
+    for (int iy = y0; iy <= y1; iy++) {
+      int cbase = (ix * M.cny + iy) * M.cnz;
+      int k0 = __ldg(M.cell_start + cbase + z0), k1 = __ldg(M.cell_start + cbase + z1 + 1);
+      for (int k = k0; k < k1; k++) {
+        n_tested++;
+        if (point_in_ellipsoid(e, px, py, pz, __ldg(M.pts + k), P.cull2)) return true;
+      }
+    }
+  return false;
+}
+
 // =====================================================================================================
-__global__ void __launch_bounds__(KT) kino_search_kernel(const KinoParamsDev* __restrict__ Pp, LatticeDev lat,
-                                                         const MapDev* __restrict__ Mp, KinoArena* arenas,
-                                                         KinoBatchDev bt, int table_bits) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+__global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev* __restrict__ Pp, LatticeDev lat,
+                                                            const MapDev* __restrict__ Mp, KinoArena* arenas,
+                                                            KinoBatchDev bt, int table_bits,
+                                                            const __grid_constant__ CUtensorMap tmap, int use_tma) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   SearchSmem& s = *reinterpret_cast<SearchSmem*>(smem_raw);
   const KinoParamsDev& P = *Pp;
   const MapDev& M = *Mp;
@@ -389,8 +505,15 @@ __global__ void __launch_bounds__(KT) kino_search_kernel(const KinoParamsDev* __
   HashSlot* table = ar.table;
   const uint32_t tmask = (1u << table_bits) - 1u;
   const bool prof = bt.phase_cycles != nullptr;
+  const int na = P.na, K = P.K, nprim = P.nprim;
   if (tid < 8) s.ph[tid] = 0;
-  if (tid == 0) s.ph_t = clock64();
+  if (tid == 0) {
+    s.ph_t = clock64();
+    mbar_init(&s.mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint32_t tma_parity = 0;
+  __syncthreads();
 
   for (;;) {
     // ---- fetch the next query --------------------------------------------------------------------
@@ -428,20 +551,21 @@ __global__ void __launch_bounds__(KT) kino_search_kernel(const KinoParamsDev* __
       double h = d_heuristic(P, s.sp[0], s.sp[1], s.sp[2], s.sv[0], s.sv[1], s.sv[2], s.gp[0], s.gp[1], s.gp[2],
                              s.gv[0], s.gv[1], s.gv[2], topt);
       s.opt_time = (topt >= 0.0) ? topt : (double)(1 << 30);
-      KinoNode nd;
-      nd.px = s.sp[0]; nd.py = s.sp[1]; nd.pz = s.sp[2]; nd.vx = s.sv[0]; nd.vy = s.sv[1]; nd.vz = s.sv[2];
-      nd.g = 0.0; nd.parent = UAVMP_NONE; nd.heap_pos = 0; nd.input = 0; nd.closed = 0; nd.pad0 = 0; nd.pad1 = 0;
-      nodes[0] = nd;
-      HeapSlot hs; hs.f = P.lambda * h; hs.id = 0; hs.dirty = 0;
-      H[1] = hs;
       int ix, iy, iz; bool ok;
       pos_to_index(M, s.sp[0], s.sp[1], s.sp[2], ix, iy, iz);
       unsigned long long k = pack_key(ix, iy, iz, ok);
       if (!ok) atomicOr(bt.error_flag, 1);
       uint32_t hh = hash_key(k, table_bits);
       while ((table[hh].key & EPOCH_MASK) == epoch) hh = (hh + 1) & tmask;  // cannot happen on a fresh epoch
-      table[hh].key = (k << EPOCH_BITS) | epoch;
-      table[hh].id = 0;
+      HashSlot hsl;
+      hsl.key = (k << EPOCH_BITS) | epoch; hsl.id = 0; hsl.heap_pos = 0; hsl.g = 0.0; hsl.closed = 0; hsl.pad = 0;
+      table[hh] = hsl;
+      KinoNode nd;
+      nd.px = s.sp[0]; nd.py = s.sp[1]; nd.pz = s.sp[2]; nd.vx = s.sv[0]; nd.vy = s.sv[1]; nd.vz = s.sv[2];
+      nd.g = 0.0; nd.parent = UAVMP_NONE; nd.hslot = hh; nd.input = 0; nd.closed = 0; nd.pad0 = 0; nd.pad1 = 0;
+      nodes[0] = nd;
+      HeapSlot hs; hs.f = P.lambda * h; hs.id = 0; hs.hs = hh;
+      H[1] = hs;
       s.heap_len = 1; s.use_num = 1; s.n_pop = 0; s.status = 0; s.hc_active = 0;
       s.pop_hash = 0xcbf29ce484222325ull;
       s.cnt[3] += 1; s.cnt[4] += 1; s.cnt[6] += 1;  // hash probe, insert, heuristic of the start node
@@ -460,19 +584,18 @@ __global__ void __launch_bounds__(KT) kino_search_kernel(const KinoParamsDev* __
         } else {
           HeapSlot top;
           int len = s.heap_len;
-          heap_pop_serial(H, nodes, len, top);
+          heap_pop_serial(H, table, len, top);
           s.heap_len = len;
           KinoNode nd = nodes[top.id];
           nodes[top.id].closed = 1;
+          table[top.hs].closed = 1;
           s.cur_id = top.id; s.cur_parent = nd.parent;
           s.cp[0] = nd.px; s.cp[1] = nd.py; s.cp[2] = nd.pz; s.cv[0] = nd.vx; s.cv[1] = nd.vy; s.cv[2] = nd.vz;
           s.cg = nd.g;
           int ix, iy, iz;
           pos_to_index(M, nd.px, nd.py, nd.pz, ix, iy, iz);
-          if (nd.parent == UAVMP_NONE) { /* start node keeps its own index */ }
-          // the node's pruning index is the voxel of its (possibly mutated) position?  No: the reference never
-          // updates node->index on mutation (:256 is commented out) but the mutated position lies in the same
-          // voxel by construction (the lookup key), so recomputing it is identical.
+          // the reference never updates node->index on an in-place mutation (:256 is commented out), but the mutated
+          // position lies in the same voxel by construction (it was found through that key), so this is identical
           unsigned long long ph = s.pop_hash;
           ph = mix64(ph, (unsigned long long)(uint32_t)ix);
           ph = mix64(ph, (unsigned long long)(uint32_t)iy);
@@ -488,10 +611,9 @@ __global__ void __launch_bounds__(KT) kino_search_kernel(const KinoParamsDev* __
           s.n_pop++;
           double dx = nd.px - s.gp[0], dy = nd.py - s.gp[1], dz = nd.pz - s.gp[2];
           s.flag = (sqrt(dot3(dx, dy, dz, dx, dy, dz)) < P.goal_tol) ? 1 : 0;
-          s.n1 = 0; s.n2 = 0;
+          s.n1 = 0; s.n2 = 0; s.nT = 0; s.tnext = 0;
         }
       }
-      for (int i = tid; i < TAB_SIZE; i += KT) s.tab[i] = 0;
       __syncthreads();
       PH_MARK(0);
       if (s.status) break;
@@ -572,41 +694,193 @@ __global__ void __launch_bounds__(KT) kino_search_kernel(const KinoParamsDev* __
         if (s.status) break;
       }
 
-      // ---- A. evaluate the motion primitives (:158-216) ---------------------------------------------
-      for (int p = tid; p < P.nprim; p += KT) {
-        const double ux = lat.ux[p], uy = lat.uy[p], uz = lat.uz[p];
+      // ---- A0. separable tables: every checkpoint / end-state coordinate is (c + t v) + h u per axis, and u comes
+      // from a tensor lattice, so there are only K * 3 * na distinct coordinates (StateTransit, :651-670) -----------
+      for (int e = tid; e < (K + 1) * 3 * na; e += KT) {
+        const int i = e / (3 * na), ax = (e / na) % 3, a = e % na;
+        const double u = P.ua[a];
+        const double t = (i < K) ? P.tk[i] : P.tau, h = (i < K) ? P.hk[i] : P.htau;
+        const double x = (s.cp[ax] + t * s.cv[ax]) + h * u;
+        const double v = s.cv[ax] + t * u;
+        const double org = ax == 0 ? M.ox : (ax == 1 ? M.oy : M.oz);
+        const int idx = (int)floor((x - org) * M.inv_res);
+        if (i < K) {
+          const double lo = ax == 0 ? M.lox : (ax == 1 ? M.loy : M.loz), hi = ax == 0 ? M.hix : (ax == 1 ? M.hiy : M.hiz);
+          const bool ok = !(x < lo) && !(x > hi) && !(v < -P.vmax) && !(v > P.vmax);
+          s.X[i][ax][a] = x; s.XI[i][ax][a] = idx; s.XOK[i][ax][a] = ok ? 1 : 0;
+        } else {
+          s.EX[ax][a] = x; s.EV[ax][a] = v; s.EI[ax][a] = idx;
+        }
+      }
+      __syncthreads();
+      // per-axis feasibility over all checkpoints + the voxel / position extent of the feasible part
+      if (tid < 3 * na) {
+        const int ax = tid / na, a = tid % na;
         bool ok = true;
-        for (int i = 0; i < P.K && ok; i++) {
-          const double t = P.tk[i], h = P.hk[i];
-          const double x = (s.cp[0] + t * s.cv[0]) + h * ux;
-          const double y = (s.cp[1] + t * s.cv[1]) + h * uy;
-          const double z = (s.cp[2] + t * s.cv[2]) + h * uz;
-          if (!in_map(M, x, y, z)) { ok = false; break; }
-          int ix, iy, iz;
-          pos_to_index(M, x, y, z, ix, iy, iz);
-          const unsigned fl = map_flags(M, ix, iy, iz);
-          my_occ++;
-          if (P.ctype == 1 && (fl & 1u)) { ok = false; break; }
-          if ((fl & 4u) && !ellipsoid_free(M, P, lat.Einv + 9 * p, x, y, z, my_cloud)) { ok = false; break; }
-          const double vx = s.cv[0] + t * ux, vy = s.cv[1] + t * uy, vz = s.cv[2] + t * uz;
-          if (vx < -P.vmax || vx > P.vmax || vy < -P.vmax || vy > P.vmax || vz < -P.vmax || vz > P.vmax) ok = false;
+        int imin = INT_MAX, imax = INT_MIN;
+        double xmin = 1e300, xmax = -1e300;
+        for (int i = 0; i < K; i++) {
+          ok = ok && s.XOK[i][ax][a];
+          imin = min(imin, s.XI[i][ax][a]); imax = max(imax, s.XI[i][ax][a]);
+          xmin = fmin(xmin, s.X[i][ax][a]); xmax = fmax(xmax, s.X[i][ax][a]);
         }
-        uint8_t st = ST_REJECT;
-        if (ok) {
-          double xe[6];
-          end_state(s, P, ux, uy, uz, xe);
-          int ix, iy, iz;
-          pos_to_index(M, xe[0], xe[1], xe[2], ix, iy, iz);
-          bool kok;
-          s.key[p] = pack_key(ix, iy, iz, kok);
-          if (!kok) atomicOr(bt.error_flag, 1);
-          st = ST_FEASIBLE;
-          s.list1[atomicAdd(&s.n1, 1)] = (uint16_t)p;
+        s.axok[ax][a] = ok ? 1 : 0;
+        s.aimin[ax][a] = ok ? imin : INT_MAX; s.aimax[ax][a] = ok ? imax : INT_MIN;
+        s.axmin[ax][a] = ok ? xmin : 1e300;   s.axmax[ax][a] = ok ? xmax : -1e300;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        bool any = true, fits = true;
+        for (int ax = 0; ax < 3; ax++) {
+          int lo = INT_MAX, hi = INT_MIN;
+          double xl = 1e300, xh = -1e300;
+          for (int a = 0; a < na; a++) {
+            lo = min(lo, s.aimin[ax][a]); hi = max(hi, s.aimax[ax][a]);
+            xl = fmin(xl, s.axmin[ax][a]); xh = fmax(xh, s.axmax[ax][a]);
+          }
+          if (ax == 2) lo &= ~15;  // measured: UTMALDG faults unless inner coordinate * element size is 16 B aligned
+          if (lo > hi) any = false;
+          else if (hi - lo + 1 > (ax == 2 ? TBZ : TB)) fits = false;
+          s.to[ax] = lo; s.xlo[ax] = xl; s.xhi[ax] = xh;
         }
-        s.state[p] = st;
+        s.any_ok = any ? 1 : 0;
+        s.tile_ok = (any && fits && use_tma) ? 1 : 0;
+        if (s.tile_ok) {
+          // stage the flags box (inner dimension z): one TMA instruction, completion on the mbarrier
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_expect_tx(&s.mbar, TB * TB * TBZ);
+          tma_load_3d(s.a.tile, &tmap, s.to[2], s.to[1], s.to[0], &s.mbar);
+        }
+      }
+      __syncthreads();
+      const bool tile_ok = s.tile_ok != 0;
+      if (tile_ok) { mbar_wait(&s.mbar, tma_parity); tma_parity ^= 1u; }
+
+      // ---- A1. grid + velocity + in-map for every primitive from shared memory (:172-211 minus the ellipsoid) ----
+      if (s.any_ok) {
+        const int tx = s.to[0], ty = s.to[1], tz = s.to[2];
+        for (int p = tid; p < nprim; p += KT) {
+          const int a = p / (na * na), b = (p / na) % na, c = p % na;
+          uint8_t st = ST_REJECT;
+          unsigned need = 0;
+          if (s.axok[0][a] && s.axok[1][b] && s.axok[2][c]) {
+            bool ok = true;
+            for (int i = 0; i < K; i++) {
+              const int ix = s.XI[i][0][a], iy = s.XI[i][1][b], iz = s.XI[i][2][c];
+              const unsigned fl = tile_ok ? s.a.tile[((ix - tx) * TB + (iy - ty)) * TBZ + (iz - tz)] : map_flags(M, ix, iy, iz);
+              my_occ++;
+              if (P.ctype == 1 && (fl & 1u)) { ok = false; break; }
+              if (fl & 4u) need |= 1u << i;
+            }
+            if (ok) st = ST_FEASIBLE;
+          }
+          s.state[p] = st;
+          if (st == ST_FEASIBLE && need) { s.need[p] = (uint16_t)need; s.listT[atomicAdd(&s.nT, 1)] = (uint16_t)p; }
+        }
+      } else {
+        for (int p = tid; p < nprim; p += KT) s.state[p] = ST_REJECT;
       }
       __syncthreads();
       PH_MARK(2);
+
+      // ---- A2. SE(3) ellipsoid vs cloud for the primitives that pass near obstacles (:721-758) ----------------------
+      const int nT = s.nT;
+      if (nT > 0) {
+        // stage the cell list of the region the feasible checkpoints can touch: cell_start entries, then the points
+        if (tid < 3) {
+          const double co = tid == 0 ? M.cox : (tid == 1 ? M.coy : M.coz);
+          const int cn = tid == 0 ? M.cnx : (tid == 1 ? M.cny : M.cnz);
+          s.rc0[tid] = max((int)floor((s.xlo[tid] - P.box_r - co) * M.inv_cell), 0);
+          s.rc1[tid] = min((int)floor((s.xhi[tid] + P.box_r - co) * M.inv_cell), cn - 1);
+        }
+        __syncthreads();
+        const int ncx = s.rc1[0] - s.rc0[0] + 1, ncy = s.rc1[1] - s.rc0[1] + 1, ncz1 = s.rc1[2] - s.rc0[2] + 2;
+        const int ncols = ncx * ncy;
+        bool staged = (ncx > 0 && ncy > 0 && ncz1 > 1) && ncols <= COL_CAP && ncols * ncz1 <= CS_CAP;
+        if (staged) {
+          for (int e = tid; e < ncols * ncz1; e += KT) {
+            const int col = e / ncz1, lz = e % ncz1;
+            const int gx = s.rc0[0] + col / ncy, gy = s.rc0[1] + col % ncy, gz = s.rc0[2] + lz;
+            s.a.cstart[e] = __ldg(M.cell_start + ((gx * M.cny + gy) * M.cnz + gz));
+          }
+          __syncthreads();
+          if (warp == 0) {  // exclusive scan of the column sizes -> shared-memory offset of each column
+            int run = 0;
+            for (int cb = 0; cb < ncols; cb += 32) {
+              const int col = cb + lane;
+              const int cnt = col < ncols ? s.a.cstart[col * ncz1 + ncz1 - 1] - s.a.cstart[col * ncz1] : 0;
+              int incl = cnt;
+#pragma unroll
+              for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+              if (col < ncols) s.a.col_delta[col] = run + incl - cnt - s.a.cstart[col * ncz1];
+              run += __shfl_sync(FULL, incl, 31);
+            }
+            if (lane == 0) s.npts = run;
+          }
+          __syncthreads();
+          staged = s.npts <= PTS_CAP;
+          if (staged) {
+            for (int col = warp; col < ncols; col += KT / 32) {
+              const int g0 = s.a.cstart[col * ncz1], g1 = s.a.cstart[col * ncz1 + ncz1 - 1], d = s.a.col_delta[col];
+              for (int g = g0 + lane; g < g1; g += 32) s.a.pts[g + d] = __ldg(M.pts + g);
+            }
+          }
+          __syncthreads();
+        }
+        if (staged) {
+          // warps pull primitives; each tests its flagged checkpoints in turn and stops at the first hit
+          for (;;) {
+            int e = 0;
+            if (lane == 0) e = atomicAdd(&s.tnext, 1);
+            e = __shfl_sync(FULL, e, 0);
+            if (e >= nT) break;
+            const int p = s.listT[e];
+            const int a = p / (na * na), b = (p / na) % na, c = p % na;
+            unsigned need = s.need[p];
+            const double* ei = lat.Einv + 9 * p;
+            double em[9];
+#pragma unroll
+            for (int j = 0; j < 9; j++) em[j] = __ldg(ei + j);
+            while (need) {
+              const int i = __ffs(need) - 1;
+              need &= need - 1;
+              if (warp_ellipsoid_hit(s, M, P, em, s.X[i][0][a], s.X[i][1][b], s.X[i][2][c], lane, my_cloud)) {
+                if (lane == 0) s.state[p] = ST_REJECT;
+                break;
+              }
+            }
+          }
+        } else {
+          for (int e = tid; e < nT; e += KT) {
+            const int p = s.listT[e];
+            const int a = p / (na * na), b = (p / na) % na, c = p % na;
+            unsigned need = s.need[p];
+            double em[9];
+            for (int j = 0; j < 9; j++) em[j] = __ldg(lat.Einv + 9 * p + j);
+            while (need) {
+              const int i = __ffs(need) - 1;
+              need &= need - 1;
+              if (ellipsoid_hit_global(M, P, em, s.X[i][0][a], s.X[i][1][b], s.X[i][2][c], my_cloud)) {
+                s.state[p] = ST_REJECT;
+                break;
+              }
+            }
+          }
+        }
+        __syncthreads();
+      }
+      // survivors: end state -> voxel key (:216, posToIndex :302-310); the dedup table lives where the tile was
+      for (int i = tid; i < TAB_SIZE; i += KT) s.b.tab[i] = 0;
+      for (int p = tid; p < nprim; p += KT) {
+        if (s.state[p] != ST_FEASIBLE) continue;
+        const int a = p / (na * na), b = (p / na) % na, c = p % na;
+        bool kok;
+        s.key[p] = pack_key(s.EI[0][a], s.EI[1][b], s.EI[2][c], kok);
+        if (!kok) atomicOr(bt.error_flag, 1);
+        s.list1[atomicAdd(&s.n1, 1)] = (uint16_t)p;
+      }
+      __syncthreads();
+      PH_MARK(3);
       const int n1 = s.n1;
 
       // ---- B1. group identical voxel keys inside this expansion --------------------------------------
@@ -615,37 +889,42 @@ __global__ void __launch_bounds__(KT) kino_search_kernel(const KinoParamsDev* __
         const unsigned long long k = s.key[p];
         uint32_t h = hash_key(k, 11);
         for (;;) {
-          uint32_t cur = s.tab[h];
+          uint32_t cur = s.b.tab[h];
           if (cur == 0) {
-            cur = atomicCAS(&s.tab[h], 0u, (uint32_t)p + 1u);
+            cur = atomicCAS(&s.b.tab[h], 0u, (uint32_t)p + 1u);
             if (cur == 0) break;
           }
-          if (s.key[cur - 1] == k) { atomicMin(&s.tab[h], (uint32_t)p + 1u); break; }
+          if (s.key[cur - 1] == k) { atomicMin(&s.b.tab[h], (uint32_t)p + 1u); break; }
           h = (h + 1) & (TAB_SIZE - 1);
         }
         s.id[p] = h;
       }
       __syncthreads();
-      // ---- B2. leaders probe the global table (:220-225) --------------------------------------------
+      // ---- B2. leaders probe the global table (:220-225): one 32 B sector per probe --------------------
       for (int e = tid; e < n1; e += KT) {
         const int p = s.list1[e];
-        const int leader = (int)s.tab[s.id[p]] - 1;
+        const int leader = (int)s.b.tab[s.id[p]] - 1;
         if (leader != p) { s.id[p] = (uint32_t)leader; s.state[p] = ST_FOLLOW_NOCAND; continue; }
         const unsigned long long k = s.key[p];
         const double gp = s.cg + lat.ginc[p];
         uint32_t h = hash_key(k, table_bits);
         uint8_t st;
+        s.b.win[p] = 0xffff;
+        s.b.inun[p] = 0;
         for (;;) {
-          HashSlot hs = table[h];
-          if ((uint32_t)(hs.key & EPOCH_MASK) != epoch) { st = ST_NEW; s.gcur[p] = gp; break; }
-          if ((hs.key >> EPOCH_BITS) == k) {
-            const KinoNode& nd = nodes[hs.id];
-            if (nd.closed) {
+          const uint4 w0 = __ldcg(reinterpret_cast<const uint4*>(&table[h]));      // key | id | heap_pos
+          const unsigned long long hk = ((unsigned long long)w0.y << 32) | w0.x;
+          if ((uint32_t)(hk & EPOCH_MASK) != epoch) { st = ST_NEW; s.b.gcur[p] = gp; break; }
+          if ((hk >> EPOCH_BITS) == k) {
+            const uint4 w1 = __ldcg(reinterpret_cast<const uint4*>(&table[h]) + 1);  // g | closed | pad
+            if (w1.z) {
               st = ST_CLOSED;
             } else {
-              double gold = nd.g;
-              s.gcur[p] = gold;
-              s.id[p] = hs.id;
+              const double gold = __longlong_as_double(((long long)w1.y << 32) | (long long)w1.x);
+              s.b.gcur[p] = gold;
+              s.id[p] = w0.z;
+              s.b.hs[p] = h;
+              s.b.hpos[p] = w0.w;
               st = (gp < gold) ? ST_OPEN_CAND : ST_OPEN_NOCAND;
             }
             break;
@@ -665,26 +944,24 @@ __global__ void __launch_bounds__(KT) kino_search_kernel(const KinoParamsDev* __
             st = ST_CLOSED;
           } else {
             const double gp = s.cg + lat.ginc[p];
-            if (gp < s.gcur[leader]) st = ST_FOLLOW_CAND;
+            if (gp < s.b.gcur[leader]) st = ST_FOLLOW_CAND;
           }
           s.state[p] = st;
         }
         if (st == ST_NEW || st == ST_OPEN_CAND || st == ST_FOLLOW_CAND) s.list2[atomicAdd(&s.n2, 1)] = (uint16_t)p;
       }
       __syncthreads();
-      PH_MARK(3);
       const int n2 = s.n2;
       // ---- B3. heuristic for every candidate (:232,:259) ----------------------------------------------
       for (int e = tid; e < n2; e += KT) {
         const int p = s.list2[e];
-        double xe[6];
-        end_state(s, P, lat.ux[p], lat.uy[p], lat.uz[p], xe);
+        const int a = p / (na * na), b = (p / na) % na, c = p % na;
         double topt;
-        const double h = d_heuristic(P, xe[0], xe[1], xe[2], xe[3], xe[4], xe[5], s.gp[0], s.gp[1], s.gp[2], s.gv[0],
-                                     s.gv[1], s.gv[2], topt);
+        const double h = d_heuristic(P, s.EX[0][a], s.EX[1][b], s.EX[2][c], s.EV[0][a], s.EV[1][b], s.EV[2][c], s.gp[0],
+                                     s.gp[1], s.gp[2], s.gv[0], s.gv[1], s.gv[2], topt);
         const double gp = s.cg + lat.ginc[p];
-        s.f[p] = gp + P.lambda * h;
-        s.topt[p] = topt;
+        s.b.f[p] = gp + P.lambda * h;
+        s.b.topt[p] = topt;
       }
       // ---- C. ordered id assignment for new nodes (== use_node_num_++ in lattice order) ----------------
       {
@@ -693,7 +970,7 @@ __global__ void __launch_bounds__(KT) kino_search_kernel(const KinoParamsDev* __
 #pragma unroll
         for (int j = 0; j < 3; j++) {
           const int p = p0 + j;
-          if (p < P.nprim && s.state[p] == ST_NEW) c++;
+          if (p < nprim && s.state[p] == ST_NEW) c++;
         }
         int incl = c;
 #pragma unroll
@@ -710,7 +987,7 @@ __global__ void __launch_bounds__(KT) kino_search_kernel(const KinoParamsDev* __
 #pragma unroll
         for (int j = 0; j < 3; j++) {
           const int p = p0 + j;
-          if (p < P.nprim && s.state[p] == ST_NEW) s.id[p] = (uint32_t)(base + excl++);
+          if (p < nprim && s.state[p] == ST_NEW) s.id[p] = (uint32_t)(base + excl++);
         }
         if (tid == KT - 1) s.n_new = woff + incl;
       }
@@ -731,14 +1008,8 @@ __global__ void __launch_bounds__(KT) kino_search_kernel(const KinoParamsDev* __
       for (int e = tid; e < n2; e += KT) {
         const int p = s.list2[e];
         if (s.state[p] != ST_NEW) continue;
-        double xe[6];
-        end_state(s, P, lat.ux[p], lat.uy[p], lat.uz[p], xe);
+        const int a = p / (na * na), b = (p / na) % na, c = p % na;
         const uint32_t nid = s.id[p];
-        KinoNode nd;
-        nd.px = xe[0]; nd.py = xe[1]; nd.pz = xe[2]; nd.vx = xe[3]; nd.vy = xe[4]; nd.vz = xe[5];
-        nd.g = s.cg + lat.ginc[p];
-        nd.parent = s.cur_id; nd.heap_pos = 0; nd.input = (uint16_t)p; nd.closed = 0; nd.pad0 = 0; nd.pad1 = 0;
-        nodes[nid] = nd;
         const unsigned long long k = s.key[p];
         const unsigned long long want = (k << EPOCH_BITS) | epoch;
         uint32_t h = hash_key(k, table_bits);
@@ -746,23 +1017,35 @@ __global__ void __launch_bounds__(KT) kino_search_kernel(const KinoParamsDev* __
           unsigned long long cur = table[h].key;
           if ((uint32_t)(cur & EPOCH_MASK) != epoch) {
             unsigned long long old = atomicCAS(&table[h].key, cur, want);
-            if (old == cur) { table[h].id = nid; break; }
+            if (old == cur) break;
             continue;  // somebody else claimed it: re-read the same slot
           }
           h = (h + 1) & tmask;
         }
+        const double g = s.cg + lat.ginc[p];
+        table[h].id = nid; table[h].g = g; table[h].closed = 0;
+        s.b.hs[p] = h;
+        KinoNode nd;
+        nd.px = s.EX[0][a]; nd.py = s.EX[1][b]; nd.pz = s.EX[2][c];
+        nd.vx = s.EV[0][a]; nd.vy = s.EV[1][b]; nd.vz = s.EV[2][c];
+        nd.g = g;
+        nd.parent = s.cur_id; nd.hslot = h; nd.input = (uint16_t)p; nd.closed = 0; nd.pad0 = 0; nd.pad1 = 0;
+        nodes[nid] = nd;
       }
       __syncthreads();
       PH_MARK(5);
 
-      // ---- D. ordered commit: heap pushes and in-place mutations (:225-266) ----------------------------
+      // ---- D. ordered commit (:225-266).  Warp 0 replays the candidates in lattice order, touching shared memory
+      // only: heap pushes go through the staged ancestor closure, in-place mutations of nodes that are NOT ancestors
+      // of any new leaf are merely recorded (their heap position cannot change during this expansion) -------------
       if (warp == 0) {
         int pushed = 0, len = s.heap_len, batch_left = 0;
+        const int len0 = len;
         double opt_time = s.opt_time;
         int n_upd = 0;
-        for (int pb = 0; pb < P.nprim; pb += 32) {
+        for (int pb = 0; pb < nprim; pb += 32) {
           const int p = pb + lane;
-          const uint8_t st = (p < P.nprim) ? s.state[p] : ST_REJECT;
+          const uint8_t st = (p < nprim) ? s.state[p] : ST_REJECT;
           unsigned evm = __ballot_sync(FULL, st == ST_NEW || st == ST_OPEN_CAND || st == ST_FOLLOW_CAND);
           while (evm) {
             const int l = __ffs(evm) - 1;
@@ -771,45 +1054,62 @@ __global__ void __launch_bounds__(KT) kino_search_kernel(const KinoParamsDev* __
             const uint8_t ste = s.state[pe];
             if (ste == ST_NEW) {
               if (batch_left == 0) {
-                closure_flush(s, H, lane);
+                closure_flush(s, H, table, lane);
                 batch_left = min(min(PUSH_BATCH, n_new - pushed), level_room(len));
                 closure_load(s, H, len, batch_left, lane);
               }
-              closure_push(s, nodes, len + 1, s.f[pe], s.id[pe], lane);
+              closure_push(s, len + 1, s.b.f[pe], s.id[pe], s.b.hs[pe], lane);
               len++;
               pushed++;
               batch_left--;
-              if (s.topt[pe] >= 0.0) opt_time = s.topt[pe];
+              if (s.b.topt[pe] >= 0.0) opt_time = s.b.topt[pe];
             } else {
-              int leader = pe;
-              uint32_t nid;
-              if (ste == ST_FOLLOW_CAND) { leader = (int)s.id[pe]; nid = s.id[leader]; }
-              else nid = s.id[pe];
+              const int leader = (ste == ST_FOLLOW_CAND) ? (int)s.id[pe] : pe;
               const double gp = s.cg + lat.ginc[pe];
-              if (gp < s.gcur[leader]) {  // tmp_g_cost < old_node->g_cost (:254)
+              if (gp < s.b.gcur[leader]) {  // tmp_g_cost < old_node->g_cost (:254)
+                const bool lead_new = s.state[leader] == ST_NEW;
+                bool in_union = lead_new;
+                if (!lead_new) {
+                  // is the node an ancestor of one of this expansion's new leaves?
+                  const int pos1 = (int)s.b.hpos[leader] + 1;
+                  const int d = lane;
+                  const int lo = (len0 + 1) >> d, hi = (len0 + n_new) >> d;
+                  in_union = __any_sync(FULL, n_new > 0 && lo >= 1 && pos1 >= lo && pos1 <= hi);
+                }
                 __syncwarp();
-                if (lane == 0) s.gcur[leader] = gp;
-                double xe[6];
-                end_state(s, P, lat.ux[pe], lat.uy[pe], lat.uz[pe], xe);
-                KinoNode* nd = nodes + nid;
-                if (lane < 6) (&nd->px)[lane] = xe[lane];
-                if (lane == 6) nd->g = gp;
-                if (lane == 7) nd->parent = s.cur_id;
-                if (lane == 8) nd->input = (uint16_t)pe;
-                heap_set_key(s, H, nodes, nid, s.f[pe], lane);
-                if (s.topt[pe] >= 0.0) opt_time = s.topt[pe];
+                if (lane == 0) { s.b.gcur[leader] = gp; s.b.win[leader] = (uint16_t)pe; if (in_union) s.b.inun[leader] = 1; }
+                if (in_union) heap_set_key_slow(s, H, table, s.id[leader], s.b.hs[leader], s.b.f[pe], lane);
+                if (s.b.topt[pe] >= 0.0) opt_time = s.b.topt[pe];
                 n_upd++;
+                __syncwarp();
               }
             }
           }
         }
-        closure_flush(s, H, lane);
+        closure_flush(s, H, table, lane);
         if (lane == 0) {
           s.heap_len = len;
           s.use_num += n_new;
           s.opt_time = opt_time;
           s.cnt[3] += n1; s.cnt[4] += n_new; s.cnt[5] += n_upd; s.cnt[6] += n_new + n_upd;
         }
+      }
+      __syncthreads();
+      // ---- D2. the recorded mutations, in parallel: node state, g in the hash slot, and the cached heap key ------
+      for (int e = tid; e < n1; e += KT) {
+        const int p = s.list1[e];
+        const uint8_t st = s.state[p];
+        if (st != ST_NEW && st != ST_OPEN_CAND && st != ST_OPEN_NOCAND) continue;  // leaders only
+        const int w = s.b.win[p];
+        if (w == 0xffff) continue;
+        const int a = w / (na * na), b = (w / na) % na, c = w % na;
+        KinoNode* nd = nodes + s.id[p];
+        nd->px = s.EX[0][a]; nd->py = s.EX[1][b]; nd->pz = s.EX[2][c];
+        nd->vx = s.EV[0][a]; nd->vy = s.EV[1][b]; nd->vz = s.EV[2][c];
+        const double g = s.cg + lat.ginc[w];
+        nd->g = g; nd->parent = s.cur_id; nd->input = (uint16_t)w;
+        table[s.b.hs[p]].g = g;
+        if (st != ST_NEW && !s.b.inun[p]) H[s.b.hpos[p] + 1].f = s.b.f[w];
       }
       __syncthreads();
       PH_MARK(6);
@@ -872,6 +1172,10 @@ __global__ void k_dilate(const uint8_t* in, uint8_t* out, int nx, int ny, int nz
 __global__ void k_or_near(uint8_t* flags, const uint8_t* near, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) flags[i] = (uint8_t)((flags[i] & 3u) | (near[i] ? 4u : 0u));
+}
+__global__ void k_pad_flags(const uint8_t* in, uint8_t* out, int nz, int nzp, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[(i / nz) * nzp + (i % nz)] = in[i];
 }
 __global__ void k_cell_ids(const float* cloud, int n, MapDev M, int* cell, int* idx) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -993,6 +1297,9 @@ int kino_upload_params(uavmp_ctx* ctx) {
   P.box_r = std::max(kp.robot_r, kp.robot_h) * 1.001 + 1e-6;
   float radius = (float)(kp.robot_r + 1e-1);
   P.kd_r2 = radius * radius;
+  P.cull2 = P.box_r * P.box_r;
+  if (std::max(kp.robot_r, kp.robot_h) >= kp.robot_r + 0.1)
+    return uavmp_fail(ctx, UAVMP_EINVAL, "robot_h >= robot_r + 0.1: the KD-tree radius of kino_astar.cpp:744 would cut the ellipsoid");
 
   // acceleration lattice by float accumulation, ax outer / az inner (kino_astar.cpp:158-160)
   std::vector<double> ux, uy, uz;
@@ -1006,6 +1313,16 @@ int kino_upload_params(uavmp_ctx* ctx) {
       }
   const int n = (int)ux.size();
   P.nprim = n;
+  // the lattice is the tensor product of one per-axis value list (same accumulation on every axis)
+  int na = 0;
+  while (na < n && (na == 0 || uz[na] > uz[na - 1]) && uy[na] == uy[0] && ux[na] == ux[0]) na++;
+  if (na < 1 || na > UAVMP_MAXNA || na * na * na != n)
+    return uavmp_fail(ctx, UAVMP_EINVAL, "acceleration lattice is not a (2r+1)^3 tensor grid with r <= %d", (UAVMP_MAXNA - 1) / 2);
+  for (int p = 0; p < n; p++)
+    if (ux[p] != uz[p / (na * na)] || uy[p] != uz[(p / na) % na] || uz[p] != uz[p % na])
+      return uavmp_fail(ctx, UAVMP_EINVAL, "acceleration lattice is not a tensor grid");
+  P.na = na;
+  for (int a = 0; a < na; a++) P.ua[a] = uz[a];
   std::vector<double> host((size_t)n * 13);
   double* hux = host.data(); double* huy = hux + n; double* huz = huy + n; double* hg = huz + n; double* hE = hg + n;
   for (int p = 0; p < n; p++) {
@@ -1119,13 +1436,42 @@ int kino_build_map(uavmp_ctx* ctx) {
   } else {
     UAVMP_CUDA(ctx, cudaMemsetAsync(ctx->d_cell_start, 0, (size_t)(ncell + 2) * sizeof(int), st));
   }
-  M.flags = ctx->d_flags;
+  // padded copy [nx][ny][nzp] (nzp multiple of 16: TMA needs 16 B strides) + the tensor map over it
+  M.nzp = (M.nz + 15) & ~15;
+  const size_t npad = (size_t)M.nx * M.ny * M.nzp;
+  if (ctx->d_flags_pad) { cudaFree(ctx->d_flags_pad); ctx->d_flags_pad = nullptr; }
+  UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_flags_pad, npad + 256));
+  UAVMP_CUDA(ctx, cudaMemsetAsync(ctx->d_flags_pad, 0, npad + 256, st));
+  k_pad_flags<<<nblk(nvox, 256), 256, 0, st>>>(ctx->d_flags, ctx->d_flags_pad, M.nz, M.nzp, nvox);
+  M.flags = ctx->d_flags_pad;
   M.cell_start = ctx->d_cell_start;
   M.pts = ctx->d_pts;
   if (!ctx->d_map) UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_map, sizeof(MapDev)));
   UAVMP_CUDA(ctx, cudaMemcpyAsync(ctx->d_map, &M, sizeof(M), cudaMemcpyHostToDevice, st));
   UAVMP_CUDA(ctx, cudaStreamSynchronize(st));
   UAVMP_CUDA(ctx, cudaGetLastError());
+  // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+  ctx->have_tmap = false;
+  {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
+        qres == cudaDriverEntryPointSuccess) {
+      static_assert(sizeof(CUtensorMap) <= sizeof(ctx->tmap_bytes), "tensor map storage");
+      cuuint64_t dims[3] = {(cuuint64_t)M.nzp, (cuuint64_t)M.ny, (cuuint64_t)M.nx};
+      cuuint64_t strides[2] = {(cuuint64_t)M.nzp, (cuuint64_t)M.nzp * M.ny};
+      cuuint32_t box[3] = {TBZ, TB, TB};
+      cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = ((EncodeFn)fn)((CUtensorMap*)ctx->tmap_bytes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ctx->d_flags_pad, dims,
+                                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      ctx->have_tmap = (r == CUDA_SUCCESS);
+    }
+    if (!ctx->have_tmap) memset(ctx->tmap_bytes, 0, sizeof(ctx->tmap_bytes));
+  }
   ctx->flags_dirty = false;
   return UAVMP_OK;
 }
@@ -1245,7 +1591,10 @@ int kino_launch_search(uavmp_ctx* ctx, int B, const double* d_sp, const double* 
   const int grid = std::min(ctx->n_arenas, B);
   ctx->last_grid = grid;
   cudaFuncSetAttribute(kino_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SearchSmem));
-  kino_search_kernel<<<grid, KT, sizeof(SearchSmem), st>>>(ctx->d_kparams, lat, ctx->d_map, ctx->d_arenas, bt, bits);
+  CUtensorMap tm;
+  memcpy(&tm, ctx->tmap_bytes, sizeof(tm));
+  kino_search_kernel<<<grid, KT, sizeof(SearchSmem), st>>>(ctx->d_kparams, lat, ctx->d_map, ctx->d_arenas, bt, bits, tm,
+                                                          (ctx->have_tmap && !getenv("UAVMP_NO_TMA")) ? 1 : 0);
   UAVMP_CUDA(ctx, cudaGetLastError());
   ctx->tm.search_launches = 1;
   return UAVMP_OK;

@@ -9,16 +9,19 @@
 #include "uavmp.h"
 
 #define UAVMP_MAXPRIM 736   // (2*acc_resolution+1)^3 <= 729  (acc_resolution <= 4), padded to 23 warps
-#define UAVMP_MAXK 32       // checkpoints per primitive: floor(sample_tau/time_step_size)+1
+#define UAVMP_MAXK 16       // checkpoints per primitive: floor(sample_tau/time_step_size)+1
+#define UAVMP_MAXNA 9       // lattice values per axis: 2*acc_resolution+1
 #define UAVMP_NONE 0xffffffffu
 
 // ---- device-side views ---------------------------------------------------------------------------
 struct KinoParamsDev {
-  int allocated, ctype, K, nprim;
+  int allocated, ctype, K, nprim, na;
+  double ua[UAVMP_MAXNA];  // the per-axis acceleration values (the lattice is their tensor product, ax outer / az inner)
   double rou, lambda, goal_tol, step, vmax, tau, tie;
   double robot_r, robot_h;
   double box_r;     // conservative half-extent of the ellipsoid bounding cube
   float kd_r2;      // (float)(robot_r + 0.1) squared: the KD-tree radius filter of kino_astar.cpp:744
+  double cull2;     // (max semi-axis * 1.001 + 1e-6)^2: farther points cannot be inside the ellipsoid
   double tk[UAVMP_MAXK];  // i * step_size
   double hk[UAVMP_MAXK];  // 0.5 * t * t
   double htau;            // 0.5 * tau * tau
@@ -33,7 +36,8 @@ struct LatticeDev {
 
 struct MapDev {
   const uint8_t* flags;  // bit0: inflate==1, bit1: inflate!=0, bit2: a cloud point may lie within the ellipsoid box
-  int nx, ny, nz;
+                         // layout [nx][ny][nzp], z fastest, nzp = nz rounded up to 16 (TMA needs 16 B row strides)
+  int nx, ny, nz, nzp;
   double ox, oy, oz;                    // mp_.map_origin_
   double lox, loy, loz, hix, hiy, hiz;  // map_min_boundary_ + 1e-4, map_max_boundary_ - 1e-4
   double inv_res;
@@ -47,7 +51,7 @@ struct MapDev {
 struct __align__(8) KinoNode {
   double px, py, pz, vx, vy, vz, g;
   uint32_t parent;    // node id or UAVMP_NONE
-  uint32_t heap_pos;  // 0-based slot in the open-list array
+  uint32_t hslot;     // this node's slot in the arena's hash table
   uint16_t input;     // lattice id of the primitive that produced this state
   uint8_t closed;
   uint8_t pad0;
@@ -56,15 +60,20 @@ struct __align__(8) KinoNode {
 static_assert(sizeof(KinoNode) == 72, "node record is 72 B");
 
 struct __align__(16) HeapSlot {
-  double f;      // cached key; kept equal to the live f_cost (mutations write through heap_pos)
+  double f;      // cached key; kept equal to the live f_cost (in-place mutations write through the slot's heap_pos)
   uint32_t id;
-  uint32_t dirty;
+  uint32_t hs;   // hash slot of node `id` (bit 31: dirty marker while staged in shared memory)
 };
-struct __align__(16) HashSlot {
+// One 32 B sector answers everything the successor classification needs: exists? closed? g? where in the open list?
+struct __align__(32) HashSlot {
   unsigned long long key;  // (packed voxel index << 10) | epoch
   uint32_t id;
+  uint32_t heap_pos;       // 0-based slot in the open-list array (valid while the node is open)
+  double g;
+  uint32_t closed;
   uint32_t pad;
 };
+static_assert(sizeof(HashSlot) == 32, "hash slot is one sector");
 
 struct KinoArena {           // one per resident CTA, reused across queries
   KinoNode* nodes;           // allocated
@@ -118,6 +127,9 @@ struct uavmp_ctx {
   float4* d_pts = nullptr;
   MapDev map_host;
   MapDev* d_map = nullptr;
+  uint8_t* d_flags_pad = nullptr;   // [nx][ny][nzp]
+  unsigned char tmap_bytes[128] __attribute__((aligned(64)));  // CUtensorMap over d_flags_pad, box 32^3
+  bool have_tmap = false;
   bool flags_dirty = true;
 
   // search arenas

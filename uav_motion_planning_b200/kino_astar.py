@@ -102,5 +102,5 @@ class KinoAstar:
         qc = np.zeros(B, np.int64)
         grid = C.c_int()
         self.ctx.check(self.lib.uavmp_kino_get_profile(self.ctx.h, _lib.ptr(ph), _lib.ptr(qc), B, C.byref(grid)))
-        names = ["pop", "shot_path", "primitives", "dedup_probe", "heuristic_scan", "node_write", "heap_commit", "setup"]
+        names = ["pop", "shot_path", "tables_tile_grid", "cloud_ellipsoid", "dedup_probe_heuristic", "node_write", "heap_commit", "setup"]
         return dict(phase_cycles=dict(zip(names, ph.tolist())), query_cycles=qc, grid=grid.value)
