@@ -156,9 +156,10 @@ int uavmp_plan_batch_dev(uavmp_ctx* ctx, int B, const double* d_start_pt, const 
 int uavmp_get_timings(uavmp_ctx* ctx, uavmp_timings* out);
 /* optional in-kernel profile of the search: SM cycles per phase (0 pop, 1 shot/path, 2 primitive evaluation, 3 dedup +
  * table probe, 4 heuristic + id scan, 5 node/hash writes, 6 ordered heap commit, 7 query setup/epilogue) summed over the
- * CTAs, the cycles every query kept its CTA busy, and the grid size of the last launch */
+ * CTAs (entries 8..15: diagnostics: cloud staging cycles, staged / unstaged expansions, staged points, flagged primitives),
+ * the cycles every query kept its CTA busy, and the grid size of the last launch */
 int uavmp_kino_set_profile(uavmp_ctx* ctx, int on);
-int uavmp_kino_get_profile(uavmp_ctx* ctx, unsigned long long phase_cycles[8], long long* query_cycles, int cap, int* grid);
+int uavmp_kino_get_profile(uavmp_ctx* ctx, unsigned long long phase_cycles[16], long long* query_cycles, int cap, int* grid);
 
 /* ---- host utilities (not on the hot path) ----------------------------------------------------------- */
 void uavmp_mapgen_params_default(uavmp_mapgen_params* p, double x_size, double y_size, uint32_t seed);

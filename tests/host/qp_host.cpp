@@ -23,7 +23,7 @@ extern "C" int host_qp_solve(int order, int S, int B, const double* pos, const d
   QpIo io;
   io.pos = pos; io.bv = bv; io.ba = ba; io.bj = bj ? bj : ba; io.T = T;
   io.coef = coef; io.solved = solved; io.status = status; io.iters = iters; io.B = B; io.stride = stride;
-  for (int b = 0; b < B; b++) qp_solve_one(D, io, *st, ws.data(), b);
+  for (int b = 0; b < B; b++) qp_solve_one(D, io, *st, ws.data(), b, nullptr);
   delete H;
   return 0;
 }

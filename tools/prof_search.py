@@ -25,9 +25,10 @@ pr = ka.profile(B)
 c = ka.counters()
 qc = pr["query_cycles"].astype(np.float64)
 pops = r["n_pop"].astype(np.float64)
+diag = {k: pr["phase_cycles"].pop(k) for k in ("n_staged", "n_unstaged", "sum_npts", "sum_flagged_prims", "commit_closure_io", "commit_slow_updates", "commit_deferred_writes")}
 tot = sum(pr["phase_cycles"].values())
 clk_ghz = qc.max() / (t["search_ms"] * 1e6)  # lower bound on the SM clock: the longest query cannot outlast the kernel
-out = dict(B=B, search_ms=t["search_ms"], grid=pr["grid"], counters=c,
+out = dict(B=B, diag=diag, search_ms=t["search_ms"], grid=pr["grid"], counters=c,
            phase_share={k: v / tot for k, v in pr["phase_cycles"].items()},
            phase_cycles_per_pop={k: v / c["n_pop"] for k, v in pr["phase_cycles"].items()},
            cycles_per_pop_mean=qc.sum() / pops.sum(), longest_query_cycles=qc.max(), longest_query_pops=float(pops[qc.argmax()]),
@@ -35,6 +36,10 @@ out = dict(B=B, search_ms=t["search_ms"], grid=pr["grid"], counters=c,
            implied_clock_ghz_lower_bound=clk_ghz,
            pops_percentiles={str(p): float(np.percentile(pops, p)) for p in (50, 90, 99, 99.9, 100)},
            status_hist=np.bincount(r["status"], minlength=3).tolist())
+top = np.argsort(-qc)[:3]
+out["longest_queries"] = [dict(q=int(q), pops=int(pops[q]), cycles=float(qc[q]), status=int(r["status"][q]),
+                              per_pop={n: float(pr["query_phase"][q][k]) / max(pops[q], 1) for k, n in enumerate(pr["names"])})
+                         for q in top]
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"prof_search_B{B}.json"), "w"), indent=1)
 print(json.dumps(out, indent=1))

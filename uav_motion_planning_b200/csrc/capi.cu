@@ -82,7 +82,7 @@ void uavmp_ctx_destroy(uavmp_ctx* ctx) {
                   ctx->d_pts, ctx->d_map, ctx->d_arena_mem, ctx->d_arenas, ctx->d_q, ctx->d_order, ctx->d_status,
                   ctx->d_use, ctx->d_npop, ctx->d_hash, ctx->d_npath, ctx->d_path_stage, ctx->d_trace, ctx->d_offsets,
                   ctx->d_path_packed, ctx->d_misc, ctx->d_counters, ctx->d_cub_tmp, ctx->d_qp_ws, ctx->d_qp_in,
-                  ctx->d_qp_out, ctx->d_qp_int, ctx->d_plan_out, ctx->d_plan_io, ctx->d_wp, ctx->d_phase, ctx->d_query_cycles, ctx->d_flags_pad};
+                  ctx->d_qp_out, ctx->d_qp_int, ctx->d_plan_out, ctx->d_plan_io, ctx->d_wp, ctx->d_phase, ctx->d_query_cycles, ctx->d_flags_pad, ctx->d_b3f};
   for (void* p : ptrs) if (p) cudaFree(p);
   qp_free_plans(ctx);
   for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->ev[i]);
@@ -237,13 +237,16 @@ int uavmp_kino_set_profile(uavmp_ctx* ctx, int on) {
   return UAVMP_OK;
 }
 
-int uavmp_kino_get_profile(uavmp_ctx* ctx, unsigned long long phase_cycles[8], long long* query_cycles, int cap, int* grid) {
+int uavmp_kino_get_profile(uavmp_ctx* ctx, unsigned long long phase_cycles[16], long long* query_cycles, int cap, int* grid) {
   if (!ctx || !phase_cycles) return UAVMP_EINVAL;
   if (!ctx->d_phase) return uavmp_fail(ctx, UAVMP_ESTATE, "profiling was off for the last search");
   cudaSetDevice(ctx->device);
-  UAVMP_CUDA(ctx, cudaMemcpyAsync(phase_cycles, ctx->d_phase, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-  if (query_cycles && cap > 0)
-    UAVMP_CUDA(ctx, cudaMemcpyAsync(query_cycles, ctx->d_query_cycles, (size_t)std::min(cap, ctx->last_B) * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  UAVMP_CUDA(ctx, cudaMemcpyAsync(phase_cycles, ctx->d_phase, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  // cap >= 17 * B: the B per-query totals followed by the B x 16 per-query phase cycles; else only the totals
+  if (query_cycles && cap > 0) {
+    const size_t nq = (cap >= 17 * ctx->last_B) ? (size_t)17 * ctx->last_B : (size_t)std::min(cap, ctx->last_B);
+    UAVMP_CUDA(ctx, cudaMemcpyAsync(query_cycles, ctx->d_query_cycles, nq * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  }
   UAVMP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (grid) *grid = ctx->last_grid;
   return UAVMP_OK;

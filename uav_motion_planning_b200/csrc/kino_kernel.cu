@@ -63,6 +63,7 @@ struct PhaseA {  // staging buffers of the primitive evaluation
   float4 pts[PTS_CAP];          // cloud points of the cells the expansion can touch, column after column
   int cstart[CS_CAP];           // their cell_start entries, [column][z]
   int col_delta[COL_CAP];       // shared-memory index = global point index + col_delta[column]
+  uint16_t need[UAVMP_MAXPRIM]; // per primitive: checkpoints whose voxel has the "cloud nearby" bit
 };
 struct PhaseB {  // successor classification / commit
   double f[UAVMP_MAXPRIM];
@@ -72,18 +73,20 @@ struct PhaseB {  // successor classification / commit
   uint32_t hpos[UAVMP_MAXPRIM];  // its open-list position at probe time
   uint32_t tab[TAB_SIZE];
   HeapSlot hc[HC_CAP];
+  uint32_t hidx[HC_CAP];         // 1-based heap index of every staged ancestor slot
   uint16_t win[UAVMP_MAXPRIM];   // last improving primitive of an existing node's group
   uint8_t inun[UAVMP_MAXPRIM];   // that node is an ancestor of a new leaf: its key was already written in order
+  double gpc[UAVMP_MAXPRIM];     // g of every commit candidate
 };
 
 struct SearchSmem {
   union __align__(128) { PhaseA a; PhaseB b; };
-  unsigned long long key[UAVMP_MAXPRIM];
-  uint32_t id[UAVMP_MAXPRIM];
+  union {
+    struct { unsigned long long key[UAVMP_MAXPRIM]; uint32_t id[UAVMP_MAXPRIM]; };
+    uint32_t units[UAVMP_MAXK * UAVMP_MAXNA * UAVMP_MAXNA];  // cloud-test work units; dead before the keys are written
+  };
   uint16_t list1[UAVMP_MAXPRIM];
   uint16_t list2[UAVMP_MAXPRIM];
-  uint16_t listT[UAVMP_MAXPRIM];
-  uint16_t need[UAVMP_MAXPRIM];
   uint8_t state[UAVMP_MAXPRIM];
   // separable tables of one expansion
   double X[UAVMP_MAXK][3][UAVMP_MAXNA];
@@ -96,9 +99,11 @@ struct SearchSmem {
   double axmin[3][UAVMP_MAXNA], axmax[3][UAVMP_MAXNA];
   double xlo[3], xhi[3];
   int to[3], rc0[3], rc1[3];
-  int any_ok, tile_ok, nT, tnext, npts;
+  int any_ok, tile_ok, nT, npts;
+  unsigned dmax, dsum, dhit;
   unsigned long long mbar;
-  int lv_lo[32], lv_off[32], lv_hi[32];
+  KinoParamsDev P;
+  MapDev M;
   double cp[3], cv[3], cg;
   double gp[3], gv[3];
   double sp[3], sv[3];
@@ -106,10 +111,11 @@ struct SearchSmem {
   double shot[12];
   unsigned long long pop_hash;
   unsigned long long cnt[8];
-  unsigned long long ph[8];   // per-phase SM cycles of this CTA (thread 0's clock), only when bt.phase_cycles != nullptr
+  unsigned long long ph[16];  // per-phase SM cycles [0..7] + diagnostics [8..15] of this CTA (thread 0's clock), only when bt.phase_cycles != nullptr
   long long ph_t;
+  unsigned long long phq[16];
   uint32_t cur_id, cur_parent, epoch;
-  int heap_len, use_num, n_pop, n1, n2, n_new, status, flag, q, hc_active, hc_total;
+  int heap_len, use_num, n_pop, n1, n2, n_new, status, flag, q;
   int wsum[KT / 32];
 };
 
@@ -117,6 +123,12 @@ __device__ __forceinline__ double dot3(double ax, double ay, double az, double b
   return (ax * bx + ay * by) + az * bz;  // Eigen fixed-size-3 reduction order
 }
 
+// (ut.dot(ut) + rou) * sample_tau (:231) of lattice point p, same association as the host table lat.ginc
+__device__ __forceinline__ double ginc_of(const KinoParamsDev& P, int p) {
+  const int na = P.na;
+  const double ux = P.ua[p / (na * na)], uy = P.ua[(p / na) % na], uz = P.ua[p % na];
+  return ((ux * ux + uy * uy) + uz * uz + P.rou) * P.tau;
+}
 __device__ __forceinline__ unsigned long long mix64(unsigned long long h, unsigned long long v) {
   h ^= v;
   h *= 0x100000001b3ull;
@@ -233,6 +245,8 @@ __device__ __forceinline__ uint32_t hash_key(unsigned long long k, int bits) {
   return (uint32_t)((k * 0x9E3779B97F4A7C15ull) >> (64 - bits));
 }
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 // ---- open list: libstdc++ heap semantics on cached keys -----------------------------------------------
 // slot i (0-based) is stored at heap[i + 1]; every move also records the new position in the node's hash slot
 #define HS_DIRTY 0x80000000u
@@ -279,49 +293,52 @@ __device__ void heap_pop_serial(HeapSlot* H, HashSlot* table, int& len, HeapSlot
 // closure = the ancestors of leaves len0+1 .. len0+m (1-based heap indices), staged in shared memory by warp 0.
 // The caller keeps every batch inside ONE level of the tree (all new leaves at the same depth), so the ancestors
 // `d` levels up form the contiguous range [(len0+1) >> d, (len0+m) >> d] and ranges of different d never share a node.
-__device__ void closure_load(SearchSmem& s, const HeapSlot* H, int len0, int m, int lane) {
-  int total = 0;
-  for (int d = 0; d < 32; d++) {
-    const int lo = (len0 + 1) >> d, hi = (len0 + m) >> d;
-    const int cnt = (lo >= 1) ? hi - lo + 1 : 0;
-    if (lane == 0) { s.lv_lo[d] = lo; s.lv_hi[d] = (lo >= 1) ? hi : -1; s.lv_off[d] = total; }
-    if (d >= 1) {
-      for (int j = lane; j < cnt; j += 32) {
-        HeapSlot e;
-        const double2 raw = __ldcg(reinterpret_cast<const double2*>(H + lo + j));
-        e.f = raw.x;
-        const unsigned long long w = (unsigned long long)__double_as_longlong(raw.y);
-        e.id = (uint32_t)w; e.hs = (uint32_t)(w >> 32) & HS_MASK;
-        s.b.hc[total + j] = e;
-      }
-    } else {
-      for (int j = lane; j < cnt; j += 32) { HeapSlot e; e.f = 0; e.id = UAVMP_NONE; e.hs = 0; s.b.hc[total + j] = e; }
-    }
-    total += cnt;
+// Lane d owns level d: its range start `lo` and its offset `off` in the staging array stay in registers.
+struct Closure {
+  int lo, off, lo_m1, off_m1, total;
+  bool active;
+};
+
+__device__ __forceinline__ void closure_load(SearchSmem& s, const HeapSlot* H, int len0, int m, int lane, Closure& c) {
+  const int lo = (len0 + 1) >> lane, hi = (len0 + m) >> lane;
+  const int cnt = (lo >= 1) ? hi - lo + 1 : 0;
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+  c.lo = lo; c.off = incl - cnt;
+  c.total = __shfl_sync(FULL, incl, 31);
+  c.lo_m1 = __shfl_up_sync(FULL, c.lo, 1);
+  c.off_m1 = __shfl_up_sync(FULL, c.off, 1);
+  c.active = true;
+  {  // level 0 = the new leaves themselves (offset 0, m entries): initialised by the whole warp
+    for (int j = lane; j < m; j += 32) { HeapSlot e; e.f = 0; e.id = UAVMP_NONE; e.hs = 0; s.b.hc[j] = e; s.b.hidx[j] = (uint32_t)(len0 + 1 + j); }
   }
-  if (lane == 0) { s.hc_total = total; s.hc_active = 1; }
+  if (lane != 0) {
+    for (int j = 0; j < cnt; j++) {
+      // asynchronous 16 B global -> shared copies (L2 only): all of a level's loads are in flight at once
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&s.b.hc[c.off + j])), "l"(H + lo + j) : "memory");
+      s.b.hidx[c.off + j] = (uint32_t)(lo + j);
+    }
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncwarp();
 }
 
-__device__ void closure_flush(SearchSmem& s, HeapSlot* H, HashSlot* table, int lane) {
-  if (!s.hc_active) return;
+__device__ __forceinline__ void closure_flush(SearchSmem& s, HeapSlot* H, HashSlot* table, int lane, Closure& c) {
+  if (!c.active) return;
   __syncwarp();
-  for (int d = 0; d < 32; d++) {
-    const int lo = s.lv_lo[d], hi = s.lv_hi[d], off = s.lv_off[d];
-    const int cnt = hi >= lo ? hi - lo + 1 : 0;
-    for (int j = lane; j < cnt; j += 32) {
-      HeapSlot e = s.b.hc[off + j];
-      if (e.hs & HS_DIRTY) {
-        e.hs &= HS_MASK;
-        H[lo + j] = e;
-        table[e.hs].heap_pos = (uint32_t)(lo + j - 1);
-      }
+  for (int e = lane; e < c.total; e += 32) {
+    HeapSlot ent = s.b.hc[e];
+    if (ent.hs & HS_DIRTY) {
+      const uint32_t idx = s.b.hidx[e];
+      ent.hs &= HS_MASK;
+      H[idx] = ent;
+      table[ent.hs].heap_pos = idx - 1;
     }
   }
   __threadfence_block();
   __syncwarp();
-  if (lane == 0) s.hc_active = 0;
-  __syncwarp();
+  c.active = false;
 }
 
 // number of leaves that can be pushed from length `len` without leaving the current tree level
@@ -332,25 +349,27 @@ __device__ __forceinline__ int level_room(int len) {
 }
 
 // std::push_heap of (f, id) as 1-based leaf n1, ancestors read from the closure
-__device__ void closure_push(SearchSmem& s, int n1, double f, uint32_t id, uint32_t hs, int lane) {
-  int a = n1 >> lane;
-  bool valid = (lane >= 1) && (a >= 1);
+__device__ __forceinline__ void closure_push(SearchSmem& s, int n1, double f, uint32_t id, uint32_t hs, int lane,
+                                             const Closure& c) {
+  const int a = n1 >> lane;
+  const bool valid = (lane >= 1) && (a >= 1);
   HeapSlot e;
   e.f = 0; e.id = 0; e.hs = 0;
-  if (valid) e = s.b.hc[s.lv_off[lane] + (a - s.lv_lo[lane])];
-  bool gt = valid && (e.f > f);
-  unsigned m = __ballot_sync(FULL, gt);
-  unsigned cont = m >> 1;            // bit j: level j+1 moves down
-  int L = __ffs(~cont) - 1;          // number of consecutive moves
+  if (valid) e = s.b.hc[c.off + (a - c.lo)];
+  const bool gt = valid && (e.f > f);
+  const unsigned m = __ballot_sync(FULL, gt);
+  const unsigned cont = m >> 1;            // bit j: level j+1 moves down
+  const int L = __ffs(~cont) - 1;          // number of consecutive moves
   if (lane >= 1 && lane <= L) {
-    int tgt = n1 >> (lane - 1);
+    const int tgt = n1 >> (lane - 1);
     e.hs |= HS_DIRTY;
-    s.b.hc[s.lv_off[lane - 1] + (tgt - s.lv_lo[lane - 1])] = e;
+    s.b.hc[c.off_m1 + (tgt - c.lo_m1)] = e;
   }
+  const int lo_L = __shfl_sync(FULL, c.lo, L), off_L = __shfl_sync(FULL, c.off, L);
   if (lane == 0) {
-    int tgt = n1 >> L;
+    const int tgt = n1 >> L;
     HeapSlot ne; ne.f = f; ne.id = id; ne.hs = hs | HS_DIRTY;
-    s.b.hc[s.lv_off[L] + (tgt - s.lv_lo[L])] = ne;
+    s.b.hc[off_L + (tgt - lo_L)] = ne;
   }
   __syncwarp();
 }
@@ -358,14 +377,13 @@ __device__ void closure_push(SearchSmem& s, int n1, double f, uint32_t id, uint3
 // in-place key mutation (kino_astar.cpp:251-265) of a node that may sit among the staged ancestors: look for it in the
 // closure; if it is not there, write through its live heap position
 __device__ void heap_set_key_slow(SearchSmem& s, HeapSlot* H, const HashSlot* table, uint32_t id, uint32_t hs, double f,
-                                  int lane) {
+                                  int lane, const Closure& c) {
   __syncwarp();
   int found = -1;
-  if (s.hc_active) {
-    const int total = s.hc_total;
-    for (int base = 0; base < total; base += 32) {
+  if (c.active) {
+    for (int base = 0; base < c.total; base += 32) {
       const int j = base + lane;
-      const bool hit = (j < total) && (s.b.hc[j].id == id);
+      const bool hit = (j < c.total) && (s.b.hc[j].id == id);
       const unsigned m = __ballot_sync(FULL, hit);
       if (m) { found = base + __ffs(m) - 1; break; }
     }
@@ -392,7 +410,6 @@ __device__ void shot_pos(const double* c, double t, double& x, double& y, double
 }
 
 // ---- TMA / mbarrier primitives (sm_90+ PTX) -------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(void* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -419,58 +436,45 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, int c0,
 // ---- ellipsoid test of one (primitive, checkpoint) against the cloud points staged in shared memory ---------
 // warp-cooperative: lanes take the points of one cell column at a time; kino_astar.cpp:721-758 semantics
 // ("any cloud point p with || E^-1 (p - pt) || <= 1"; the KD-tree radius r + 0.1 is a pure superset filter, §9.1 Q12)
-__device__ __forceinline__ bool point_in_ellipsoid(const double* e, double px, double py, double pz, float4 q,
-                                                   double cull2) {
-  const double ddx = (double)q.x - px, ddy = (double)q.y - py, ddz = (double)q.z - pz;
-  if ((ddx * ddx + ddy * ddy) + ddz * ddz > cull2) return false;  // farther than the longest semi-axis (+ margin)
-  const double tx = (e[0] * ddx + e[1] * ddy) + e[2] * ddz;
-  const double ty = (e[3] * ddx + e[4] * ddy) + e[5] * ddz;
-  const double tz = (e[6] * ddx + e[7] * ddy) + e[8] * ddz;
+// Exact decision of kino_astar.cpp:749-753 for one cloud point, reached through two conservative filters:
+//   1. float distance cull: a point farther than the longest semi-axis (+2 mm) cannot be inside;
+//   2. because the ellipsoid is diag(r, r, h) in the body frame, || E^-1 d ||^2 == (|d|^2 - w^2)/r^2 + w^2/h^2 with
+//      w = d . b3 in exact arithmetic; its f64 evaluation decides every point that is not within 1e-9 of the surface;
+//   3. only those borderline points take the reference's own expression: sqrt(|E^-1 d|^2) <= 1 with Eigen's association.
+struct EllipsoidTest {
+  float fx, fy, fz, cullf;
+  double px, py, pz, b3x, b3y, b3z, inv_r2, inv_h2, cull2;
+  const double* e;  // E^-1, row-major, global
+};
+__device__ __forceinline__ bool point_hits(const EllipsoidTest& t, float4 q) {
+  const float dx = q.x - t.fx, dy = q.y - t.fy, dz = q.z - t.fz;
+  if (dx * dx + dy * dy + dz * dz > t.cullf) return false;
+  const double ddx = (double)q.x - t.px, ddy = (double)q.y - t.py, ddz = (double)q.z - t.pz;
+  const double dd = (ddx * ddx + ddy * ddy) + ddz * ddz;
+  if (dd > t.cull2) return false;
+  const double w = (ddx * t.b3x + ddy * t.b3y) + ddz * t.b3z;
+  const double w2 = w * w;
+  const double sv = (dd - w2) * t.inv_r2 + w2 * t.inv_h2;
+  if (sv < 1.0 - 1e-9) return true;
+  if (sv > 1.0 + 1e-9) return false;
+  const double* e = t.e;
+  const double tx = (__ldg(e + 0) * ddx + __ldg(e + 1) * ddy) + __ldg(e + 2) * ddz;
+  const double ty = (__ldg(e + 3) * ddx + __ldg(e + 4) * ddy) + __ldg(e + 5) * ddz;
+  const double tz = (__ldg(e + 6) * ddx + __ldg(e + 7) * ddy) + __ldg(e + 8) * ddz;
   return sqrt(dot3(tx, ty, tz, tx, ty, tz)) <= 1.0;
 }
-
-__device__ bool warp_ellipsoid_hit(const SearchSmem& s, const MapDev& M, const KinoParamsDev& P, const double* e,
-                                   double px, double py, double pz, int lane, unsigned& n_tested) {
-  // cell range of the bounding cube, relative to the staged region
-  const int x0 = max((int)floor((px - P.box_r - M.cox) * M.inv_cell), s.rc0[0]) - s.rc0[0];
-  const int x1 = min((int)floor((px + P.box_r - M.cox) * M.inv_cell), s.rc1[0]) - s.rc0[0];
-  const int y0 = max((int)floor((py - P.box_r - M.coy) * M.inv_cell), s.rc0[1]) - s.rc0[1];
-  const int y1 = min((int)floor((py + P.box_r - M.coy) * M.inv_cell), s.rc1[1]) - s.rc0[1];
-  const int z0 = max((int)floor((pz - P.box_r - M.coz) * M.inv_cell), s.rc0[2]) - s.rc0[2];
-  const int z1 = min((int)floor((pz + P.box_r - M.coz) * M.inv_cell), s.rc1[2]) - s.rc0[2];
-  if (x1 < x0 || y1 < y0 || z1 < z0) return false;
-  const int ncy = s.rc1[1] - s.rc0[1] + 1, ncz1 = s.rc1[2] - s.rc0[2] + 2;
-  const int wy = y1 - y0 + 1, ncol = (x1 - x0 + 1) * wy;
-  bool hit = false;
-  for (int cb = 0; cb < ncol; cb += 32) {
-    int beg = 0, cnt = 0;
-    if (cb + lane < ncol) {
-      const int lx = x0 + (cb + lane) / wy, ly = y0 + (cb + lane) % wy;
-      const int col = lx * ncy + ly;
-      const int g0 = s.a.cstart[col * ncz1 + z0], g1 = s.a.cstart[col * ncz1 + z1 + 1];
-      beg = g0 + s.a.col_delta[col];
-      cnt = g1 - g0;
-    }
-    unsigned nonempty = __ballot_sync(FULL, cnt > 0);
-    while (nonempty) {
-      const int l = __ffs(nonempty) - 1;
-      nonempty &= nonempty - 1;
-      const int b = __shfl_sync(FULL, beg, l), c = __shfl_sync(FULL, cnt, l);
-      for (int j = lane; j < c + ((32 - (c & 31)) & 31); j += 32) {  // uniform trip count for the ballot
-        bool h = false;
-        if (j < c) { h = point_in_ellipsoid(e, px, py, pz, s.a.pts[b + j], P.cull2); n_tested++; }
-        if (__any_sync(FULL, h)) { hit = true; break; }
-      }
-      if (hit) break;
-    }
-    if (hit) break;
-  }
-  return hit;
+__device__ __forceinline__ void make_test(EllipsoidTest& t, const KinoParamsDev& P, const LatticeDev& lat, int p, double px,
+                                          double py, double pz) {
+  t.px = px; t.py = py; t.pz = pz;
+  t.fx = (float)px; t.fy = (float)py; t.fz = (float)pz;
+  t.cullf = P.cullf; t.cull2 = P.cull2; t.inv_r2 = P.inv_r2; t.inv_h2 = P.inv_h2;
+  t.b3x = __ldg(lat.b3 + 3 * p); t.b3y = __ldg(lat.b3 + 3 * p + 1); t.b3z = __ldg(lat.b3 + 3 * p + 2);
+  t.e = lat.Einv + 9 * p;
 }
 
 // fallback when the region's points do not fit in shared memory: the lane-serial cell-list walk over global memory
-__device__ bool ellipsoid_hit_global(const MapDev& M, const KinoParamsDev& P, const double* e, double px, double py,
-                                     double pz, unsigned& n_tested) {
+__device__ bool ellipsoid_hit_global(const MapDev& M, const KinoParamsDev& P, const EllipsoidTest& t, unsigned& n_tested) {
+  const double px = t.px, py = t.py, pz = t.pz;
   int x0 = max((int)floor((px - P.box_r - M.cox) * M.inv_cell), 0);
   int x1 = min((int)floor((px + P.box_r - M.cox) * M.inv_cell), M.cnx - 1);
   int y0 = max((int)floor((py - P.box_r - M.coy) * M.inv_cell), 0);
@@ -483,7 +487,7 @@ __device__ bool ellipsoid_hit_global(const MapDev& M, const KinoParamsDev& P, co
       int k0 = __ldg(M.cell_start + cbase + z0), k1 = __ldg(M.cell_start + cbase + z1 + 1);
       for (int k = k0; k < k1; k++) {
         n_tested++;
-        if (point_in_ellipsoid(e, px, py, pz, __ldg(M.pts + k), P.cull2)) return true;
+        if (point_hits(t, __ldg(M.pts + k))) return true;
       }
     }
   return false;
@@ -496,9 +500,13 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
                                                             const __grid_constant__ CUtensorMap tmap, int use_tma) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SearchSmem& s = *reinterpret_cast<SearchSmem*>(smem_raw);
-  const KinoParamsDev& P = *Pp;
-  const MapDev& M = *Mp;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // parameter blocks live in shared memory: every hot loop reads them
+  for (int i = tid; i < (int)(sizeof(KinoParamsDev) / 4); i += KT) reinterpret_cast<uint32_t*>(&s.P)[i] = reinterpret_cast<const uint32_t*>(Pp)[i];
+  for (int i = tid; i < (int)(sizeof(MapDev) / 4); i += KT) reinterpret_cast<uint32_t*>(&s.M)[i] = reinterpret_cast<const uint32_t*>(Mp)[i];
+  __syncthreads();
+  const KinoParamsDev& P = s.P;
+  const MapDev& M = s.M;
   KinoArena ar = arenas[blockIdx.x];
   KinoNode* nodes = ar.nodes;
   HeapSlot* H = ar.heap;
@@ -506,9 +514,9 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
   const uint32_t tmask = (1u << table_bits) - 1u;
   const bool prof = bt.phase_cycles != nullptr;
   const int na = P.na, K = P.K, nprim = P.nprim;
-  if (tid < 8) s.ph[tid] = 0;
+  if (tid < 16) { s.ph[tid] = 0; s.phq[tid] = 0; }
   if (tid == 0) {
-    s.ph_t = clock64();
+    s.ph_t = clock64(); s.dmax = 0; s.dsum = 0; s.dhit = 0;
     mbar_init(&s.mbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -566,7 +574,7 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
       nodes[0] = nd;
       HeapSlot hs; hs.f = P.lambda * h; hs.id = 0; hs.hs = hh;
       H[1] = hs;
-      s.heap_len = 1; s.use_num = 1; s.n_pop = 0; s.status = 0; s.hc_active = 0;
+      s.heap_len = 1; s.use_num = 1; s.n_pop = 0; s.status = 0;
       s.pop_hash = 0xcbf29ce484222325ull;
       s.cnt[3] += 1; s.cnt[4] += 1; s.cnt[6] += 1;  // hash probe, insert, heuristic of the start node
     }
@@ -611,7 +619,7 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
           s.n_pop++;
           double dx = nd.px - s.gp[0], dy = nd.py - s.gp[1], dz = nd.pz - s.gp[2];
           s.flag = (sqrt(dot3(dx, dy, dz, dx, dy, dz)) < P.goal_tol) ? 1 : 0;
-          s.n1 = 0; s.n2 = 0; s.nT = 0; s.tnext = 0;
+          s.n1 = 0; s.n2 = 0; s.nT = 0;
         }
       }
       __syncthreads();
@@ -775,15 +783,44 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
             if (ok) st = ST_FEASIBLE;
           }
           s.state[p] = st;
-          if (st == ST_FEASIBLE && need) { s.need[p] = (uint16_t)need; s.listT[atomicAdd(&s.nT, 1)] = (uint16_t)p; }
+          s.a.need[p] = (st == ST_FEASIBLE) ? (uint16_t)need : (uint16_t)0;
         }
       } else {
         for (int p = tid; p < nprim; p += KT) s.state[p] = ST_REJECT;
       }
       __syncthreads();
+      // work units of the cloud test: (checkpoint i, lattice column a, b) with the set of c whose checkpoint is flagged.
+      // The nine centres of a unit share x and y, so one pass over the candidate points serves all of them.  Ordered
+      // compaction keeps neighbouring units on neighbouring lanes (similar candidate sets -> similar trip counts).
+      {
+        const int nU = s.any_ok ? K * na * na : 0;
+        const int per = (nU + KT - 1) / KT;
+        uint32_t mine[8];
+        int cnt = 0;
+        for (int j = 0; j < per && j < 8; j++) {
+          const int u = tid * per + j;
+          uint32_t m = 0;
+          if (u < nU) {
+            const int i = u / (na * na), ab = u % (na * na);
+            for (int c = 0; c < na; c++) m |= (uint32_t)((s.a.need[ab * na + c] >> i) & 1u) << c;
+          }
+          mine[j] = m ? ((uint32_t)u | (m << 11)) : 0u;
+          cnt += m ? 1 : 0;
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) s.wsum[warp] = incl;
+        __syncthreads();
+        int off = incl - cnt;
+        for (int w = 0; w < warp; w++) off += s.wsum[w];
+        for (int j = 0; j < per && j < 8; j++) if (mine[j]) s.units[off++] = mine[j];
+        if (tid == KT - 1) s.nT = off;
+      }
+      __syncthreads();
       PH_MARK(2);
 
-      // ---- A2. SE(3) ellipsoid vs cloud for the primitives that pass near obstacles (:721-758) ----------------------
+      // ---- A2. SE(3) ellipsoid vs cloud for the checkpoints that pass near obstacles (:721-758) ----------------------
       const int nT = s.nT;
       if (nT > 0) {
         // stage the cell list of the region the feasible checkpoints can touch: cell_start entries, then the points
@@ -827,43 +864,75 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
           }
           __syncthreads();
         }
+        PH_MARK(8);  // staging time
+        if (prof && tid == 0) { s.ph[staged ? 9 : 10] += 1; s.ph[11] += (unsigned long long)(staged ? s.npts : 0); s.ph[12] += (unsigned long long)nT; }
+        unsigned my_hits = 0;
+        (void)my_hits;
         if (staged) {
-          // warps pull primitives; each tests its flagged checkpoints in turn and stops at the first hit
-          for (;;) {
-            int e = 0;
-            if (lane == 0) e = atomicAdd(&s.tnext, 1);
-            e = __shfl_sync(FULL, e, 0);
-            if (e >= nT) break;
-            const int p = s.listT[e];
-            const int a = p / (na * na), b = (p / na) % na, c = p % na;
-            unsigned need = s.need[p];
-            const double* ei = lat.Einv + 9 * p;
-            double em[9];
+          // Point-major sweep.  Every unit looks at (almost) the same few hundred staged points, so each thread keeps ONE
+          // unit's nine centres in registers and all threads stream through the staged points in the same order: the
+          // loads are shared-memory broadcasts and the instruction stream is uniform.  With few units, G lanes share a
+          // unit and split the points between them.
+          int G = 1;
+          while (G < 8 && nT * (G * 2) <= KT) G *= 2;
+          const int slots = KT / G, npts = s.npts;
+          const float cullf = P.cullf;
+          for (int base = 0; base < nT; base += slots) {
+            const int e = base + tid / G, r = tid % G;
+            if (e >= nT) continue;
+            const uint32_t un = s.units[e];
+            const int u = (int)(un & 2047u);
+            const int i = u / (na * na), ab = u % (na * na), a = ab / na, b = ab % na;
+            uint32_t mask = 0;
+            for (int c = 0; c < na; c++)   // drop primitives another checkpoint has rejected meanwhile
+              if (((un >> (11 + c)) & 1u) && s.state[ab * na + c] == ST_FEASIBLE) mask |= 1u << c;
+            const double px = s.X[i][0][a], py = s.X[i][1][b];
+            const float fx = (float)px, fy = (float)py;
+            float fz[UAVMP_MAXNA];
 #pragma unroll
-            for (int j = 0; j < 9; j++) em[j] = __ldg(ei + j);
-            while (need) {
-              const int i = __ffs(need) - 1;
-              need &= need - 1;
-              if (warp_ellipsoid_hit(s, M, P, em, s.X[i][0][a], s.X[i][1][b], s.X[i][2][c], lane, my_cloud)) {
-                if (lane == 0) s.state[p] = ST_REJECT;
-                break;
+            for (int c = 0; c < UAVMP_MAXNA; c++) fz[c] = (c < na) ? (float)s.X[i][2][c] : 1e30f;
+            int trip = 0;
+            for (int g = r; g < npts && mask; g += G, trip++) {
+              if ((trip & 63) == 63) {  // somebody else may have rejected these primitives in the meantime
+                for (int c = 0; c < na; c++) if (s.state[ab * na + c] != ST_FEASIBLE) mask &= ~(1u << c);
+              }
+              const float4 q = s.a.pts[g];
+              my_cloud++;
+              const float dx = q.x - fx, dy = q.y - fy;
+              const float dxy2 = dx * dx + dy * dy;
+              if (dxy2 > cullf) continue;  // outside the cylinder every centre of the unit lives in
+              uint32_t cand = 0;
+#pragma unroll
+              for (int c = 0; c < UAVMP_MAXNA; c++) {
+                const float dz = q.z - fz[c];
+                if (dxy2 + dz * dz <= cullf) cand |= 1u << c;
+              }
+              cand &= mask;
+              while (cand) {
+                const int c = __ffs(cand) - 1;
+                cand &= cand - 1;
+                {  // float slab test: || E^-1 d ||^2 = (|d|^2 - w^2)/r^2 + w^2/h^2, w = d . b3; 1 % margin >> float error
+                  const float4 bf = __ldg(lat.b3f + (ab * na + c));
+                  const float dz = q.z - fz[c];
+                  const float w = (dx * bf.x + dy * bf.y) + dz * bf.z, w2 = w * w;
+                  if (((dxy2 + dz * dz) - w2) * P.inv_r2f + w2 * P.inv_h2f > 1.01f) continue;
+                }
+                EllipsoidTest t;
+                make_test(t, P, lat, ab * na + c, px, py, s.X[i][2][c]);
+                if (point_hits(t, q)) { s.state[ab * na + c] = ST_REJECT; mask &= ~(1u << c); my_hits++; }
               }
             }
           }
         } else {
           for (int e = tid; e < nT; e += KT) {
-            const int p = s.listT[e];
-            const int a = p / (na * na), b = (p / na) % na, c = p % na;
-            unsigned need = s.need[p];
-            double em[9];
-            for (int j = 0; j < 9; j++) em[j] = __ldg(lat.Einv + 9 * p + j);
-            while (need) {
-              const int i = __ffs(need) - 1;
-              need &= need - 1;
-              if (ellipsoid_hit_global(M, P, em, s.X[i][0][a], s.X[i][1][b], s.X[i][2][c], my_cloud)) {
-                s.state[p] = ST_REJECT;
-                break;
-              }
+            const uint32_t un = s.units[e];
+            const int u = (int)(un & 2047u);
+            const int i = u / (na * na), ab = u % (na * na), a = ab / na, b = ab % na;
+            for (int c = 0; c < na; c++) {
+              if (!((un >> (11 + c)) & 1u) || s.state[ab * na + c] != ST_FEASIBLE) continue;
+              EllipsoidTest t;
+              make_test(t, P, lat, ab * na + c, s.X[i][0][a], s.X[i][1][b], s.X[i][2][c]);
+              if (ellipsoid_hit_global(M, P, t, my_cloud)) { s.state[ab * na + c] = ST_REJECT; my_hits++; }
             }
           }
         }
@@ -906,7 +975,7 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
         const int leader = (int)s.b.tab[s.id[p]] - 1;
         if (leader != p) { s.id[p] = (uint32_t)leader; s.state[p] = ST_FOLLOW_NOCAND; continue; }
         const unsigned long long k = s.key[p];
-        const double gp = s.cg + lat.ginc[p];
+        const double gp = s.cg + ginc_of(P, p);
         uint32_t h = hash_key(k, table_bits);
         uint8_t st;
         s.b.win[p] = 0xffff;
@@ -943,34 +1012,27 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
           if (ls == ST_CLOSED) {
             st = ST_CLOSED;
           } else {
-            const double gp = s.cg + lat.ginc[p];
+            const double gp = s.cg + ginc_of(P, p);
             if (gp < s.b.gcur[leader]) st = ST_FOLLOW_CAND;
           }
           s.state[p] = st;
         }
-        if (st == ST_NEW || st == ST_OPEN_CAND || st == ST_FOLLOW_CAND) s.list2[atomicAdd(&s.n2, 1)] = (uint16_t)p;
+        if (st == ST_NEW || st == ST_OPEN_CAND || st == ST_FOLLOW_CAND) atomicAdd(&s.n2, 1);
       }
       __syncthreads();
       const int n2 = s.n2;
-      // ---- B3. heuristic for every candidate (:232,:259) ----------------------------------------------
-      for (int e = tid; e < n2; e += KT) {
-        const int p = s.list2[e];
-        const int a = p / (na * na), b = (p / na) % na, c = p % na;
-        double topt;
-        const double h = d_heuristic(P, s.EX[0][a], s.EX[1][b], s.EX[2][c], s.EV[0][a], s.EV[1][b], s.EV[2][c], s.gp[0],
-                                     s.gp[1], s.gp[2], s.gv[0], s.gv[1], s.gv[2], topt);
-        const double gp = s.cg + lat.ginc[p];
-        s.b.f[p] = gp + P.lambda * h;
-        s.b.topt[p] = topt;
-      }
       // ---- C. ordered id assignment for new nodes (== use_node_num_++ in lattice order) ----------------
       {
         const int p0 = tid * 3;
-        int c = 0;
+        int c = 0;  // low 16 bits: new nodes, high 16 bits: all commit candidates (new + improving), both in lattice order
 #pragma unroll
         for (int j = 0; j < 3; j++) {
           const int p = p0 + j;
-          if (p < nprim && s.state[p] == ST_NEW) c++;
+          if (p < nprim) {
+            const uint8_t st = s.state[p];
+            if (st == ST_NEW) c += 0x10001;
+            else if (st == ST_OPEN_CAND || st == ST_FOLLOW_CAND) c += 0x10000;
+          }
         }
         int incl = c;
 #pragma unroll
@@ -984,12 +1046,17 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
         for (int w = 0; w < warp; w++) woff += s.wsum[w];
         int excl = woff + incl - c;
         const int base = s.use_num;
+        int en = excl & 0xffff, ec = excl >> 16;
 #pragma unroll
         for (int j = 0; j < 3; j++) {
           const int p = p0 + j;
-          if (p < nprim && s.state[p] == ST_NEW) s.id[p] = (uint32_t)(base + excl++);
+          if (p < nprim) {
+            const uint8_t st = s.state[p];
+            if (st == ST_NEW) { s.id[p] = (uint32_t)(base + en++); s.list2[ec++] = (uint16_t)p; }
+            else if (st == ST_OPEN_CAND || st == ST_FOLLOW_CAND) s.list2[ec++] = (uint16_t)p;
+          }
         }
-        if (tid == KT - 1) s.n_new = woff + incl;
+        if (tid == KT - 1) s.n_new = (woff + incl) & 0xffff;
       }
       __syncthreads();
       PH_MARK(4);
@@ -1003,6 +1070,18 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
         }
         __syncthreads();
         break;
+      }
+      // ---- B3. heuristic for every candidate (:232,:259) ----------------------------------------------
+      for (int e = tid; e < n2; e += KT) {
+        const int p = s.list2[e];
+        const int a = p / (na * na), b = (p / na) % na, c = p % na;
+        double topt;
+        const double h = d_heuristic(P, s.EX[0][a], s.EX[1][b], s.EX[2][c], s.EV[0][a], s.EV[1][b], s.EV[2][c], s.gp[0],
+                                     s.gp[1], s.gp[2], s.gv[0], s.gv[1], s.gv[2], topt);
+        const double gp = s.cg + ginc_of(P, p);
+        s.b.f[p] = gp + P.lambda * h;
+        s.b.gpc[p] = gp;
+        s.b.topt[p] = topt;
       }
       // ---- C2. node records + hash slots of the new nodes, in parallel -----------------------------------
       for (int e = tid; e < n2; e += KT) {
@@ -1022,7 +1101,7 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
           }
           h = (h + 1) & tmask;
         }
-        const double g = s.cg + lat.ginc[p];
+        const double g = s.cg + ginc_of(P, p);
         table[h].id = nid; table[h].g = g; table[h].closed = 0;
         s.b.hs[p] = h;
         KinoNode nd;
@@ -1043,50 +1122,73 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
         const int len0 = len;
         double opt_time = s.opt_time;
         int n_upd = 0;
-        for (int pb = 0; pb < nprim; pb += 32) {
-          const int p = pb + lane;
-          const uint8_t st = (p < nprim) ? s.state[p] : ST_REJECT;
-          unsigned evm = __ballot_sync(FULL, st == ST_NEW || st == ST_OPEN_CAND || st == ST_FOLLOW_CAND);
+        Closure cl;
+        cl.lo = cl.off = cl.lo_m1 = cl.off_m1 = cl.total = 0; cl.active = false;
+        // does heap slot `pos1` (1-based) belong to the ancestors of this expansion's new leaves? (lane d tests level d)
+        const int un_lo = (len0 + 1) >> lane, un_hi = (len0 + n_new) >> lane;
+        for (int cb = 0; cb < n2; cb += 32) {
+          // list2 holds the candidates in lattice order (phase C); every lane fetches its own candidate once and the
+          // serial replay below only shuffles registers
+          const bool cand = cb + lane < n2;
+          const int p = cand ? (int)s.list2[cb + lane] : 0;
+          const int st = cand ? (int)s.state[p] : (int)ST_REJECT;
+          double c_f = 0.0, c_topt = -1.0, c_gp = 0.0;
+          uint32_t c_id = 0, c_hs = 0;
+          int c_leader = p;
+          if (cand) {
+            c_f = s.b.f[p]; c_topt = s.b.topt[p]; c_gp = s.b.gpc[p];
+            if (st == ST_NEW) { c_id = s.id[p]; c_hs = s.b.hs[p]; }
+            else if (st == ST_FOLLOW_CAND) c_leader = (int)s.id[p];
+          }
+          unsigned evm = __ballot_sync(FULL, cand);
           while (evm) {
             const int l = __ffs(evm) - 1;
             evm &= evm - 1;
-            const int pe = pb + l;
-            const uint8_t ste = s.state[pe];
+            const int ste = __shfl_sync(FULL, st, l);
+            const double f = __shfl_sync(FULL, c_f, l), topt = __shfl_sync(FULL, c_topt, l);
             if (ste == ST_NEW) {
               if (batch_left == 0) {
-                closure_flush(s, H, table, lane);
+                const long long t0 = prof ? clock64() : 0;
+                closure_flush(s, H, table, lane, cl);
                 batch_left = min(min(PUSH_BATCH, n_new - pushed), level_room(len));
-                closure_load(s, H, len, batch_left, lane);
+                closure_load(s, H, len, batch_left, lane, cl);
+                if (prof && lane == 0) s.ph[13] += (unsigned long long)(clock64() - t0);
               }
-              closure_push(s, len + 1, s.b.f[pe], s.id[pe], s.b.hs[pe], lane);
+              closure_push(s, len + 1, f, __shfl_sync(FULL, c_id, l), __shfl_sync(FULL, c_hs, l), lane, cl);
               len++;
               pushed++;
               batch_left--;
-              if (s.b.topt[pe] >= 0.0) opt_time = s.b.topt[pe];
+              if (topt >= 0.0) opt_time = topt;
             } else {
-              const int leader = (ste == ST_FOLLOW_CAND) ? (int)s.id[pe] : pe;
-              const double gp = s.cg + lat.ginc[pe];
+              const int leader = __shfl_sync(FULL, c_leader, l);
+              const double gp = __shfl_sync(FULL, c_gp, l);
               if (gp < s.b.gcur[leader]) {  // tmp_g_cost < old_node->g_cost (:254)
+                const int pe = __shfl_sync(FULL, p, l);
                 const bool lead_new = s.state[leader] == ST_NEW;
                 bool in_union = lead_new;
                 if (!lead_new) {
-                  // is the node an ancestor of one of this expansion's new leaves?
                   const int pos1 = (int)s.b.hpos[leader] + 1;
-                  const int d = lane;
-                  const int lo = (len0 + 1) >> d, hi = (len0 + n_new) >> d;
-                  in_union = __any_sync(FULL, n_new > 0 && lo >= 1 && pos1 >= lo && pos1 <= hi);
+                  in_union = __any_sync(FULL, n_new > 0 && un_lo >= 1 && pos1 >= un_lo && pos1 <= un_hi);
                 }
                 __syncwarp();
                 if (lane == 0) { s.b.gcur[leader] = gp; s.b.win[leader] = (uint16_t)pe; if (in_union) s.b.inun[leader] = 1; }
-                if (in_union) heap_set_key_slow(s, H, table, s.id[leader], s.b.hs[leader], s.b.f[pe], lane);
-                if (s.b.topt[pe] >= 0.0) opt_time = s.b.topt[pe];
+                if (in_union) {
+                  const long long t0 = prof ? clock64() : 0;
+                  heap_set_key_slow(s, H, table, s.id[leader], s.b.hs[leader], f, lane, cl);
+                  if (prof && lane == 0) s.ph[14] += (unsigned long long)(clock64() - t0);
+                }
+                if (topt >= 0.0) opt_time = topt;
                 n_upd++;
                 __syncwarp();
               }
             }
           }
         }
-        closure_flush(s, H, table, lane);
+        {
+          const long long t0 = prof ? clock64() : 0;
+          closure_flush(s, H, table, lane, cl);
+          if (prof && lane == 0) s.ph[13] += (unsigned long long)(clock64() - t0);
+        }
         if (lane == 0) {
           s.heap_len = len;
           s.use_num += n_new;
@@ -1095,6 +1197,7 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
         }
       }
       __syncthreads();
+      const long long t_d2 = (prof && tid == 0) ? clock64() : 0;
       // ---- D2. the recorded mutations, in parallel: node state, g in the hash slot, and the cached heap key ------
       for (int e = tid; e < n1; e += KT) {
         const int p = s.list1[e];
@@ -1106,12 +1209,13 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
         KinoNode* nd = nodes + s.id[p];
         nd->px = s.EX[0][a]; nd->py = s.EX[1][b]; nd->pz = s.EX[2][c];
         nd->vx = s.EV[0][a]; nd->vy = s.EV[1][b]; nd->vz = s.EV[2][c];
-        const double g = s.cg + lat.ginc[w];
+        const double g = s.cg + ginc_of(P, w);
         nd->g = g; nd->parent = s.cur_id; nd->input = (uint16_t)w;
         table[s.b.hs[p]].g = g;
         if (st != ST_NEW && !s.b.inun[p]) H[s.b.hpos[p] + 1].f = s.b.f[w];
       }
       __syncthreads();
+      if (prof && tid == 0) s.ph[15] += (unsigned long long)(clock64() - t_d2);
       PH_MARK(6);
     }  // main loop
 
@@ -1127,13 +1231,14 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
       if (s.status != UAVMP_REACH_END) bt.n_path[q] = 0;
       s.cnt[0] = (unsigned long long)s.n_pop;
       if (prof && bt.query_cycles) bt.query_cycles[q] = clock64() - q_t0;
+      if (prof && bt.query_phase) { for (int k = 0; k < 16; k++) { bt.query_phase[(size_t)q * 16 + k] = s.ph[k] - s.phq[k]; s.phq[k] = s.ph[k]; } }
     }
     __syncthreads();
     if (tid < 8) atomicAdd(&bt.counters[tid], s.cnt[tid]);
   }
   PH_MARK(7);
   __syncthreads();
-  if (prof && tid < 8) atomicAdd(&bt.phase_cycles[tid], s.ph[tid]);
+  if (prof && tid < 16) atomicAdd(&bt.phase_cycles[tid], s.ph[tid]);
 }
 
 // ---- map preprocessing -------------------------------------------------------------------------------
@@ -1298,6 +1403,10 @@ int kino_upload_params(uavmp_ctx* ctx) {
   float radius = (float)(kp.robot_r + 1e-1);
   P.kd_r2 = radius * radius;
   P.cull2 = P.box_r * P.box_r;
+  P.cullf = (float)((P.box_r + 2e-3) * (P.box_r + 2e-3));
+  P.inv_r2 = 1.0 / (kp.robot_r * kp.robot_r);
+  P.inv_h2 = 1.0 / (kp.robot_h * kp.robot_h);
+  P.inv_r2f = (float)P.inv_r2; P.inv_h2f = (float)P.inv_h2;
   if (std::max(kp.robot_r, kp.robot_h) >= kp.robot_r + 0.1)
     return uavmp_fail(ctx, UAVMP_EINVAL, "robot_h >= robot_r + 0.1: the KD-tree radius of kino_astar.cpp:744 would cut the ellipsoid");
 
@@ -1323,8 +1432,9 @@ int kino_upload_params(uavmp_ctx* ctx) {
       return uavmp_fail(ctx, UAVMP_EINVAL, "acceleration lattice is not a tensor grid");
   P.na = na;
   for (int a = 0; a < na; a++) P.ua[a] = uz[a];
-  std::vector<double> host((size_t)n * 13);
+  std::vector<double> host((size_t)n * 16);
   double* hux = host.data(); double* huy = hux + n; double* huz = huy + n; double* hg = huz + n; double* hE = hg + n;
+  double* hb3 = hE + (size_t)9 * n;
   for (int p = 0; p < n; p++) {
     hux[p] = ux[p]; huy[p] = uy[p]; huz[p] = uz[p];
     double usq = (ux[p] * ux[p] + uy[p] * uy[p]) + uz[p] * uz[p];
@@ -1355,10 +1465,18 @@ int kino_upload_params(uavmp_ctx* ctx) {
     double cc0 = cof(0, 0), cc1 = cof(1, 0), cc2 = cof(2, 0);
     double det = (cc0 * E[0][0] + cc1 * E[1][0]) + cc2 * E[2][0];
     double invdet = 1.0 / det;
+    hb3[3 * p] = b3[0]; hb3[3 * p + 1] = b3[1]; hb3[3 * p + 2] = b3[2];
     double* Ei = hE + 9 * p;
     Ei[0] = cc0 * invdet; Ei[1] = cc1 * invdet; Ei[2] = cc2 * invdet;
     Ei[3] = cof(0, 1) * invdet; Ei[4] = cof(1, 1) * invdet; Ei[5] = cof(2, 1) * invdet;
     Ei[6] = cof(0, 2) * invdet; Ei[7] = cof(1, 2) * invdet; Ei[8] = cof(2, 2) * invdet;
+  }
+  {
+    std::vector<float> hb3f((size_t)n * 4, 0.f);
+    for (int p = 0; p < n; p++) for (int j = 0; j < 3; j++) hb3f[4 * p + j] = (float)hb3[3 * p + j];
+    if (ctx->d_b3f) cudaFree(ctx->d_b3f);
+    UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_b3f, hb3f.size() * sizeof(float)));
+    UAVMP_CUDA(ctx, cudaMemcpy(ctx->d_b3f, hb3f.data(), hb3f.size() * sizeof(float), cudaMemcpyHostToDevice));
   }
   if (ctx->d_lattice) cudaFree(ctx->d_lattice);
   UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_lattice, host.size() * sizeof(double)));
@@ -1572,20 +1690,22 @@ int kino_launch_search(uavmp_ctx* ctx, int B, const double* d_sp, const double* 
   bt.n_path = ctx->d_npath; bt.path_stage = ctx->d_path_stage; bt.path_cap = ctx->path_cap;
   bt.pop_trace = ctx->d_trace; bt.pop_cap = ctx->pop_cap;
   bt.error_flag = ctx->d_misc; bt.next_query = ctx->d_misc + 1; bt.counters = ctx->d_counters;
-  bt.phase_cycles = nullptr; bt.query_cycles = nullptr;
+  bt.phase_cycles = nullptr; bt.query_cycles = nullptr; bt.query_phase = nullptr;
   if (ctx->profile_phases) {
-    if (!ctx->d_phase) UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_phase, 8 * sizeof(unsigned long long)));
+    if (!ctx->d_phase) UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_phase, 16 * sizeof(unsigned long long)));
     if (ctx->query_cycles_cap < B) {
       if (ctx->d_query_cycles) cudaFree(ctx->d_query_cycles);
-      UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_query_cycles, (size_t)B * sizeof(long long)));
+      UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_query_cycles, (size_t)B * 17 * sizeof(long long)));
       ctx->query_cycles_cap = B;
     }
-    UAVMP_CUDA(ctx, cudaMemsetAsync(ctx->d_phase, 0, 8 * sizeof(unsigned long long), st));
+    UAVMP_CUDA(ctx, cudaMemsetAsync(ctx->d_phase, 0, 16 * sizeof(unsigned long long), st));
     bt.phase_cycles = ctx->d_phase; bt.query_cycles = ctx->d_query_cycles;
+    bt.query_phase = (unsigned long long*)(ctx->d_query_cycles + B);
   }
   LatticeDev lat;
   const int n = ctx->nprim;
-  lat.ux = ctx->d_lattice; lat.uy = lat.ux + n; lat.uz = lat.uy + n; lat.ginc = lat.uz + n; lat.Einv = lat.ginc + n;
+  lat.ux = ctx->d_lattice; lat.uy = lat.ux + n; lat.uz = lat.uy + n; lat.ginc = lat.uz + n; lat.Einv = lat.ginc + n; lat.b3 = lat.Einv + (size_t)9 * n;
+  lat.b3f = ctx->d_b3f;
   int bits = 0;
   while ((1 << bits) < ctx->table_size) bits++;
   const int grid = std::min(ctx->n_arenas, B);

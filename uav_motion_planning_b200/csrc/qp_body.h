@@ -16,10 +16,20 @@
 #if defined(__CUDACC__)
 #define QP_HD __device__ __forceinline__
 #define QP_LDG(p) __ldg(p)
+#define QP_TID ((int)threadIdx.x)
 #else
 #define QP_HD static inline
 #define QP_LDG(p) (*(p))
+#define QP_TID 0
 #endif
+#define QP_TPB 32  // threads per CTA of the device instantiation (one problem per thread)
+
+// The two vectors every triangular solve hammers (the permuted right-hand side `bp` and the KKT vector `xz`; the
+// factorisation's scatter vector shares bp's storage) can live in shared memory, [element][thread] so that a warp's
+// accesses are conflict-free: sv != nullptr selects that placement, otherwise they stay in the global workspace.
+#define WBP(i) (*(sv ? &sv[(size_t)(i) * QP_TPB + QP_TID] : &W(pl.o_bp, i)))
+#define WXZ(i) (*(sv ? &sv[(size_t)(pl.N + (i)) * QP_TPB + QP_TID] : &W(pl.o_xz, i)))
+#define WYW(i) (*(sv ? &sv[(size_t)(i) * QP_TPB + QP_TID] : &W(pl.o_yw, i)))
 
 #define OSQP_INFTY_ 1e30
 #define OSQP_MIN_SCALING_ 1e-4
@@ -43,9 +53,12 @@ QP_HD double limit_scaling(double v) {
 #define W(off, i) ws[((size_t)((off) + (i))) * stride + b]
 
 // numeric LDL' of the permuted KKT matrix (up-looking, static reach lists) — QDLDL_factor's arithmetic
-QP_HD int qp_factor(const QpPlanDev& pl, double* ws, size_t stride, int b, double sigma) {
+QP_HD int qp_factor(const QpPlanDev& pl, double* ws, size_t stride, int b, double sigma, double* sv) {
   const int N = pl.N;
   int positive = 0;
+  // the scatter vector starts at zero (QDLDL_factor clears yVals the same way); it shares storage with bp when in
+  // shared memory, and the global workspace is reused across batches without being zeroed by the host
+  for (int i = 0; i < N; i++) WYW(i) = 0.0;
   for (int k = 0; k < N; k++) {
     double Dk = 0.0;
     for (int p = QP_LDG(pl.Kp + k); p < QP_LDG(pl.Kp + k + 1); p++) {
@@ -56,19 +69,19 @@ QP_HD int qp_factor(const QpPlanDev& pl, double* ws, size_t stride, int b, doubl
       else if (kind == 2) v = sigma;
       else if (kind == 3) v = W(pl.o_Ax, idx);
       else v = -W(pl.o_rhoinv, idx);
-      if (i == k) Dk = v; else W(pl.o_yw, i) = v;
+      if (i == k) Dk = v; else WYW(i) = v;
     }
     for (int e = QP_LDG(pl.Rp + k); e < QP_LDG(pl.Rp + k + 1); e++) {
       const int c = QP_LDG(pl.Rc + e), pos = QP_LDG(pl.Rpos + e);
-      const double yc = W(pl.o_yw, c);
+      const double yc = WYW(c);
       for (int j = QP_LDG(pl.Lp + c); j < pos; j++) {
         const int r = QP_LDG(pl.Li + j);
-        W(pl.o_yw, r) = W(pl.o_yw, r) - W(pl.o_Lx, j) * yc;
+        WYW(r) = WYW(r) - W(pl.o_Lx, j) * yc;
       }
       const double lv = yc * W(pl.o_Ddinv, c);
       W(pl.o_Lx, pos) = lv;
       Dk -= yc * lv;
-      W(pl.o_yw, c) = 0.0;
+      WYW(c) = 0.0;
     }
     if (Dk == 0.0) return -1;
     if (Dk > 0.0) positive++;
@@ -79,23 +92,23 @@ QP_HD int qp_factor(const QpPlanDev& pl, double* ws, size_t stride, int b, doubl
 }
 
 // xz <- K^-1 xz  (qdldl_interface.c:394-415: permute, L solve, D^-1, L' solve, permute back)
-QP_HD void qp_kkt_solve(const QpPlanDev& pl, double* ws, size_t stride, int b) {
+QP_HD void qp_kkt_solve(const QpPlanDev& pl, double* ws, size_t stride, int b, double* sv) {
   const int N = pl.N;
-  for (int j = 0; j < N; j++) W(pl.o_bp, j) = W(pl.o_xz, QP_LDG(pl.perm + j));
+  for (int j = 0; j < N; j++) WBP(j) = WXZ(QP_LDG(pl.perm + j));
   for (int i = 0; i < N; i++) {
-    const double val = W(pl.o_bp, i);
+    const double val = WBP(i);
     for (int j = QP_LDG(pl.Lp + i); j < QP_LDG(pl.Lp + i + 1); j++) {
       const int r = QP_LDG(pl.Li + j);
-      W(pl.o_bp, r) = W(pl.o_bp, r) - W(pl.o_Lx, j) * val;
+      WBP(r) = WBP(r) - W(pl.o_Lx, j) * val;
     }
   }
-  for (int i = 0; i < N; i++) W(pl.o_bp, i) = W(pl.o_bp, i) * W(pl.o_Ddinv, i);
+  for (int i = 0; i < N; i++) WBP(i) = WBP(i) * W(pl.o_Ddinv, i);
   for (int i = N - 1; i >= 0; i--) {
-    double val = W(pl.o_bp, i);
-    for (int j = QP_LDG(pl.Lp + i); j < QP_LDG(pl.Lp + i + 1); j++) val -= W(pl.o_Lx, j) * W(pl.o_bp, QP_LDG(pl.Li + j));
-    W(pl.o_bp, i) = val;
+    double val = WBP(i);
+    for (int j = QP_LDG(pl.Lp + i); j < QP_LDG(pl.Lp + i + 1); j++) val -= W(pl.o_Lx, j) * WBP(QP_LDG(pl.Li + j));
+    WBP(i) = val;
   }
-  for (int j = 0; j < N; j++) W(pl.o_xz, QP_LDG(pl.perm + j)) = W(pl.o_bp, j);
+  for (int j = 0; j < N; j++) WXZ(QP_LDG(pl.perm + j)) = WBP(j);
 }
 
 // out(m) = A * v(n)
@@ -245,7 +258,7 @@ QP_HD int qp_check_termination(const QpPlanDev& pl, double* ws, size_t stride, i
 
 
 // one problem: assembly -> osqp_setup -> osqp_solve -> store_solution
-QP_HD void qp_solve_one(const QpPlanDev& pl, const QpIo& io, const uavmp_osqp_settings& S, double* ws, int b) {
+QP_HD void qp_solve_one(const QpPlanDev& pl, const QpIo& io, const uavmp_osqp_settings& S, double* ws, int b, double* sv) {
   const size_t stride = (size_t)io.stride;
   const int n = pl.n, m = pl.m, Sg = pl.S, nc = pl.nc;
 
@@ -344,11 +357,8 @@ QP_HD void qp_solve_one(const QpPlanDev& pl, const QpIo& io, const uavmp_osqp_se
   set_rho(rho);
 
   int status = ST_UNSOLVED, iter_out = 0;
-  // the factorisation's scatter vector must start at zero (QDLDL_factor clears yVals the same way); the workspace is
-  // reused across batches and is NOT zeroed by the host
-  for (int i = 0; i < pl.N; i++) W(pl.o_yw, i) = 0.0;
   // ---- KKT factorisation (init_linsys_solver_qdldl) -----------------------------------------------------------------------
-  if (qp_factor(pl, ws, stride, b, S.sigma) < n) status = ST_NONCVX;  // osqp_setup fails: OSQP_NONCVX_ERROR
+  if (qp_factor(pl, ws, stride, b, S.sigma, sv) < n) status = ST_NONCVX;  // osqp_setup fails: OSQP_NONCVX_ERROR
 
   if (status == ST_UNSOLVED) {
     for (int i = 0; i < n; i++) { W(pl.o_x, i) = 0.0; W(pl.o_xprev, i) = 0.0; }
@@ -366,27 +376,27 @@ QP_HD void qp_solve_one(const QpPlanDev& pl, const QpIo& io, const uavmp_osqp_se
       for (int i = 0; i < n; i++) {
         const double xv = W(pl.o_x, i);
         W(pl.o_xprev, i) = xv;
-        W(pl.o_xz, i) = sigma * xv + (-1.0) * W(pl.o_q, i);
+        WXZ(i) = sigma * xv + (-1.0) * W(pl.o_q, i);
       }
       for (int i = 0; i < m; i++) {
         const double zv = W(pl.o_z, i);
         W(pl.o_zprev, i) = zv;
         const double t = W(pl.o_rhoinv, i) * W(pl.o_y, i);
-        W(pl.o_xz, n + i) = (-1.0) * t + 1.0 * zv;
+        WXZ(n + i) = (-1.0) * t + 1.0 * zv;
       }
       // keep the right-hand side of the z block: ztilde = rhs_z + rho^-1 * nu  (qdldl_interface.c:447-450)
-      for (int i = 0; i < m; i++) W(pl.o_tm, i) = W(pl.o_xz, n + i);
-      qp_kkt_solve(pl, ws, stride, b);
-      for (int i = 0; i < m; i++) W(pl.o_xz, n + i) = W(pl.o_tm, i) + W(pl.o_rhoinv, i) * W(pl.o_xz, n + i);
+      for (int i = 0; i < m; i++) W(pl.o_tm, i) = WXZ(n + i);
+      qp_kkt_solve(pl, ws, stride, b, sv);
+      for (int i = 0; i < m; i++) WXZ(n + i) = W(pl.o_tm, i) + W(pl.o_rhoinv, i) * WXZ(n + i);
       // update_x, update_z, update_y (auxil.c:171-228)
       for (int i = 0; i < n; i++) {
         const double xp = W(pl.o_xprev, i);
-        const double xn = alpha * W(pl.o_xz, i) + one_m_alpha * xp;
+        const double xn = alpha * WXZ(i) + one_m_alpha * xp;
         W(pl.o_x, i) = xn;
         W(pl.o_dx, i) = xn - xp;
       }
       for (int i = 0; i < m; i++) {
-        const double zt = W(pl.o_xz, n + i), zp = W(pl.o_zprev, i), yv = W(pl.o_y, i);
+        const double zt = WXZ(n + i), zp = W(pl.o_zprev, i), yv = W(pl.o_y, i);
         double zn = W(pl.o_rhoinv, i) * yv;
         zn = (1.0 * zn + alpha * zt) + one_m_alpha * zp;
         zn = fmin(fmax(zn, W(pl.o_l, i)), W(pl.o_u, i));
@@ -427,7 +437,7 @@ QP_HD void qp_solve_one(const QpPlanDev& pl, const QpIo& io, const uavmp_osqp_se
             W(pl.o_rho, i) = r;
             W(pl.o_rhoinv, i) = 1.0 / r;
           }
-          if (qp_factor(pl, ws, stride, b, sigma) < 0) { status = ST_NONCVX; break; }
+          if (qp_factor(pl, ws, stride, b, sigma, sv) < 0) { status = ST_NONCVX; break; }
         }
       }
     }
@@ -458,3 +468,6 @@ QP_HD void qp_solve_one(const QpPlanDev& pl, const QpIo& io, const uavmp_osqp_se
 }
 
 #undef W
+#undef WBP
+#undef WXZ
+#undef WYW

@@ -38,10 +38,11 @@ struct QpPlan {
 
 namespace {
 
-__global__ void __launch_bounds__(128) qp_solve_kernel(QpPlanDev pl, QpIo io, uavmp_osqp_settings S, double* ws) {
+__global__ void __launch_bounds__(QP_TPB) qp_solve_kernel(QpPlanDev pl, QpIo io, uavmp_osqp_settings S, double* ws, int use_smem) {
+  extern __shared__ __align__(16) double qp_sv[];  // [2 N][QP_TPB]: bp | xz of every thread's problem
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= io.B) return;
-  qp_solve_one(pl, io, S, ws, b);
+  qp_solve_one(pl, io, S, ws, b, use_smem ? qp_sv : nullptr);
 }
 
 // ---- pipeline glue: waypoints from the searched paths, outputs back to per-plan layout --------------------------------------
@@ -138,8 +139,13 @@ int qp_solve_batch_dev(uavmp_ctx* ctx, int order, int S, int B, const double* d_
   QpIo io;
   io.pos = d_pos; io.bv = d_bv; io.ba = d_ba; io.bj = d_bj ? d_bj : d_ba; io.T = d_T;
   io.coef = d_coef; io.solved = d_solved; io.status = d_status; io.iters = d_iters; io.B = B; io.stride = stride;
-  const int threads = 128;
-  qp_solve_kernel<<<(B + threads - 1) / threads, threads, 0, ctx->stream>>>(p->dev, io, *st, (double*)ctx->d_qp_ws);
+  const int threads = QP_TPB;
+  // bp and xz in shared memory when they fit (2 N doubles per thread); otherwise everything stays in the workspace
+  size_t smem = (size_t)2 * p->dev.N * sizeof(double) * threads;
+  const int use_smem = smem <= 200 * 1024 ? 1 : 0;
+  if (!use_smem) smem = 0;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(qp_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  qp_solve_kernel<<<(B + threads - 1) / threads, threads, smem, ctx->stream>>>(p->dev, io, *st, (double*)ctx->d_qp_ws, use_smem);
   UAVMP_CUDA(ctx, cudaGetLastError());
   ctx->tm.qp_launches = 1;
   return UAVMP_OK;

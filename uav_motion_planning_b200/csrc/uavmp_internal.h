@@ -22,6 +22,9 @@ struct KinoParamsDev {
   double box_r;     // conservative half-extent of the ellipsoid bounding cube
   float kd_r2;      // (float)(robot_r + 0.1) squared: the KD-tree radius filter of kino_astar.cpp:744
   double cull2;     // (max semi-axis * 1.001 + 1e-6)^2: farther points cannot be inside the ellipsoid
+  float cullf;      // the same with a 2 mm margin, for the float pre-cull
+  double inv_r2, inv_h2;
+  float inv_r2f, inv_h2f;
   double tk[UAVMP_MAXK];  // i * step_size
   double hk[UAVMP_MAXK];  // 0.5 * t * t
   double htau;            // 0.5 * tau * tau
@@ -32,6 +35,8 @@ struct LatticeDev {
   const double* ux; const double* uy; const double* uz;  // acceleration lattice in the reference's loop order
   const double* ginc;                                    // (u.u + rou) * tau
   const double* Einv;                                    // nprim x 9, row-major inverse of Rot diag(r,r,h) Rot^T
+  const double* b3;                                      // nprim x 3, body z axis (thrust direction)
+  const float4* b3f;                                     // the same in float (w unused), for the float slab pre-test
 };
 
 struct MapDev {
@@ -96,6 +101,7 @@ struct KinoBatchDev {
   int* next_query;           // work counter
   unsigned long long* phase_cycles;  // optional profiling: 8 words, SM cycles per phase summed over CTAs
   long long* query_cycles;           // optional profiling: B words, SM cycles each query occupied its CTA
+  unsigned long long* query_phase;   // optional profiling: B x 16 words, the phase cycles of every query
 };
 
 // ---- host-side context -----------------------------------------------------------------------------
@@ -111,7 +117,8 @@ struct uavmp_ctx {
   uavmp_kino_params kp;
   bool params_dirty = true;
   KinoParamsDev* d_kparams = nullptr;
-  double* d_lattice = nullptr;  // ux|uy|uz|ginc|Einv
+  double* d_lattice = nullptr;  // ux|uy|uz|ginc|Einv|b3
+  float4* d_b3f = nullptr;
   int nprim = 0;
 
   // map

@@ -98,9 +98,11 @@ class KinoAstar:
         self.ctx.check(self.lib.uavmp_kino_set_profile(self.ctx.h, int(on)))
 
     def profile(self, B):
-        ph = np.zeros(8, np.uint64)
-        qc = np.zeros(B, np.int64)
+        ph = np.zeros(16, np.uint64)
+        qc = np.zeros(17 * B, np.int64)
         grid = C.c_int()
-        self.ctx.check(self.lib.uavmp_kino_get_profile(self.ctx.h, _lib.ptr(ph), _lib.ptr(qc), B, C.byref(grid)))
-        names = ["pop", "shot_path", "tables_tile_grid", "cloud_ellipsoid", "dedup_probe_heuristic", "node_write", "heap_commit", "setup"]
-        return dict(phase_cycles=dict(zip(names, ph.tolist())), query_cycles=qc, grid=grid.value)
+        self.ctx.check(self.lib.uavmp_kino_get_profile(self.ctx.h, _lib.ptr(ph), _lib.ptr(qc), 17 * B, C.byref(grid)))
+        qphase = qc[B:].reshape(B, 16).copy()
+        qc = qc[:B].copy()
+        names = ["pop", "shot_path", "tables_tile_grid", "cloud_ellipsoid", "dedup_probe_heuristic", "node_write", "heap_commit", "setup", "cloud_staging", "n_staged", "n_unstaged", "sum_npts", "sum_flagged_prims", "commit_closure_io", "commit_slow_updates", "commit_deferred_writes"]
+        return dict(phase_cycles=dict(zip(names, ph.tolist())), query_cycles=qc, query_phase=qphase, names=names, grid=grid.value)
