@@ -44,6 +44,7 @@
 #define PTS_CAP 2048   // cloud points staged per expansion
 #define CS_CAP 1280    // cell_start entries staged per expansion
 #define COL_CAP 128    // cell columns staged per expansion
+#define HTOP 256       // heap slots 1 .. HTOP-1 (the top 8 levels) live in shared memory: a pop's sift-down starts on chip
 #define FULL 0xffffffffu
 // phase timers: thread 0 charges the cycles since the last mark to phase `k`
 #define PH_MARK(k) do { if (prof && tid == 0) { long long t_ = clock64(); s.ph[k] += (unsigned long long)(t_ - s.ph_t); s.ph_t = t_; } } while (0)
@@ -74,7 +75,8 @@ struct PhaseB {  // successor classification / commit
   uint32_t tab[TAB_SIZE];
   HeapSlot hc[HC_CAP];
   uint32_t hidx[HC_CAP];         // 1-based heap index of every staged ancestor slot
-  uint16_t win[UAVMP_MAXPRIM];   // last improving primitive of an existing node's group
+  int winm[UAVMP_MAXPRIM];       // position in list2 of the last improving candidate of a group (-1: none)
+  uint8_t imp[UAVMP_MAXPRIM];    // per candidate: 0 not improving, 1 improving, 2 improving and ordered with the pushes
   uint8_t inun[UAVMP_MAXPRIM];   // that node is an ancestor of a new leaf: its key was already written in order
   double gpc[UAVMP_MAXPRIM];     // g of every commit candidate
 };
@@ -99,9 +101,10 @@ struct SearchSmem {
   double axmin[3][UAVMP_MAXNA], axmax[3][UAVMP_MAXNA];
   double xlo[3], xhi[3];
   int to[3], rc0[3], rc1[3];
-  int any_ok, tile_ok, nT, npts;
+  int any_ok, tile_ok, nT, npts, n_upd, last_ev, nq;
   unsigned dmax, dsum, dhit;
   unsigned long long mbar;
+  HeapSlot htop[HTOP];
   KinoParamsDev P;
   MapDev M;
   double cp[3], cv[3], cg;
@@ -252,41 +255,45 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 #define HS_DIRTY 0x80000000u
 #define HS_MASK 0x7fffffffu
 
-__device__ void heap_pop_serial(HeapSlot* H, HashSlot* table, int& len, HeapSlot& top) {
+__device__ __forceinline__ HeapSlot hload(const SearchSmem& s, const HeapSlot* H, int i) { return i < HTOP ? s.htop[i] : H[i]; }
+__device__ __forceinline__ void hstore(SearchSmem& s, HeapSlot* H, int i, const HeapSlot& v) { if (i < HTOP) s.htop[i] = v; else H[i] = v; }
+__device__ __forceinline__ void hstore_key(SearchSmem& s, HeapSlot* H, int i, double f) { if (i < HTOP) s.htop[i].f = f; else __stcg(&H[i].f, f); }
+
+__device__ void heap_pop_serial(SearchSmem& s, HeapSlot* H, HashSlot* table, int& len, HeapSlot& top) {
   // std::pop_heap + pop_back (bits/stl_heap.h __pop_heap -> __adjust_heap -> __push_heap), comp(a,b) = f[a] > f[b]
-  top = H[1];
+  top = hload(s, H, 1);
   int old_len = len;
   len = old_len - 1;
   if (old_len <= 1) return;
-  HeapSlot value = H[old_len];  // last element
+  HeapSlot value = hload(s, H, old_len);  // last element
   int n = len;
   int hole = 0;
   int second = 0;
   while (second < (n - 1) / 2) {
     second = 2 * (second + 1);
-    HeapSlot r = H[second + 1], l = H[second];  // right child = slot `second`, left = second-1
+    HeapSlot r = hload(s, H, second + 1), l = hload(s, H, second);  // right child = slot `second`, left = second-1
     if (r.f > l.f) { second--; r = l; }
-    H[hole + 1] = r;
+    hstore(s, H, hole + 1, r);
     table[r.hs].heap_pos = (uint32_t)hole;
     hole = second;
   }
   if ((n & 1) == 0 && second == (n - 2) / 2) {
     second = 2 * (second + 1);
-    HeapSlot l = H[second];  // slot second-1
-    H[hole + 1] = l;
+    HeapSlot l = hload(s, H, second);  // slot second-1
+    hstore(s, H, hole + 1, l);
     table[l.hs].heap_pos = (uint32_t)hole;
     hole = second - 1;
   }
   int parent = (hole - 1) / 2;
   while (hole > 0) {
-    HeapSlot pe = H[parent + 1];
+    HeapSlot pe = hload(s, H, parent + 1);
     if (!(pe.f > value.f)) break;
-    H[hole + 1] = pe;
+    hstore(s, H, hole + 1, pe);
     table[pe.hs].heap_pos = (uint32_t)hole;
     hole = parent;
     parent = (hole - 1) / 2;
   }
-  H[hole + 1] = value;
+  hstore(s, H, hole + 1, value);
   table[value.hs].heap_pos = (uint32_t)hole;
 }
 
@@ -316,7 +323,8 @@ __device__ __forceinline__ void closure_load(SearchSmem& s, const HeapSlot* H, i
   if (lane != 0) {
     for (int j = 0; j < cnt; j++) {
       // asynchronous 16 B global -> shared copies (L2 only): all of a level's loads are in flight at once
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&s.b.hc[c.off + j])), "l"(H + lo + j) : "memory");
+      if (lo + j < HTOP) s.b.hc[c.off + j] = s.htop[lo + j];
+      else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&s.b.hc[c.off + j])), "l"(H + lo + j) : "memory");
       s.b.hidx[c.off + j] = (uint32_t)(lo + j);
     }
   }
@@ -332,7 +340,7 @@ __device__ __forceinline__ void closure_flush(SearchSmem& s, HeapSlot* H, HashSl
     if (ent.hs & HS_DIRTY) {
       const uint32_t idx = s.b.hidx[e];
       ent.hs &= HS_MASK;
-      H[idx] = ent;
+      hstore(s, H, (int)idx, ent);
       table[ent.hs].heap_pos = idx - 1;
     }
   }
@@ -395,7 +403,7 @@ __device__ void heap_set_key_slow(SearchSmem& s, HeapSlot* H, const HashSlot* ta
     } else {
       __threadfence_block();
       const uint32_t pos = __ldcg(&table[hs].heap_pos);
-      __stcg(&H[pos + 1].f, f);
+      hstore_key(s, H, (int)pos + 1, f);
     }
   }
   __syncwarp();
@@ -573,7 +581,7 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
       nd.g = 0.0; nd.parent = UAVMP_NONE; nd.hslot = hh; nd.input = 0; nd.closed = 0; nd.pad0 = 0; nd.pad1 = 0;
       nodes[0] = nd;
       HeapSlot hs; hs.f = P.lambda * h; hs.id = 0; hs.hs = hh;
-      H[1] = hs;
+      hstore(s, H, 1, hs);
       s.heap_len = 1; s.use_num = 1; s.n_pop = 0; s.status = 0;
       s.pop_hash = 0xcbf29ce484222325ull;
       s.cnt[3] += 1; s.cnt[4] += 1; s.cnt[6] += 1;  // hash probe, insert, heuristic of the start node
@@ -592,7 +600,7 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
         } else {
           HeapSlot top;
           int len = s.heap_len;
-          heap_pop_serial(H, table, len, top);
+          heap_pop_serial(s, H, table, len, top);
           s.heap_len = len;
           KinoNode nd = nodes[top.id];
           nodes[top.id].closed = 1;
@@ -619,7 +627,7 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
           s.n_pop++;
           double dx = nd.px - s.gp[0], dy = nd.py - s.gp[1], dz = nd.pz - s.gp[2];
           s.flag = (sqrt(dot3(dx, dy, dz, dx, dy, dz)) < P.goal_tol) ? 1 : 0;
-          s.n1 = 0; s.n2 = 0; s.nT = 0;
+          s.n1 = 0; s.n2 = 0; s.nT = 0; s.n_upd = 0; s.last_ev = -1;
         }
       }
       __syncthreads();
@@ -737,11 +745,13 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
         s.axmin[ax][a] = ok ? xmin : 1e300;   s.axmax[ax][a] = ok ? xmax : -1e300;
       }
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0) {
+        // lanes 0..26 hold (axis, a); butterfly min/max inside each 9-lane... simpler: lane < 3 reduces one axis from smem
         bool any = true, fits = true;
-        for (int ax = 0; ax < 3; ax++) {
-          int lo = INT_MAX, hi = INT_MIN;
-          double xl = 1e300, xh = -1e300;
+        int lo = INT_MAX, hi = INT_MIN;
+        double xl = 1e300, xh = -1e300;
+        if (lane < 3) {
+          const int ax = lane;
           for (int a = 0; a < na; a++) {
             lo = min(lo, s.aimin[ax][a]); hi = max(hi, s.aimax[ax][a]);
             xl = fmin(xl, s.axmin[ax][a]); xh = fmax(xh, s.axmax[ax][a]);
@@ -751,9 +761,14 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
           else if (hi - lo + 1 > (ax == 2 ? TBZ : TB)) fits = false;
           s.to[ax] = lo; s.xlo[ax] = xl; s.xhi[ax] = xh;
         }
-        s.any_ok = any ? 1 : 0;
-        s.tile_ok = (any && fits && use_tma) ? 1 : 0;
-        if (s.tile_ok) {
+        any = __all_sync(FULL, any);
+        fits = __all_sync(FULL, fits);
+        if (lane == 0) {
+          s.any_ok = any ? 1 : 0;
+          s.tile_ok = (any && fits && use_tma) ? 1 : 0;
+        }
+        __syncwarp();
+        if (lane == 0 && any && fits && use_tma) {
           // stage the flags box (inner dimension z): one TMA instruction, completion on the mbarrier
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           mbar_expect_tx(&s.mbar, TB * TB * TBZ);
@@ -765,6 +780,7 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
       if (tile_ok) { mbar_wait(&s.mbar, tma_parity); tma_parity ^= 1u; }
 
       // ---- A1. grid + velocity + in-map for every primitive from shared memory (:172-211 minus the ellipsoid) ----
+      int my_need = 0;
       if (s.any_ok) {
         const int tx = s.to[0], ty = s.to[1], tz = s.to[2];
         for (int p = tid; p < nprim; p += KT) {
@@ -784,15 +800,16 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
           }
           s.state[p] = st;
           s.a.need[p] = (st == ST_FEASIBLE) ? (uint16_t)need : (uint16_t)0;
+          if (st == ST_FEASIBLE && need) my_need = 1;
         }
       } else {
         for (int p = tid; p < nprim; p += KT) s.state[p] = ST_REJECT;
       }
-      __syncthreads();
+      const int any_need = __syncthreads_or(my_need);
       // work units of the cloud test: (checkpoint i, lattice column a, b) with the set of c whose checkpoint is flagged.
       // The nine centres of a unit share x and y, so one pass over the candidate points serves all of them.  Ordered
       // compaction keeps neighbouring units on neighbouring lanes (similar candidate sets -> similar trip counts).
-      {
+      if (any_need) {
         const int nU = s.any_ok ? K * na * na : 0;
         const int per = (nU + KT - 1) / KT;
         uint32_t mine[8];
@@ -891,26 +908,12 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
             float fz[UAVMP_MAXNA];
 #pragma unroll
             for (int c = 0; c < UAVMP_MAXNA; c++) fz[c] = (c < na) ? (float)s.X[i][2][c] : 1e30f;
-            int trip = 0;
-            for (int g = r; g < npts && mask; g += G, trip++) {
-              if ((trip & 63) == 63) {  // somebody else may have rejected these primitives in the meantime
-                for (int c = 0; c < na; c++) if (s.state[ab * na + c] != ST_FEASIBLE) mask &= ~(1u << c);
-              }
-              const float4 q = s.a.pts[g];
-              my_cloud++;
-              const float dx = q.x - fx, dy = q.y - fy;
-              const float dxy2 = dx * dx + dy * dy;
-              if (dxy2 > cullf) continue;  // outside the cylinder every centre of the unit lives in
-              uint32_t cand = 0;
-#pragma unroll
-              for (int c = 0; c < UAVMP_MAXNA; c++) {
-                const float dz = q.z - fz[c];
-                if (dxy2 + dz * dz <= cullf) cand |= 1u << c;
-              }
-              cand &= mask;
+            // two points per trip: their cull chains are independent, which roughly halves the dependent latency
+            auto decide = [&](const float4& q, float dx, float dy, float dxy2, uint32_t cand) {
               while (cand) {
                 const int c = __ffs(cand) - 1;
                 cand &= cand - 1;
+                if (!((mask >> c) & 1u)) continue;
                 {  // float slab test: || E^-1 d ||^2 = (|d|^2 - w^2)/r^2 + w^2/h^2, w = d . b3; 1 % margin >> float error
                   const float4 bf = __ldg(lat.b3f + (ab * na + c));
                   const float dz = q.z - fz[c];
@@ -919,8 +922,44 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
                 }
                 EllipsoidTest t;
                 make_test(t, P, lat, ab * na + c, px, py, s.X[i][2][c]);
-                if (point_hits(t, q)) { s.state[ab * na + c] = ST_REJECT; mask &= ~(1u << c); my_hits++; }
+                if (point_hits(t, q)) { s.state[ab * na + c] = ST_REJECT; mask &= ~(1u << c); }
               }
+            };
+            int trip = 0;
+            constexpr int NP = 4;  // points per trip
+            for (int g = r; g < npts && mask; g += NP * G, trip++) {
+              if ((trip & 15) == 15) {  // somebody else may have rejected these primitives in the meantime
+                for (int c = 0; c < na; c++) if (s.state[ab * na + c] != ST_FEASIBLE) mask &= ~(1u << c);
+              }
+              float4 q[NP];
+              float dx[NP], dy[NP], d2[NP];
+              bool in[NP];
+              bool any_in = false;
+#pragma unroll
+              for (int k = 0; k < NP; k++) {
+                const bool ok = g + k * G < npts;
+                q[k] = s.a.pts[ok ? g + k * G : g];
+                dx[k] = q[k].x - fx; dy[k] = q[k].y - fy;
+                d2[k] = dx[k] * dx[k] + dy[k] * dy[k];
+                in[k] = ok && d2[k] <= cullf;
+                any_in = any_in || in[k];
+                my_cloud += ok ? 1u : 0u;
+              }
+              if (!any_in) continue;  // outside the cylinder every centre of the unit lives in
+              uint32_t cm[NP];
+#pragma unroll
+              for (int k = 0; k < NP; k++) cm[k] = 0;
+#pragma unroll
+              for (int c = 0; c < UAVMP_MAXNA; c++) {
+#pragma unroll
+                for (int k = 0; k < NP; k++) {
+                  const float z = q[k].z - fz[c];
+                  if (d2[k] + z * z <= cullf) cm[k] |= 1u << c;
+                }
+              }
+#pragma unroll
+              for (int k = 0; k < NP; k++)
+                if (in[k]) decide(q[k], dx[k], dy[k], d2[k], cm[k] & mask);
             }
           }
         } else {
@@ -978,7 +1017,7 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
         const double gp = s.cg + ginc_of(P, p);
         uint32_t h = hash_key(k, table_bits);
         uint8_t st;
-        s.b.win[p] = 0xffff;
+        s.b.winm[p] = -1;
         s.b.inun[p] = 0;
         for (;;) {
           const uint4 w0 = __ldcg(reinterpret_cast<const uint4*>(&table[h]));      // key | id | heap_pos
@@ -1112,40 +1151,77 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
         nodes[nid] = nd;
       }
       __syncthreads();
+      // ---- U. in-place mutations (:249-266), resolved in parallel.  Within one voxel group the reference applies the
+      // candidates in lattice order, each one iff its g is below the running minimum; whether candidate e improves
+      // depends only on the group's earlier candidates, the group's final state is its LAST improving candidate, and
+      // `optimal_time` (Q2) is left by the last improving candidate / new node overall.  Only groups whose node is an
+      // ancestor of a new leaf (or a new leaf itself) must still touch the open list in order, in phase D. -------------
+      for (int e = tid; e < n2; e += KT) {
+        const int p = s.list2[e];
+        const uint8_t st = s.state[p];
+        bool event = false;  // does this candidate change optimal_time / count as an update?
+        if (st == ST_NEW) {
+          event = true;
+        } else {
+          const int leader = (st == ST_FOLLOW_CAND) ? (int)s.id[p] : p;
+          double run = s.b.gcur[leader];  // g of the existing node (or of the new leader) before this expansion's updates
+          for (int e2 = 0; e2 < e; e2++) {
+            const int p2 = s.list2[e2];
+            const uint8_t st2 = s.state[p2];
+            if (st2 == ST_NEW) continue;
+            const int l2 = (st2 == ST_FOLLOW_CAND) ? (int)s.id[p2] : p2;
+            if (l2 == leader) run = fmin(run, s.b.gpc[p2]);
+          }
+          if (s.b.gpc[p] < run) {  // tmp_g_cost < old_node->g_cost (:254)
+            event = true;
+            atomicMax(&s.b.winm[leader], e);
+            atomicAdd(&s.n_upd, 1);
+            bool in_union = s.state[leader] == ST_NEW;
+            if (!in_union && n_new > 0) {
+              const int pos1 = (int)s.b.hpos[leader] + 1, l0 = s.heap_len;
+              for (int d = 0; d < 32; d++) {
+                const int lo = (l0 + 1) >> d, hi = (l0 + n_new) >> d;
+                if (lo < 1) break;
+                if (pos1 >= lo && pos1 <= hi) { in_union = true; break; }
+              }
+            }
+            if (in_union) s.b.inun[leader] = 1;
+            s.b.imp[p] = in_union ? 2 : 1;
+          } else {
+            s.b.imp[p] = 0;
+          }
+        }
+        if (event && s.b.topt[p] >= 0.0) atomicMax(&s.last_ev, e);
+      }
+      __syncthreads();
       PH_MARK(5);
 
-      // ---- D. ordered commit (:225-266).  Warp 0 replays the candidates in lattice order, touching shared memory
-      // only: heap pushes go through the staged ancestor closure, in-place mutations of nodes that are NOT ancestors
-      // of any new leaf are merely recorded (their heap position cannot change during this expansion) -------------
+      // ---- D. ordered part of the commit (:225-266): warp 0 replays, in lattice order, the heap pushes of the new nodes
+      // (through the staged ancestor closure: one push = one ballot) and the key mutations of nodes that are ancestors
+      // of new leaves.  Everything else was resolved in U and is written back in D2. -------------------------------------
       if (warp == 0) {
         int pushed = 0, len = s.heap_len, batch_left = 0;
-        const int len0 = len;
-        double opt_time = s.opt_time;
-        int n_upd = 0;
         Closure cl;
         cl.lo = cl.off = cl.lo_m1 = cl.off_m1 = cl.total = 0; cl.active = false;
-        // does heap slot `pos1` (1-based) belong to the ancestors of this expansion's new leaves? (lane d tests level d)
-        const int un_lo = (len0 + 1) >> lane, un_hi = (len0 + n_new) >> lane;
         for (int cb = 0; cb < n2; cb += 32) {
-          // list2 holds the candidates in lattice order (phase C); every lane fetches its own candidate once and the
-          // serial replay below only shuffles registers
-          const bool cand = cb + lane < n2;
-          const int p = cand ? (int)s.list2[cb + lane] : 0;
-          const int st = cand ? (int)s.state[p] : (int)ST_REJECT;
-          double c_f = 0.0, c_topt = -1.0, c_gp = 0.0;
+          const bool in = cb + lane < n2;
+          const int p = in ? (int)s.list2[cb + lane] : 0;
+          const int st = in ? (int)s.state[p] : (int)ST_REJECT;
+          const bool cand = in && (st == ST_NEW || s.b.imp[p] == 2);
+          double c_f = 0.0;
           uint32_t c_id = 0, c_hs = 0;
-          int c_leader = p;
           if (cand) {
-            c_f = s.b.f[p]; c_topt = s.b.topt[p]; c_gp = s.b.gpc[p];
-            if (st == ST_NEW) { c_id = s.id[p]; c_hs = s.b.hs[p]; }
-            else if (st == ST_FOLLOW_CAND) c_leader = (int)s.id[p];
+            c_f = s.b.f[p];
+            const int leader = (st == ST_NEW) ? p : ((st == ST_FOLLOW_CAND) ? (int)s.id[p] : p);
+            c_id = s.id[leader]; c_hs = s.b.hs[leader];
           }
           unsigned evm = __ballot_sync(FULL, cand);
           while (evm) {
             const int l = __ffs(evm) - 1;
             evm &= evm - 1;
             const int ste = __shfl_sync(FULL, st, l);
-            const double f = __shfl_sync(FULL, c_f, l), topt = __shfl_sync(FULL, c_topt, l);
+            const double f = __shfl_sync(FULL, c_f, l);
+            const uint32_t nid = __shfl_sync(FULL, c_id, l), nhs = __shfl_sync(FULL, c_hs, l);
             if (ste == ST_NEW) {
               if (batch_left == 0) {
                 const long long t0 = prof ? clock64() : 0;
@@ -1154,33 +1230,14 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
                 closure_load(s, H, len, batch_left, lane, cl);
                 if (prof && lane == 0) s.ph[13] += (unsigned long long)(clock64() - t0);
               }
-              closure_push(s, len + 1, f, __shfl_sync(FULL, c_id, l), __shfl_sync(FULL, c_hs, l), lane, cl);
+              closure_push(s, len + 1, f, nid, nhs, lane, cl);
               len++;
               pushed++;
               batch_left--;
-              if (topt >= 0.0) opt_time = topt;
             } else {
-              const int leader = __shfl_sync(FULL, c_leader, l);
-              const double gp = __shfl_sync(FULL, c_gp, l);
-              if (gp < s.b.gcur[leader]) {  // tmp_g_cost < old_node->g_cost (:254)
-                const int pe = __shfl_sync(FULL, p, l);
-                const bool lead_new = s.state[leader] == ST_NEW;
-                bool in_union = lead_new;
-                if (!lead_new) {
-                  const int pos1 = (int)s.b.hpos[leader] + 1;
-                  in_union = __any_sync(FULL, n_new > 0 && un_lo >= 1 && pos1 >= un_lo && pos1 <= un_hi);
-                }
-                __syncwarp();
-                if (lane == 0) { s.b.gcur[leader] = gp; s.b.win[leader] = (uint16_t)pe; if (in_union) s.b.inun[leader] = 1; }
-                if (in_union) {
-                  const long long t0 = prof ? clock64() : 0;
-                  heap_set_key_slow(s, H, table, s.id[leader], s.b.hs[leader], f, lane, cl);
-                  if (prof && lane == 0) s.ph[14] += (unsigned long long)(clock64() - t0);
-                }
-                if (topt >= 0.0) opt_time = topt;
-                n_upd++;
-                __syncwarp();
-              }
+              const long long t0 = prof ? clock64() : 0;
+              heap_set_key_slow(s, H, table, nid, nhs, f, lane, cl);
+              if (prof && lane == 0) s.ph[14] += (unsigned long long)(clock64() - t0);
             }
           }
         }
@@ -1192,8 +1249,8 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
         if (lane == 0) {
           s.heap_len = len;
           s.use_num += n_new;
-          s.opt_time = opt_time;
-          s.cnt[3] += n1; s.cnt[4] += n_new; s.cnt[5] += n_upd; s.cnt[6] += n_new + n_upd;
+          if (s.last_ev >= 0) s.opt_time = s.b.topt[s.list2[s.last_ev]];
+          s.cnt[3] += n1; s.cnt[4] += n_new; s.cnt[5] += s.n_upd; s.cnt[6] += n_new + s.n_upd;
         }
       }
       __syncthreads();
@@ -1203,8 +1260,9 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
         const int p = s.list1[e];
         const uint8_t st = s.state[p];
         if (st != ST_NEW && st != ST_OPEN_CAND && st != ST_OPEN_NOCAND) continue;  // leaders only
-        const int w = s.b.win[p];
-        if (w == 0xffff) continue;
+        const int we = s.b.winm[p];
+        if (we < 0) continue;
+        const int w = s.list2[we];
         const int a = w / (na * na), b = (w / na) % na, c = w % na;
         KinoNode* nd = nodes + s.id[p];
         nd->px = s.EX[0][a]; nd->py = s.EX[1][b]; nd->pz = s.EX[2][c];
@@ -1212,7 +1270,7 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
         const double g = s.cg + ginc_of(P, w);
         nd->g = g; nd->parent = s.cur_id; nd->input = (uint16_t)w;
         table[s.b.hs[p]].g = g;
-        if (st != ST_NEW && !s.b.inun[p]) H[s.b.hpos[p] + 1].f = s.b.f[w];
+        if (st != ST_NEW && !s.b.inun[p]) hstore_key(s, H, (int)s.b.hpos[p] + 1, s.b.f[w]);
       }
       __syncthreads();
       if (prof && tid == 0) s.ph[15] += (unsigned long long)(clock64() - t_d2);

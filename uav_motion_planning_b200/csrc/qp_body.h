@@ -80,6 +80,7 @@ QP_HD int qp_factor(const QpPlanDev& pl, double* ws, size_t stride, int b, doubl
       }
       const double lv = yc * W(pl.o_Ddinv, c);
       W(pl.o_Lx, pos) = lv;
+      W(pl.o_LxT, QP_LDG(pl.Ltpos + pos)) = lv;  // second copy in the order the L' solve consumes it
       Dk -= yc * lv;
       WYW(c) = 0.0;
     }
@@ -91,21 +92,54 @@ QP_HD int qp_factor(const QpPlanDev& pl, double* ws, size_t stride, int b, doubl
   return positive;
 }
 
-// xz <- K^-1 xz  (qdldl_interface.c:394-415: permute, L solve, D^-1, L' solve, permute back)
+// xz <- K^-1 xz  (qdldl_interface.c:394-415: permute, L solve, D^-1, L' solve, permute back).
+// The arithmetic and its order are QDLDL_solve's; only the FETCH of L's values is reorganised: both triangular solves
+// consume L as a linear stream (Lx in column order, LxT in the L' solve's order), fetched 8 values at a time so that a
+// thread has 8 loads in flight instead of one.
 QP_HD void qp_kkt_solve(const QpPlanDev& pl, double* ws, size_t stride, int b, double* sv) {
-  const int N = pl.N;
+  const int N = pl.N, nnzL = pl.nnzL;
   for (int j = 0; j < N; j++) WBP(j) = WXZ(QP_LDG(pl.perm + j));
-  for (int i = 0; i < N; i++) {
-    const double val = WBP(i);
-    for (int j = QP_LDG(pl.Lp + i); j < QP_LDG(pl.Lp + i + 1); j++) {
-      const int r = QP_LDG(pl.Li + j);
-      WBP(r) = WBP(r) - W(pl.o_Lx, j) * val;
+  {  // QDLDL_Lsolve: for i: val = x[i]; for j in col i: x[Li[j]] -= Lx[j] * val
+    int i = 0, cend = QP_LDG(pl.Lp + 1);
+    double val = WBP(0);
+    for (int j0 = 0; j0 < nnzL; j0 += 8) {
+      double lx[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) lx[u] = (j0 + u < nnzL) ? W(pl.o_Lx, j0 + u) : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int j = j0 + u;
+        if (j < nnzL) {
+          while (j >= cend) { i++; cend = QP_LDG(pl.Lp + i + 1); val = WBP(i); }
+          const int r = QP_LDG(pl.Li + j);
+          WBP(r) = WBP(r) - lx[u] * val;
+        }
+      }
     }
   }
-  for (int i = 0; i < N; i++) WBP(i) = WBP(i) * W(pl.o_Ddinv, i);
-  for (int i = N - 1; i >= 0; i--) {
-    double val = WBP(i);
-    for (int j = QP_LDG(pl.Lp + i); j < QP_LDG(pl.Lp + i + 1); j++) val -= W(pl.o_Lx, j) * WBP(QP_LDG(pl.Li + j));
+  for (int i0 = 0; i0 < N; i0 += 8) {
+    double dv[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) dv[u] = (i0 + u < N) ? W(pl.o_Ddinv, i0 + u) : 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; u++) if (i0 + u < N) WBP(i0 + u) = WBP(i0 + u) * dv[u];
+  }
+  {  // QDLDL_Ltsolve: for i = N-1..0: val = x[i]; for j in col i: val -= Lx[j] * x[Li[j]]; x[i] = val
+    int t = 0, i = N - 1, cend = QP_LDG(pl.LtEnd);
+    double val = WBP(N - 1);
+    for (int k0 = 0; k0 < nnzL; k0 += 8) {
+      double lx[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) lx[u] = (k0 + u < nnzL) ? W(pl.o_LxT, k0 + u) : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int k = k0 + u;
+        if (k < nnzL) {
+          while (k >= cend) { WBP(i) = val; t++; i = N - 1 - t; val = WBP(i); cend = QP_LDG(pl.LtEnd + t); }
+          val -= lx[u] * WBP(QP_LDG(pl.LtR + k));
+        }
+      }
+    }
     WBP(i) = val;
   }
   for (int j = 0; j < N; j++) WXZ(QP_LDG(pl.perm + j)) = WBP(j);
@@ -372,39 +406,61 @@ QP_HD void qp_solve_one(const QpPlanDev& pl, const QpIo& io, const uavmp_osqp_se
     int iter;
     for (iter = 1; iter <= S.max_iter; iter++) {
       // x_prev <- x, z_prev <- z (the reference swaps pointers; x and z are fully overwritten below)
-      // compute_rhs (auxil.c:135-157)
-      for (int i = 0; i < n; i++) {
-        const double xv = W(pl.o_x, i);
-        W(pl.o_xprev, i) = xv;
-        WXZ(i) = sigma * xv + (-1.0) * W(pl.o_q, i);
+      // compute_rhs (auxil.c:135-157).  Loops are written in batches of 4 with all loads ahead of the stores: the values
+      // and their order are unchanged, a thread merely keeps several independent loads in flight.
+      for (int i0 = 0; i0 < n; i0 += 4) {
+        double xv[4], qv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (i0 + u < n) { xv[u] = W(pl.o_x, i0 + u); qv[u] = W(pl.o_q, i0 + u); }
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (i0 + u < n) { W(pl.o_xprev, i0 + u) = xv[u]; WXZ(i0 + u) = sigma * xv[u] + (-1.0) * qv[u]; }
       }
-      for (int i = 0; i < m; i++) {
-        const double zv = W(pl.o_z, i);
-        W(pl.o_zprev, i) = zv;
-        const double t = W(pl.o_rhoinv, i) * W(pl.o_y, i);
-        WXZ(n + i) = (-1.0) * t + 1.0 * zv;
+      for (int i0 = 0; i0 < m; i0 += 4) {
+        double zv[4], rv[4], yv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (i0 + u < m) { zv[u] = W(pl.o_z, i0 + u); rv[u] = W(pl.o_rhoinv, i0 + u); yv[u] = W(pl.o_y, i0 + u); }
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (i0 + u < m) {
+          W(pl.o_zprev, i0 + u) = zv[u];
+          const double t = rv[u] * yv[u];
+          const double rhs = (-1.0) * t + 1.0 * zv[u];
+          WXZ(n + i0 + u) = rhs;
+          W(pl.o_tm, i0 + u) = rhs;  // keep the right-hand side of the z block (qdldl_interface.c:447-450)
+        }
       }
-      // keep the right-hand side of the z block: ztilde = rhs_z + rho^-1 * nu  (qdldl_interface.c:447-450)
-      for (int i = 0; i < m; i++) W(pl.o_tm, i) = WXZ(n + i);
       qp_kkt_solve(pl, ws, stride, b, sv);
-      for (int i = 0; i < m; i++) WXZ(n + i) = W(pl.o_tm, i) + W(pl.o_rhoinv, i) * WXZ(n + i);
-      // update_x, update_z, update_y (auxil.c:171-228)
-      for (int i = 0; i < n; i++) {
-        const double xp = W(pl.o_xprev, i);
-        const double xn = alpha * WXZ(i) + one_m_alpha * xp;
-        W(pl.o_x, i) = xn;
-        W(pl.o_dx, i) = xn - xp;
+      // update_x (auxil.c:171-186)
+      for (int i0 = 0; i0 < n; i0 += 4) {
+        double xp[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (i0 + u < n) xp[u] = W(pl.o_xprev, i0 + u);
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (i0 + u < n) {
+          const double xn = alpha * WXZ(i0 + u) + one_m_alpha * xp[u];
+          W(pl.o_x, i0 + u) = xn;
+          W(pl.o_dx, i0 + u) = xn - xp[u];
+        }
       }
-      for (int i = 0; i < m; i++) {
-        const double zt = WXZ(n + i), zp = W(pl.o_zprev, i), yv = W(pl.o_y, i);
-        double zn = W(pl.o_rhoinv, i) * yv;
-        zn = (1.0 * zn + alpha * zt) + one_m_alpha * zp;
-        zn = fmin(fmax(zn, W(pl.o_l, i)), W(pl.o_u, i));
-        W(pl.o_z, i) = zn;
-        double dy = (alpha * zt + one_m_alpha * zp) + (-1.0) * zn;
-        dy = dy * W(pl.o_rho, i);
-        W(pl.o_dy, i) = dy;
-        W(pl.o_y, i) = yv + dy;
+      // ztilde = rhs_z + rho^-1 * nu, then update_z / update_y (auxil.c:188-228)
+      for (int i0 = 0; i0 < m; i0 += 2) {
+        double tmv[2], rv[2], zp[2], yv[2], lv[2], uv[2], rh[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) if (i0 + u < m) {
+          tmv[u] = W(pl.o_tm, i0 + u); rv[u] = W(pl.o_rhoinv, i0 + u); zp[u] = W(pl.o_zprev, i0 + u); yv[u] = W(pl.o_y, i0 + u);
+          lv[u] = W(pl.o_l, i0 + u); uv[u] = W(pl.o_u, i0 + u); rh[u] = W(pl.o_rho, i0 + u);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) if (i0 + u < m) {
+          const double zt = tmv[u] + rv[u] * WXZ(n + i0 + u);
+          double zn = rv[u] * yv[u];
+          zn = (1.0 * zn + alpha * zt) + one_m_alpha * zp[u];
+          zn = fmin(fmax(zn, lv[u]), uv[u]);
+          W(pl.o_z, i0 + u) = zn;
+          double dy = (alpha * zt + one_m_alpha * zp[u]) + (-1.0) * zn;
+          dy = dy * rh[u];
+          W(pl.o_dy, i0 + u) = dy;
+          W(pl.o_y, i0 + u) = yv[u] + dy;
+        }
       }
       const bool can_check = S.check_termination && (iter % S.check_termination == 0);
       checked_last = can_check;

@@ -218,6 +218,17 @@ QpPlanHost* qp_plan_build(int order, int S) {
     }
     P.Rp[kk + 1] = (int)P.Rc.size();
   }
+  // ---- L in the order QDLDL_Ltsolve consumes it: columns N-1 .. 0, entries of a column in storage order ---------------
+  P.Ltpos.assign(P.nnzL, 0); P.LtR.assign(P.nnzL, 0); P.LtEnd.assign(N + 1, 0);
+  {
+    int k = 0;
+    for (int t = 0; t < N; t++) {
+      const int i = N - 1 - t;
+      for (int j = P.Lp[i]; j < P.Lp[i + 1]; j++) { P.Ltpos[j] = k; P.LtR[k] = P.Li[j]; k++; }
+      P.LtEnd[t] = k;
+    }
+    P.LtEnd[N] = k;
+  }
   return pl;
 }
 
@@ -228,6 +239,7 @@ void qp_plan_pack(const QpPlanHost& H, std::vector<int>& ints, std::vector<doubl
   o.Ap = push(H.Ap); o.Ai = push(H.Ai); o.A_seg = push(H.A_seg); o.A_pow = push(H.A_pow);
   o.l_src = push(H.l_src); o.perm = push(H.perm); o.Kp = push(H.Kp); o.Ki = push(H.Ki); o.Kkind = push(H.Kkind);
   o.Kidx = push(H.Kidx); o.Lp = push(H.Lp); o.Li = push(H.Li); o.Rp = push(H.Rp); o.Rc = push(H.Rc); o.Rpos = push(H.Rpos);
+  o.Ltpos = push(H.Ltpos); o.LtR = push(H.LtR); o.LtEnd = push(H.LtEnd);
   dbls = H.P_coef;
   o.A_coef = dbls.size();
   dbls.insert(dbls.end(), H.A_coef.begin(), H.A_coef.end());
@@ -241,13 +253,14 @@ void qp_plan_bind(const QpPlanHost& H, const QpPlanOffsets& o, const int* I, con
   D.P_coef = Dbl; D.A_coef = Dbl + o.A_coef;
   D.l_src = I + o.l_src; D.perm = I + o.perm; D.Kp = I + o.Kp; D.Ki = I + o.Ki; D.Kkind = I + o.Kkind; D.Kidx = I + o.Kidx;
   D.Lp = I + o.Lp; D.Li = I + o.Li; D.Rp = I + o.Rp; D.Rc = I + o.Rc; D.Rpos = I + o.Rpos;
+  D.Ltpos = I + o.Ltpos; D.LtR = I + o.LtR; D.LtEnd = I + o.LtEnd;
   // workspace layout (offsets in doubles; element e of problem b lives at ws[e * stride + b])
   int at = 0;
   auto take = [&](int len) { int r = at; at += len; return r; };
   const int n = H.n, m = H.m, N = H.N;
   D.o_Px = take(H.nnzP); D.o_Ax = take(H.nnzA); D.o_q = take(n); D.o_l = take(m); D.o_u = take(m);
   D.o_D = take(n); D.o_Dinv = take(n); D.o_E = take(m); D.o_Einv = take(m); D.o_rho = take(m); D.o_rhoinv = take(m);
-  D.o_Lx = take(H.nnzL); D.o_Dd = take(N); D.o_Ddinv = take(N); D.o_yw = take(N);
+  D.o_Lx = take(H.nnzL); D.o_LxT = take(H.nnzL); D.o_Dd = take(N); D.o_Ddinv = take(N); D.o_yw = take(N);
   D.o_x = take(n); D.o_xprev = take(n); D.o_dx = take(n); D.o_Pxv = take(n); D.o_Aty = take(n);
   D.o_z = take(m); D.o_zprev = take(m); D.o_y = take(m); D.o_dy = take(m); D.o_Axv = take(m);
   D.o_xz = take(N); D.o_bp = take(N); D.o_tn = take(n); D.o_tm = take(m);
