@@ -943,7 +943,6 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
                 d2[k] = dx[k] * dx[k] + dy[k] * dy[k];
                 in[k] = ok && d2[k] <= cullf;
                 any_in = any_in || in[k];
-                my_cloud += ok ? 1u : 0u;
               }
               if (!any_in) continue;  // outside the cylinder every centre of the unit lives in
               uint32_t cm[NP];
@@ -959,7 +958,7 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
               }
 #pragma unroll
               for (int k = 0; k < NP; k++)
-                if (in[k]) decide(q[k], dx[k], dy[k], d2[k], cm[k] & mask);
+                if (in[k]) { my_cloud += (unsigned)__popc(cm[k] & mask); decide(q[k], dx[k], dy[k], d2[k], cm[k] & mask); }
             }
           }
         } else {

@@ -102,17 +102,27 @@ QP_HD void qp_kkt_solve(const QpPlanDev& pl, double* ws, size_t stride, int b, d
   {  // QDLDL_Lsolve: for i: val = x[i]; for j in col i: x[Li[j]] -= Lx[j] * val
     int i = 0, cend = QP_LDG(pl.Lp + 1);
     double val = WBP(0);
+    double nx[8];
+    int nr[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) { nx[u] = (u < nnzL) ? W(pl.o_Lx, u) : 0.0; nr[u] = (u < nnzL) ? QP_LDG(pl.Li + u) : 0; }
     for (int j0 = 0; j0 < nnzL; j0 += 8) {
       double lx[8];
+      int lr[8];
 #pragma unroll
-      for (int u = 0; u < 8; u++) lx[u] = (j0 + u < nnzL) ? W(pl.o_Lx, j0 + u) : 0.0;
+      for (int u = 0; u < 8; u++) { lx[u] = nx[u]; lr[u] = nr[u]; }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {  // next batch in flight while this one is consumed
+        const int j = j0 + 8 + u;
+        nx[u] = (j < nnzL) ? W(pl.o_Lx, j) : 0.0;
+        nr[u] = (j < nnzL) ? QP_LDG(pl.Li + j) : 0;
+      }
 #pragma unroll
       for (int u = 0; u < 8; u++) {
         const int j = j0 + u;
         if (j < nnzL) {
           while (j >= cend) { i++; cend = QP_LDG(pl.Lp + i + 1); val = WBP(i); }
-          const int r = QP_LDG(pl.Li + j);
-          WBP(r) = WBP(r) - lx[u] * val;
+          WBP(lr[u]) = WBP(lr[u]) - lx[u] * val;
         }
       }
     }
@@ -127,16 +137,27 @@ QP_HD void qp_kkt_solve(const QpPlanDev& pl, double* ws, size_t stride, int b, d
   {  // QDLDL_Ltsolve: for i = N-1..0: val = x[i]; for j in col i: val -= Lx[j] * x[Li[j]]; x[i] = val
     int t = 0, i = N - 1, cend = QP_LDG(pl.LtEnd);
     double val = WBP(N - 1);
+    double nx[8];
+    int nr[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) { nx[u] = (u < nnzL) ? W(pl.o_LxT, u) : 0.0; nr[u] = (u < nnzL) ? QP_LDG(pl.LtR + u) : 0; }
     for (int k0 = 0; k0 < nnzL; k0 += 8) {
       double lx[8];
+      int lr[8];
 #pragma unroll
-      for (int u = 0; u < 8; u++) lx[u] = (k0 + u < nnzL) ? W(pl.o_LxT, k0 + u) : 0.0;
+      for (int u = 0; u < 8; u++) { lx[u] = nx[u]; lr[u] = nr[u]; }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int k = k0 + 8 + u;
+        nx[u] = (k < nnzL) ? W(pl.o_LxT, k) : 0.0;
+        nr[u] = (k < nnzL) ? QP_LDG(pl.LtR + k) : 0;
+      }
 #pragma unroll
       for (int u = 0; u < 8; u++) {
         const int k = k0 + u;
         if (k < nnzL) {
           while (k >= cend) { WBP(i) = val; t++; i = N - 1 - t; val = WBP(i); cend = QP_LDG(pl.LtEnd + t); }
-          val -= lx[u] * WBP(QP_LDG(pl.LtR + k));
+          val -= lx[u] * WBP(lr[u]);
         }
       }
     }
