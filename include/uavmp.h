@@ -116,6 +116,13 @@ int uavmp_kino_set_params(uavmp_ctx* ctx, const uavmp_kino_params* p);
 int uavmp_map_set(uavmp_ctx* ctx, const int8_t* occ_inflate, int nx, int ny, int nz, const double origin[3],
                   const double map_size[3], double resolution, const float* cloud_xyz, int n_cloud);
 
+/* the same, with GridMap::cloudCallback's inflation (src/planner/plan_env/src/grid_map.cpp:733-785: every point stamps its
+ * (2s+1) x (2s+1) x 3 voxel neighbourhood, s = ceil(obstacles_inflation / resolution)) done on the device: only the cloud
+ * crosses PCIe.  uavmp_map_get_occupancy returns the resulting occupancy_buffer_inflate_ (nx*ny*nz bytes). */
+int uavmp_map_set_from_cloud(uavmp_ctx* ctx, const float* cloud_xyz, int n_cloud, int nx, int ny, int nz, const double origin[3],
+                             const double map_size[3], double resolution, double obstacles_inflation);
+int uavmp_map_get_occupancy(uavmp_ctx* ctx, int8_t* occ_inflate, long long cap);
+
 /* ---- hot path (a): batched KinoAstar::search -------------------------------------------------------- */
 /* start_pt/start_vel/end_pt/end_vel: B x 3 f64.  status: 1|2 per query.  use_node_num: KinoAstar::use_node_num_
  * at return.  path_offsets: B+1 prefix sums of path point counts (the points search() push_back's into `path`).
@@ -152,6 +159,12 @@ int uavmp_plan_batch(uavmp_ctx* ctx, int B, const double* start_pt, const double
 int uavmp_plan_batch_dev(uavmp_ctx* ctx, int B, const double* d_start_pt, const double* d_start_vel,
                          const double* d_end_pt, const double* d_end_vel, int order, int S, double seg_time,
                          const uavmp_osqp_settings* settings, int* d_search_status, int* d_qp_solved, double* d_coef);
+
+/* ---- consumer of the coefficients: PolyTraj::evaluatePos / Vel / Acc (traj_utils/poly_traj.hpp:74-168), batched ------- */
+/* coef: B x 3 x S x (order+1) (axis-major per trajectory == uavmp_plan_batch's layout); times: B x S segment durations;
+ * t: n_t sample times shared by all trajectories; deriv 0 position, 1 velocity, 2 acceleration; out: B x n_t x 3. */
+int uavmp_polytraj_eval_batch(uavmp_ctx* ctx, int B, int order, int S, const double* coef, const double* times, int n_t,
+                              const double* t, int deriv, double* out);
 
 int uavmp_get_timings(uavmp_ctx* ctx, uavmp_timings* out);
 /* optional in-kernel profile of the search: SM cycles per phase (0 pop, 1 shot/path, 2 primitive evaluation, 3 dedup +

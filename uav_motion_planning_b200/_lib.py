@@ -55,7 +55,7 @@ SYMBOLS = [
     "uavmp_kino_set_trace", "uavmp_kino_get_trace", "uavmp_kino_get_counters", "uavmp_minctrl_solve_batch",
     "uavmp_plan_batch", "uavmp_plan_batch_dev", "uavmp_get_timings", "uavmp_mapgen_params_default",
     "uavmp_mapgen_cloud", "uavmp_grid_inflate_host", "uavmp_fpmath_eval", "uavmp_kino_set_profile",
-    "uavmp_kino_get_profile",
+    "uavmp_kino_get_profile", "uavmp_map_set_from_cloud", "uavmp_map_get_occupancy", "uavmp_polytraj_eval_batch",
 ]
 
 _lib = None
@@ -104,6 +104,9 @@ def load():
     lib.uavmp_grid_inflate_host.argtypes = [vp, C.c_int, vp, vp, C.c_double, C.c_double, vp, C.c_int, C.c_int,
                                             C.c_int]
     lib.uavmp_fpmath_eval.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_longlong]
+    lib.uavmp_map_set_from_cloud.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_double, C.c_double]
+    lib.uavmp_map_get_occupancy.argtypes = [vp, vp, C.c_longlong]
+    lib.uavmp_polytraj_eval_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp]
     lib.uavmp_kino_set_profile.argtypes = [vp, C.c_int]
     lib.uavmp_kino_get_profile.argtypes = [vp, vp, vp, C.c_int, ip]
     _lib = lib

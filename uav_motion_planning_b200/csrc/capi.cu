@@ -28,6 +28,17 @@ int ensure_bytes(uavmp_ctx* ctx, void** p, size_t* have, size_t want) {
   return UAVMP_OK;
 }
 
+// d_occ / d_cloud are in place: record the geometry and build the derived structures (flag grid, cell list, tensor map)
+int uavmp_map_commit(uavmp_ctx* ctx, int nx, int ny, int nz, const double origin[3], const double map_size[3], double resolution,
+                     int n_cloud) {
+  ctx->nx = nx; ctx->ny = ny; ctx->nz = nz; ctx->n_cloud = n_cloud; ctx->resolution = resolution;
+  for (int i = 0; i < 3; i++) { ctx->origin[i] = origin[i]; ctx->map_size[i] = map_size[i]; }
+  ctx->have_map = true;
+  ctx->flags_dirty = true;
+  if (ctx->params_dirty) { int r = kino_upload_params(ctx); if (r) return r; }
+  return kino_build_map(ctx);
+}
+
 extern "C" {
 
 const char* uavmp_version(void) { return "uavmp-b200 0.1 (sm_100a)"; }
@@ -123,12 +134,7 @@ int uavmp_map_set(uavmp_ctx* ctx, const int8_t* occ, int nx, int ny, int nz, con
     UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_cloud, (size_t)n_cloud * 3 * sizeof(float)));
     UAVMP_CUDA(ctx, cudaMemcpyAsync(ctx->d_cloud, cloud_xyz, (size_t)n_cloud * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   }
-  ctx->nx = nx; ctx->ny = ny; ctx->nz = nz; ctx->n_cloud = n_cloud; ctx->resolution = resolution;
-  for (int i = 0; i < 3; i++) { ctx->origin[i] = origin[i]; ctx->map_size[i] = map_size[i]; }
-  ctx->have_map = true;
-  ctx->flags_dirty = true;
-  if (ctx->params_dirty) { int r = kino_upload_params(ctx); if (r) return r; }
-  return kino_build_map(ctx);
+  return uavmp_map_commit(ctx, nx, ny, nz, origin, map_size, resolution, n_cloud);
 }
 
 static int prepare_search(uavmp_ctx* ctx, int B) {

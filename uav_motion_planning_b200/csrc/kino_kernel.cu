@@ -271,6 +271,13 @@ __device__ void heap_pop_serial(SearchSmem& s, HeapSlot* H, HashSlot* table, int
   int second = 0;
   while (second < (n - 1) / 2) {
     second = 2 * (second + 1);
+    {  // the next hole is slot second or second-1: their child pairs are the two adjacent 32 B sectors at H[2*second]
+      const int g = 2 * second;
+      if (g >= HTOP && g + 3 <= n) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(H + g));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(H + g + 2));
+      }
+    }
     HeapSlot r = hload(s, H, second + 1), l = hload(s, H, second);  // right child = slot `second`, left = second-1
     if (r.f > l.f) { second--; r = l; }
     hstore(s, H, hole + 1, r);
@@ -712,6 +719,30 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
 
       // ---- A0. separable tables: every checkpoint / end-state coordinate is (c + t v) + h u per axis, and u comes
       // from a tensor lattice, so there are only K * 3 * na distinct coordinates (StateTransit, :651-670) -----------
+      if (tid == KT - 1) {
+        // the flags box is requested first, from a conservative extent (all checkpoints, feasible or not: x is monotone in
+        // u, so the extremes sit at the two end values of the lattice), so that the TMA runs under the table computation
+        bool fits = use_tma != 0;
+        for (int ax = 0; ax < 3; ax++) {
+          const double org = ax == 0 ? M.ox : (ax == 1 ? M.oy : M.oz);
+          int lo = INT_MAX, hi = INT_MIN;
+          for (int i = 0; i < K; i++) {
+            const double b = s.cp[ax] + P.tk[i] * s.cv[ax];
+            const int i0 = (int)floor(((b + P.hk[i] * P.ua[0]) - org) * M.inv_res);
+            const int i1 = (int)floor(((b + P.hk[i] * P.ua[na - 1]) - org) * M.inv_res);
+            lo = min(lo, min(i0, i1)); hi = max(hi, max(i0, i1));
+          }
+          if (ax == 2) lo &= ~15;  // measured: UTMALDG faults unless inner coordinate * element size is 16 B aligned
+          if (hi - lo + 1 > (ax == 2 ? TBZ : TB)) fits = false;
+          s.to[ax] = lo;
+        }
+        s.tile_ok = fits ? 1 : 0;
+        if (fits) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_expect_tx(&s.mbar, TB * TB * TBZ);
+          tma_load_3d(s.a.tile, &tmap, s.to[2], s.to[1], s.to[0], &s.mbar);
+        }
+      }
       for (int e = tid; e < (K + 1) * 3 * na; e += KT) {
         const int i = e / (3 * na), ax = (e / na) % 3, a = e % na;
         const double u = P.ua[a];
@@ -746,34 +777,21 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
       }
       __syncthreads();
       if (warp == 0) {
-        // lanes 0..26 hold (axis, a); butterfly min/max inside each 9-lane... simpler: lane < 3 reduces one axis from smem
-        bool any = true, fits = true;
-        int lo = INT_MAX, hi = INT_MIN;
-        double xl = 1e300, xh = -1e300;
+        // any feasible coordinate per axis? + the position extent of the feasible part (for the cloud staging region)
+        bool any = true;
         if (lane < 3) {
           const int ax = lane;
+          int lo = INT_MAX, hi = INT_MIN;
+          double xl = 1e300, xh = -1e300;
           for (int a = 0; a < na; a++) {
             lo = min(lo, s.aimin[ax][a]); hi = max(hi, s.aimax[ax][a]);
             xl = fmin(xl, s.axmin[ax][a]); xh = fmax(xh, s.axmax[ax][a]);
           }
-          if (ax == 2) lo &= ~15;  // measured: UTMALDG faults unless inner coordinate * element size is 16 B aligned
           if (lo > hi) any = false;
-          else if (hi - lo + 1 > (ax == 2 ? TBZ : TB)) fits = false;
-          s.to[ax] = lo; s.xlo[ax] = xl; s.xhi[ax] = xh;
+          s.xlo[ax] = xl; s.xhi[ax] = xh;
         }
         any = __all_sync(FULL, any);
-        fits = __all_sync(FULL, fits);
-        if (lane == 0) {
-          s.any_ok = any ? 1 : 0;
-          s.tile_ok = (any && fits && use_tma) ? 1 : 0;
-        }
-        __syncwarp();
-        if (lane == 0 && any && fits && use_tma) {
-          // stage the flags box (inner dimension z): one TMA instruction, completion on the mbarrier
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_expect_tx(&s.mbar, TB * TB * TBZ);
-          tma_load_3d(s.a.tile, &tmap, s.to[2], s.to[1], s.to[0], &s.mbar);
-        }
+        if (lane == 0) s.any_ok = any ? 1 : 0;
       }
       __syncthreads();
       const bool tile_ok = s.tile_ok != 0;

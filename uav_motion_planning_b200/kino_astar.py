@@ -106,3 +106,17 @@ class KinoAstar:
         qc = qc[:B].copy()
         names = ["pop", "shot_path", "tables_tile_grid", "cloud_ellipsoid", "dedup_probe_heuristic", "node_write", "heap_commit", "setup", "cloud_staging", "n_staged", "n_unstaged", "sum_npts", "sum_flagged_prims", "commit_closure_io", "commit_slow_updates", "commit_deferred_writes"]
         return dict(phase_cycles=dict(zip(names, ph.tolist())), query_cycles=qc, query_phase=qphase, names=names, grid=grid.value)
+
+    # -- GridMap::cloudCallback on the device (grid_map.cpp:733-785): only the cloud is uploaded -----------------
+    def setGridMapFromCloud(self, world, obstacles_inflation=0.099):
+        self._world = world
+        cloud = np.ascontiguousarray(world.cloud, np.float32)
+        origin, msz = _lib.as_f64(world.origin), _lib.as_f64(world.map_size)
+        self.ctx.check(self.lib.uavmp_map_set_from_cloud(self.ctx.h, _lib.ptr(cloud), len(cloud), *world.dims, _lib.ptr(origin),
+                                                         _lib.ptr(msz), world.resolution, obstacles_inflation))
+
+    def occupancy(self):
+        nx, ny, nz = self._world.dims
+        occ = np.zeros(nx * ny * nz, np.int8)
+        self.ctx.check(self.lib.uavmp_map_get_occupancy(self.ctx.h, _lib.ptr(occ), occ.size))
+        return occ
