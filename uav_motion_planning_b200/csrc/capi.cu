@@ -2,6 +2,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -18,6 +19,8 @@ int qp_waypoints_from_paths(uavmp_ctx* ctx, int B, int S, double seg_time, const
 int qp_scatter_plan_outputs(uavmp_ctx* ctx, int B, int order, int S, const int* d_solved3, const double* d_coef3,
                             int* d_qp_solved, double* d_coef);
 void qp_free_plans(uavmp_ctx* ctx);
+int qp_launch_fused(uavmp_ctx* ctx, int order, int S, int B, double seg_time, const double* d_sv, const double* d_ev,
+                    const int* d_order, const uavmp_osqp_settings* st, double* d_coef, int* d_qp_solved, bool prepare_only);
 
 int ensure_bytes(uavmp_ctx* ctx, void** p, size_t* have, size_t want) {
   if (*have >= want) return UAVMP_OK;
@@ -76,7 +79,13 @@ int uavmp_ctx_create(uavmp_ctx** out, int device) {
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);
   ctx->sm_count = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return UAVMP_ECUDA; }
+  {
+    // the context's stream gets the highest priority so that the overlapped QP kernel (lowest priority, second stream) only
+    // takes SM space the persistent search CTAs have given up
+    int least = 0, greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, greatest) != cudaSuccess) { delete ctx; return UAVMP_ECUDA; }
+  }
   for (int i = 0; i < 8; i++) cudaEventCreate(&ctx->ev[i]);
   uavmp_kino_params_launch(&ctx->kp);
   memset(&ctx->tm, 0, sizeof(ctx->tm));
@@ -93,10 +102,11 @@ void uavmp_ctx_destroy(uavmp_ctx* ctx) {
                   ctx->d_pts, ctx->d_map, ctx->d_arena_mem, ctx->d_arenas, ctx->d_q, ctx->d_order, ctx->d_status,
                   ctx->d_use, ctx->d_npop, ctx->d_hash, ctx->d_npath, ctx->d_path_stage, ctx->d_trace, ctx->d_offsets,
                   ctx->d_path_packed, ctx->d_misc, ctx->d_counters, ctx->d_cub_tmp, ctx->d_qp_ws, ctx->d_qp_in,
-                  ctx->d_qp_out, ctx->d_qp_int, ctx->d_plan_out, ctx->d_plan_io, ctx->d_wp, ctx->d_phase, ctx->d_query_cycles, ctx->d_flags_pad, ctx->d_b3f};
+                  ctx->d_qp_out, ctx->d_qp_int, ctx->d_plan_out, ctx->d_plan_io, ctx->d_wp, ctx->d_phase, ctx->d_query_cycles, ctx->d_flags_pad, ctx->d_b3f, ctx->d_done_flags};
   for (void* p : ptrs) if (p) cudaFree(p);
   qp_free_plans(ctx);
   for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->fuse_ready) { cudaStreamSynchronize(ctx->stream2); cudaEventDestroy(ctx->ev_fuse[0]); cudaEventDestroy(ctx->ev_fuse[1]); cudaStreamDestroy(ctx->stream2); }
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -154,6 +164,7 @@ static int check_error_flag(uavmp_ctx* ctx) {
   if (flag & 1) return uavmp_fail(ctx, UAVMP_ECAP, "voxel index outside the 18-bit key range");
   if (flag & 2) return uavmp_fail(ctx, UAVMP_ECAP, "path has more than %d nodes", UAVMP_MAXPRIM);
   if (flag & 4) return uavmp_fail(ctx, UAVMP_ECAP, "path longer than path_cap=%d points", ctx->path_cap);
+  if (flag & 8) return uavmp_fail(ctx, UAVMP_ECUDA, "overlapped QP gave up waiting for a search to finish");
   return UAVMP_OK;
 }
 
@@ -258,6 +269,13 @@ int uavmp_kino_get_profile(uavmp_ctx* ctx, unsigned long long phase_cycles[16], 
   return UAVMP_OK;
 }
 
+int uavmp_debug_overlap(uavmp_ctx* ctx, unsigned long long out[4]) {
+  if (!ctx || !ctx->dbg_ptr) return UAVMP_ESTATE;
+  cudaDeviceSynchronize();
+  cudaMemcpy(out, ctx->dbg_ptr, 32, cudaMemcpyDeviceToHost);
+  return UAVMP_OK;
+}
+
 int uavmp_get_timings(uavmp_ctx* ctx, uavmp_timings* out) {
   if (!ctx || !out) return UAVMP_EINVAL;
   if (ctx->tm_pending_dev) {
@@ -338,6 +356,47 @@ int uavmp_plan_batch_dev(uavmp_ctx* ctx, int B, const double* d_sp, const double
   int r = prepare_search(ctx, B);
   if (r) return r;
   cudaStream_t st = ctx->stream;
+  const bool overlap = !getenv("UAVMP_NO_OVERLAP");
+  if (overlap) {
+    // overlapped pipeline: search on the context's stream, the QP kernel on a second low-priority stream; every QP thread
+    // waits for its own query's completion flag, so the QP runs on the SMs the search's long tail leaves idle
+    if (!ctx->fuse_ready) {
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);
+      UAVMP_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, lo));
+      cudaEventCreateWithFlags(&ctx->ev_fuse[0], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&ctx->ev_fuse[1], cudaEventDisableTiming);
+      ctx->fuse_ready = true;
+    }
+    if (ctx->done_flags_cap < B) {
+      if (ctx->d_done_flags) cudaFree(ctx->d_done_flags);
+      ctx->d_done_flags = nullptr;
+      UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_done_flags, (size_t)B * sizeof(int)));
+      ctx->done_flags_cap = B;
+    }
+    r = qp_launch_fused(ctx, order, S, B, seg_time, d_sv, d_ev, nullptr, settings, d_coef, d_qp_solved, /*prepare_only=*/true);
+    if (r) return r;
+    cudaEventRecord(ctx->ev[5], st);
+    UAVMP_CUDA(ctx, cudaMemsetAsync(ctx->d_done_flags, 0, (size_t)B * sizeof(int), st));
+    // kino_launch_search records ev_fuse[0] right before the search kernel (after the flags are zero and the processing order
+    // is sorted): the QP stream waits for that event, NOT for the search kernel
+    ctx->fuse_flags = ctx->d_done_flags; ctx->fuse_qp_solved = d_qp_solved;
+    r = kino_launch_search(ctx, B, d_sp, d_sv, d_ep, d_ev, true);
+    ctx->fuse_flags = nullptr; ctx->fuse_qp_solved = nullptr;
+    if (r) return r;
+    cudaEventRecord(ctx->ev[6], st);
+    UAVMP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fuse[0], 0));
+    r = qp_launch_fused(ctx, order, S, B, seg_time, d_sv, d_ev, B > 1 ? ctx->d_order + B : nullptr, settings, d_coef, d_qp_solved, false);
+    if (r) return r;
+    cudaEventRecord(ctx->ev_fuse[1], ctx->stream2);
+    UAVMP_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_fuse[1], 0));  // everything after this call on `st` sees the QP's results
+    UAVMP_CUDA(ctx, cudaMemcpyAsync(d_search_status, ctx->d_status, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    cudaEventRecord(ctx->ev[7], st);
+    ctx->last_B = B;
+    ctx->tm_pending_dev = true;
+    ctx->tm.aux_launches = 1;  // k_dist_keys (+ cub's radix-sort kernels, library code)
+    return UAVMP_OK;
+  }
   cudaEventRecord(ctx->ev[5], st);
   r = kino_launch_search(ctx, B, d_sp, d_sv, d_ep, d_ev, true);
   if (r) return r;

@@ -1310,7 +1310,15 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
     }
     __syncthreads();
     if (tid < 8) atomicAdd(&bt.counters[tid], s.cnt[tid]);
+    if (bt.done_flag) {
+      // every thread's writes of this query (path points, status, n_path) become visible before the flag: the QP
+      // kernel running on the second stream picks the query up from here
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) { if (bt.qp_solved) bt.qp_solved[q] = (s.status == UAVMP_REACH_END) ? 1 : 0; __threadfence(); atomicExch(&bt.done_flag[q], 1); }
+    }
   }
+  if (bt.dbg && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); atomicMin(&bt.dbg[2], t); atomicMax(&bt.dbg[3], t); }
   PH_MARK(7);
   __syncthreads();
   if (prof && tid < 16) atomicAdd(&bt.phase_cycles[tid], s.ph[tid]);
@@ -1766,6 +1774,9 @@ int kino_launch_search(uavmp_ctx* ctx, int B, const double* d_sp, const double* 
   bt.pop_trace = ctx->d_trace; bt.pop_cap = ctx->pop_cap;
   bt.error_flag = ctx->d_misc; bt.next_query = ctx->d_misc + 1; bt.counters = ctx->d_counters;
   bt.phase_cycles = nullptr; bt.query_cycles = nullptr; bt.query_phase = nullptr;
+  bt.done_flag = ctx->fuse_flags; bt.qp_solved = ctx->fuse_qp_solved;
+  bt.dbg = (ctx->fuse_flags && ctx->dbg_ptr) ? ctx->dbg_ptr : nullptr;
+  if (bt.dbg) { unsigned long long init2[2] = {~0ull, 0ull}; cudaMemcpyAsync(ctx->dbg_ptr + 2, init2, sizeof(init2), cudaMemcpyHostToDevice, st); }
   if (ctx->profile_phases) {
     if (!ctx->d_phase) UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_phase, 16 * sizeof(unsigned long long)));
     if (ctx->query_cycles_cap < B) {
@@ -1788,6 +1799,7 @@ int kino_launch_search(uavmp_ctx* ctx, int B, const double* d_sp, const double* 
   cudaFuncSetAttribute(kino_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SearchSmem));
   CUtensorMap tm;
   memcpy(&tm, ctx->tmap_bytes, sizeof(tm));
+  if (ctx->fuse_flags) cudaEventRecord(ctx->ev_fuse[0], st);  // flags zeroed, order sorted: the overlapped QP may start polling
   kino_search_kernel<<<grid, KT, sizeof(SearchSmem), st>>>(ctx->d_kparams, lat, ctx->d_map, ctx->d_arenas, bt, bits, tm,
                                                           (ctx->have_tmap && !getenv("UAVMP_NO_TMA")) ? 1 : 0);
   UAVMP_CUDA(ctx, cudaGetLastError());

@@ -19,6 +19,7 @@
 // (~1e-9 relative), not bit for bit; the parity gate is 1e-5 relative plus identical status / iteration counts.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -43,6 +44,60 @@ __global__ void __launch_bounds__(QP_TPB) qp_solve_kernel(QpPlanDev pl, QpIo io,
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= io.B) return;
   qp_solve_one(pl, io, S, ws, b, use_smem ? qp_sv : nullptr);
+}
+
+// ---- overlapped pipeline: the QP of a query starts as soon as ITS search has finished ---------------------------------------
+// Launched on a second, low-priority stream right after the search kernel.  Its CTAs become resident as the persistent search
+// CTAs retire (the search kernel's tail is a handful of very long queries on otherwise idle SMs), wait for their query's
+// completion flag, build the waypoints themselves and write straight into the caller's coefficient array.
+struct QpFuse {
+  int B, path_cap, Sg, n;
+  double seg_time;
+  const int* done_flag; const int* order; const int* search_status; const int* n_path; const double* path_stage;
+  const double* sv; const double* ev;
+  double* pos; double* bv; double* ba; double* bj; double* T;
+  double* coef_out; int* qp_solved; int* error_flag;
+  unsigned long long* dbg;
+};
+
+__global__ void __launch_bounds__(QP_TPB) qp_solve_fused_kernel(QpPlanDev pl, QpIo io, uavmp_osqp_settings S, double* ws, int use_smem,
+                                                                QpFuse fu) {
+  extern __shared__ __align__(16) double qp_sv[];
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= io.B) return;
+  if (fu.dbg && threadIdx.x == 0) {  // diagnostics: when did this CTA become resident / finish (globaltimer, ns)
+    unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    atomicMin(&fu.dbg[0], t); atomicMax(&fu.dbg[1], t);
+  }
+  const int ax = b / fu.B, w = b % fu.B;
+  const int q = fu.order ? fu.order[w] : w;   // neighbouring lanes = queries dispatched at about the same time
+  {
+    const volatile int* flag = fu.done_flag + q;
+    long long spins = 0;
+    while (*flag == 0) {
+      __nanosleep(2000);
+      if (++spins > 4000000ll) { atomicOr(fu.error_flag, 8); return; }  // ~8 s: the search never finished; do not hang the GPU
+    }
+    __threadfence();
+  }
+  const int np = fu.n_path[q];
+  const bool ok = (fu.search_status[q] == UAVMP_REACH_END) && np >= 1;
+  double* out = fu.coef_out + ((size_t)q * 3 + ax) * fu.n;
+  if (!ok) {
+    for (int j = 0; j < fu.n; j++) out[j] = 0.0;
+    return;
+  }
+  const int Sg = fu.Sg;
+  const double* path = fu.path_stage + (size_t)q * fu.path_cap * 3;
+  for (int k = 0; k <= Sg; k++) fu.pos[(size_t)b * (Sg + 1) + k] = path[3 * (((long long)k * (np - 1)) / Sg) + ax];
+  fu.bv[(size_t)b * 2] = fu.sv[3 * q + ax]; fu.bv[(size_t)b * 2 + 1] = fu.ev[3 * q + ax];
+  fu.ba[(size_t)b * 2] = 0.0; fu.ba[(size_t)b * 2 + 1] = 0.0;
+  fu.bj[(size_t)b * 2] = 0.0; fu.bj[(size_t)b * 2 + 1] = 0.0;
+  for (int sgm = 0; sgm < Sg; sgm++) fu.T[(size_t)b * Sg + sgm] = fu.seg_time;
+  qp_solve_one(pl, io, S, ws, b, use_smem ? qp_sv : nullptr);
+  const double* mine = io.coef + (size_t)b * fu.n;
+  for (int j = 0; j < fu.n; j++) out[j] = mine[j];
+  if (!io.solved[b]) atomicAnd(fu.qp_solved + q, 0);
 }
 
 // ---- pipeline glue: waypoints from the searched paths, outputs back to per-plan layout --------------------------------------
@@ -146,6 +201,50 @@ int qp_solve_batch_dev(uavmp_ctx* ctx, int order, int S, int B, const double* d_
   if (!use_smem) smem = 0;
   if (smem > 48 * 1024) cudaFuncSetAttribute(qp_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   qp_solve_kernel<<<(B + threads - 1) / threads, threads, smem, ctx->stream>>>(p->dev, io, *st, (double*)ctx->d_qp_ws, use_smem);
+  UAVMP_CUDA(ctx, cudaGetLastError());
+  ctx->tm.qp_launches = 1;
+  return UAVMP_OK;
+}
+
+// issue the overlapped QP of a plan batch on ctx->stream2 (the caller has already launched the search on ctx->stream)
+int qp_launch_fused(uavmp_ctx* ctx, int order, int S, int B, double seg_time, const double* d_sv, const double* d_ev,
+                    const int* d_order, const uavmp_osqp_settings* st, double* d_coef, int* d_qp_solved, bool prepare_only) {
+  QpPlan* p = get_plan(ctx, order, S);
+  if (!p) return uavmp_fail(ctx, UAVMP_ECUDA, "cannot build the QP plan");
+  const int nB = 3 * B, n = (order + 1) * S;
+  const int stride = (nB + 31) & ~31;
+  int r = ensure_bytes(ctx, &ctx->d_qp_ws, &ctx->qp_ws_bytes, (size_t)p->dev.ws_doubles * stride * sizeof(double)); if (r) return r;
+  r = ensure_bytes(ctx, (void**)&ctx->d_wp, &ctx->wp_bytes, (size_t)nB * ((S + 1) + 6 + S) * sizeof(double)); if (r) return r;
+  r = ensure_bytes(ctx, (void**)&ctx->d_qp_out, &ctx->qp_out_bytes, (size_t)nB * n * sizeof(double)); if (r) return r;
+  r = ensure_bytes(ctx, (void**)&ctx->d_qp_int, &ctx->qp_int_bytes, (size_t)nB * 3 * sizeof(int)); if (r) return r;
+  if (prepare_only) return UAVMP_OK;  // allocations (which synchronise the device) are done before the search is launched
+  double* pos = ctx->d_wp; double* bv = pos + (size_t)nB * (S + 1); double* ba = bv + (size_t)nB * 2; double* bj = ba + (size_t)nB * 2;
+  double* T = bj + (size_t)nB * 2;
+  QpIo io;
+  io.pos = pos; io.bv = bv; io.ba = ba; io.bj = bj; io.T = T;
+  io.coef = ctx->d_qp_out; io.solved = ctx->d_qp_int; io.status = ctx->d_qp_int + nB; io.iters = ctx->d_qp_int + 2 * nB;
+  io.B = nB; io.stride = stride;
+  QpFuse fu;
+  fu.B = B; fu.path_cap = ctx->path_cap; fu.Sg = S; fu.n = n; fu.seg_time = seg_time;
+  fu.done_flag = ctx->d_done_flags; fu.order = d_order; fu.search_status = ctx->d_status; fu.n_path = ctx->d_npath;
+  fu.path_stage = ctx->d_path_stage; fu.sv = d_sv; fu.ev = d_ev;
+  fu.pos = pos; fu.bv = bv; fu.ba = ba; fu.bj = bj; fu.T = T;
+  fu.coef_out = d_coef; fu.qp_solved = d_qp_solved; fu.error_flag = ctx->d_misc;
+  fu.dbg = nullptr;
+  if (getenv("UAVMP_DBG_OVERLAP")) {
+    static unsigned long long* d_dbg = nullptr;
+    if (!d_dbg) cudaMalloc(&d_dbg, 64);
+    unsigned long long init[4] = {~0ull, 0ull, 0, 0};
+    cudaMemcpyAsync(d_dbg, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream2);
+    fu.dbg = d_dbg;
+    ctx->dbg_ptr = d_dbg;
+  }
+  const int threads = QP_TPB;
+  size_t smem = (size_t)2 * p->dev.N * sizeof(double) * threads;
+  const int use_smem = smem <= 200 * 1024 ? 1 : 0;
+  if (!use_smem) smem = 0;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(qp_solve_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  qp_solve_fused_kernel<<<(nB + threads - 1) / threads, threads, smem, ctx->stream2>>>(p->dev, io, *st, (double*)ctx->d_qp_ws, use_smem, fu);
   UAVMP_CUDA(ctx, cudaGetLastError());
   ctx->tm.qp_launches = 1;
   return UAVMP_OK;

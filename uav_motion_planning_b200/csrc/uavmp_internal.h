@@ -102,6 +102,9 @@ struct KinoBatchDev {
   unsigned long long* phase_cycles;  // optional profiling: 8 words, SM cycles per phase summed over CTAs
   long long* query_cycles;           // optional profiling: B words, SM cycles each query occupied its CTA
   unsigned long long* query_phase;   // optional profiling: B x 16 words, the phase cycles of every query
+  int* done_flag;                    // optional: done_flag[q] = 1 once query q's outputs are visible (overlapped QP)
+  unsigned long long* dbg;           // optional diagnostics (globaltimer stamps)
+  int* qp_solved;                    // optional: initialised to "search reached the goal" for the overlapped QP to AND into
 };
 
 // ---- host-side context -----------------------------------------------------------------------------
@@ -157,6 +160,11 @@ struct uavmp_ctx {
   int last_B = 0;
   void* d_cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
   bool profile_phases = false;
+  // overlapped pipeline: second (low-priority) stream for the QP kernel, per-query completion flags
+  cudaStream_t stream2 = nullptr; cudaEvent_t ev_fuse[2]; bool fuse_ready = false;
+  int* d_done_flags = nullptr; int done_flags_cap = 0;
+  unsigned long long* dbg_ptr = nullptr;
+  int* fuse_flags = nullptr; int* fuse_qp_solved = nullptr;  // set only while a fused launch is being issued
   unsigned long long* d_phase = nullptr; long long* d_query_cycles = nullptr; int query_cycles_cap = 0;
   int last_grid = 0;
 
