@@ -814,7 +814,14 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
               if (P.ctype == 1 && (fl & 1u)) { ok = false; break; }
               if (fl & 4u) need |= 1u << i;
             }
-            if (ok) st = ST_FEASIBLE;
+            if (ok) {
+              st = ST_FEASIBLE;
+              // the successor classification will probe this voxel's hash slot: start pulling its sector towards L2 now,
+              // under the cloud tests (a primitive the ellipsoid test rejects costs one wasted prefetch)
+              bool kok;
+              const unsigned long long k = pack_key(s.EI[0][a], s.EI[1][b], s.EI[2][c], kok);
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(table + hash_key(k, table_bits)));
+            }
           }
           s.state[p] = st;
           s.a.need[p] = (st == ST_FEASIBLE) ? (uint16_t)need : (uint16_t)0;
@@ -1264,6 +1271,7 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
           if (prof && lane == 0) s.ph[13] += (unsigned long long)(clock64() - t0);
         }
         if (lane == 0) {
+          if (len > 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes + s.htop[1].id));  // the next pop's node record
           s.heap_len = len;
           s.use_num += n_new;
           if (s.last_ev >= 0) s.opt_time = s.b.topt[s.list2[s.last_ev]];
