@@ -42,3 +42,39 @@ extern "C" int host_qp_kkt_pattern(int order, int S, int* N_out, int* nnz_out, l
   delete H;
   return 0;
 }
+
+// ---- the warp-per-problem body (qp_body_warp.h) as "one lane": forward and reversed parallel-loop order ------------------
+#define QPW_HOST 1
+namespace fwd {
+#include "../../uav_motion_planning_b200/csrc/qp_body_warp.h"
+}
+#define QPW_REVERSED 1
+namespace rev {
+#include "../../uav_motion_planning_b200/csrc/qp_body_warp.h"
+}
+
+static int host_qp_solve_warp_impl(int reversed, int order, int S, int B, const double* pos, const double* bv, const double* ba,
+                                   const double* bj, const double* T, const uavmp_osqp_settings* st, double* coef, int* solved,
+                                   int* status, int* iters) {
+  QpPlanHost* H = qp_plan_build(order, S);
+  std::vector<int> ints;
+  std::vector<double> dbls;
+  QpPlanOffsets off;
+  QpPlanDev D;
+  qp_plan_pack(*H, ints, dbls, off);
+  qp_plan_bind(*H, off, ints.data(), dbls.data(), D);
+  QpIo io;
+  io.pos = pos; io.bv = bv; io.ba = ba; io.bj = bj ? bj : ba; io.T = T;
+  io.coef = coef; io.solved = solved; io.status = status; io.iters = iters; io.B = B; io.stride = 0;
+  for (int b = 0; b < B; b++) {
+    std::vector<double> w((size_t)D.ws_warp, fpm::from_bits(0x7ff8000000000000ull));  // poisoned
+    if (reversed) rev::qp_warp_solve_one(D, io, *st, w.data(), b); else fwd::qp_warp_solve_one(D, io, *st, w.data(), b);
+  }
+  delete H;
+  return 0;
+}
+extern "C" int host_qp_solve_warp(int reversed, int order, int S, int B, const double* pos, const double* bv, const double* ba,
+                                  const double* bj, const double* T, const uavmp_osqp_settings* st, double* coef, int* solved,
+                                  int* status, int* iters) {
+  return host_qp_solve_warp_impl(reversed, order, S, B, pos, bv, ba, bj, T, st, coef, solved, status, iters);
+}

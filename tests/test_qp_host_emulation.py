@@ -74,3 +74,36 @@ def test_max_iter_status():
                                                   settings=oracle_lib.osqp_settings(max_iter=10))
         assert (ok, info["status_val"], info["iter"]) == (0, got["status"][0], 10)
         assert np.abs(coef - got["coef"][0]).max() / np.abs(coef).max() < RTOL
+
+
+@pytest.mark.parametrize("case", GOLD, ids=lambda c: f"warp_order{c['order']}_S{c['S']}")
+def test_warp_body_against_golden_in_both_loop_orders(case):
+    """qp_body_warp.h (one warp per problem on the GPU) run as a single lane, with every parallel loop executed forwards and then
+    BACKWARDS: both must reproduce the reference OSQP bit for bit, so no parallel loop depends on its iteration order."""
+    pr = case["problems"]
+    arr = lambda k: np.array([p[k] for p in pr])
+    for rev in (False, True):
+        got = host_qp.solve_batch_warp(case["order"], arr("pos"), arr("bound_vel"), arr("bound_acc"), arr("T"), arr("bound_jerk"),
+                                       settings=default_settings(**case["settings"]), reversed_loops=rev)
+        for b, p in enumerate(pr):
+            assert (got["solved"][b], got["status"][b], got["iters"][b]) == (p["solved"], p["status_val"], p["iter"])
+            assert np.array_equal(np.array(p["coef"]), got["coef"][b])
+
+
+def test_warp_body_equals_thread_body_on_random_problems():
+    rng = np.random.default_rng(77)
+    for order, S in [(5, 1), (5, 6), (7, 2), (7, 12)]:
+        B = 5
+        pos = np.cumsum(rng.normal(size=(B, S + 1)), axis=1)
+        bv, ba, bj = rng.normal(size=(B, 2)) * 0.5, rng.normal(size=(B, 2)) * 0.2, np.zeros((B, 2))
+        T = rng.uniform(0.5, 2.0, size=(B, S))
+        a = host_qp.solve_batch(order, pos, bv, ba, T, bj)
+        for rev in (False, True):
+            w = host_qp.solve_batch_warp(order, pos, bv, ba, T, bj, reversed_loops=rev)
+            assert np.array_equal(a["coef"], w["coef"]) and np.array_equal(a["iters"], w["iters"]) and np.array_equal(a["status"], w["status"])
+    # max_iter below the first check and the fallback ordering (S = 41 is not tabulated)
+    pos = np.cumsum(rng.normal(size=(2, 42)), axis=1)
+    z = np.zeros((2, 2))
+    a = host_qp.solve_batch(5, pos, z, z, np.ones((2, 41)), settings=default_settings(max_iter=10))
+    w = host_qp.solve_batch_warp(5, pos, z, z, np.ones((2, 41)), settings=default_settings(max_iter=10), reversed_loops=True)
+    assert np.array_equal(a["coef"], w["coef"]) and np.array_equal(a["status"], w["status"])

@@ -25,6 +25,7 @@
 
 #include "fpmath.h"
 #include "qp_body.h"
+#include "qp_body_warp.h"
 #include "qp_plan.h"
 #include "uavmp_internal.h"
 
@@ -44,6 +45,15 @@ __global__ void __launch_bounds__(QP_TPB) qp_solve_kernel(QpPlanDev pl, QpIo io,
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= io.B) return;
   qp_solve_one(pl, io, S, ws, b, use_smem ? qp_sv : nullptr);
+}
+
+// ---- K2w: one warp per problem, workspace in shared memory (qp_body_warp.h) ------------------------------------------------------
+__global__ void qp_solve_warp_kernel(QpPlanDev pl, QpIo io, uavmp_osqp_settings S, int warps_per_cta) {
+  extern __shared__ __align__(16) double qpw_sm[];
+  const int warp = threadIdx.x >> 5;
+  const int b = blockIdx.x * warps_per_cta + warp;
+  if (b >= io.B) return;  // whole warps leave together
+  qp_warp_solve_one(pl, io, S, qpw_sm + (size_t)warp * pl.ws_warp, b);
 }
 
 // ---- overlapped pipeline: the QP of a query starts as soon as ITS search has finished ---------------------------------------
@@ -98,6 +108,63 @@ __global__ void __launch_bounds__(QP_TPB) qp_solve_fused_kernel(QpPlanDev pl, Qp
   const double* mine = io.coef + (size_t)b * fu.n;
   for (int j = 0; j < fu.n; j++) out[j] = mine[j];
   if (!io.solved[b]) atomicAnd(fu.qp_solved + q, 0);
+}
+
+__global__ void qp_solve_warp_fused_kernel(QpPlanDev pl, QpIo io, uavmp_osqp_settings S, int warps_per_cta, QpFuse fu) {
+  extern __shared__ __align__(16) double qpw_sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * warps_per_cta + warp;
+  if (b >= io.B) return;
+  if (fu.dbg && lane == 0) {
+    unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    atomicMin(&fu.dbg[0], t); atomicMax(&fu.dbg[1], t);
+  }
+  const int ax = b / fu.B, wq = b % fu.B;
+  const int q = fu.order ? fu.order[wq] : wq;
+  int gave_up = 0;
+  if (lane == 0) {
+    const volatile int* flag = fu.done_flag + q;
+    long long spins = 0;
+    while (*flag == 0) {
+      __nanosleep(1000);
+      if (++spins > 8000000ll) { atomicOr(fu.error_flag, 8); gave_up = 1; break; }  // ~8 s: never hang the GPU
+    }
+    __threadfence();
+  }
+  gave_up = __shfl_sync(0xffffffffu, gave_up, 0);
+  if (gave_up) return;
+  const int np = fu.n_path[q];
+  const bool ok = (fu.search_status[q] == UAVMP_REACH_END) && np >= 1;
+  double* out = fu.coef_out + ((size_t)q * 3 + ax) * fu.n;
+  if (!ok) {
+    for (int j = lane; j < fu.n; j += 32) out[j] = 0.0;
+    return;
+  }
+  const int Sg = fu.Sg;
+  const double* path = fu.path_stage + (size_t)q * fu.path_cap * 3;
+  for (int k = lane; k <= Sg; k += 32) fu.pos[(size_t)b * (Sg + 1) + k] = path[3 * (((long long)k * (np - 1)) / Sg) + ax];
+  for (int sgm = lane; sgm < Sg; sgm += 32) fu.T[(size_t)b * Sg + sgm] = fu.seg_time;
+  if (lane == 0) {
+    fu.bv[(size_t)b * 2] = fu.sv[3 * q + ax]; fu.bv[(size_t)b * 2 + 1] = fu.ev[3 * q + ax];
+    fu.ba[(size_t)b * 2] = 0.0; fu.ba[(size_t)b * 2 + 1] = 0.0;
+    fu.bj[(size_t)b * 2] = 0.0; fu.bj[(size_t)b * 2 + 1] = 0.0;
+  }
+  __syncwarp();
+  qp_warp_solve_one(pl, io, S, qpw_sm + (size_t)warp * pl.ws_warp, b);
+  const double* mine = io.coef + (size_t)b * fu.n;
+  for (int j = lane; j < fu.n; j += 32) out[j] = mine[j];
+  if (lane == 0 && !io.solved[b]) atomicAnd(fu.qp_solved + q, 0);
+}
+
+// warps per CTA of the warp-per-problem kernels: as many problems as ~100 KB of shared memory hold (2 CTAs / SM); 0 = does not fit
+static int qpw_warps_per_cta(const QpPlanDev& pl) {
+  if (getenv("UAVMP_QP_THREAD")) return 0;
+  const size_t per = (size_t)pl.ws_warp * sizeof(double);
+  if (per > 200 * 1024) return 0;
+  int w = (int)((100 * 1024) / per);
+  if (w < 1) w = 1;
+  if (w > 8) w = 8;
+  return w;
 }
 
 // ---- pipeline glue: waypoints from the searched paths, outputs back to per-plan layout --------------------------------------
@@ -194,6 +261,15 @@ int qp_solve_batch_dev(uavmp_ctx* ctx, int order, int S, int B, const double* d_
   QpIo io;
   io.pos = d_pos; io.bv = d_bv; io.ba = d_ba; io.bj = d_bj ? d_bj : d_ba; io.T = d_T;
   io.coef = d_coef; io.solved = d_solved; io.status = d_status; io.iters = d_iters; io.B = B; io.stride = stride;
+  if (const int wpc = qpw_warps_per_cta(p->dev)) {
+    // one warp per problem, everything in shared memory: no global workspace at all
+    const size_t smem = (size_t)wpc * p->dev.ws_warp * sizeof(double);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(qp_solve_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    qp_solve_warp_kernel<<<(B + wpc - 1) / wpc, 32 * wpc, smem, ctx->stream>>>(p->dev, io, *st, wpc);
+    UAVMP_CUDA(ctx, cudaGetLastError());
+    ctx->tm.qp_launches = 1;
+    return UAVMP_OK;
+  }
   const int threads = QP_TPB;
   // bp and xz in shared memory when they fit (2 N doubles per thread); otherwise everything stays in the workspace
   size_t smem = (size_t)2 * p->dev.N * sizeof(double) * threads;
@@ -238,6 +314,14 @@ int qp_launch_fused(uavmp_ctx* ctx, int order, int S, int B, double seg_time, co
     cudaMemcpyAsync(d_dbg, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream2);
     fu.dbg = d_dbg;
     ctx->dbg_ptr = d_dbg;
+  }
+  if (const int wpc = qpw_warps_per_cta(p->dev)) {
+    const size_t smem_w = (size_t)wpc * p->dev.ws_warp * sizeof(double);
+    if (smem_w > 48 * 1024) cudaFuncSetAttribute(qp_solve_warp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
+    qp_solve_warp_fused_kernel<<<(nB + wpc - 1) / wpc, 32 * wpc, smem_w, ctx->stream2>>>(p->dev, io, *st, wpc, fu);
+    UAVMP_CUDA(ctx, cudaGetLastError());
+    ctx->tm.qp_launches = 1;
+    return UAVMP_OK;
   }
   const int threads = QP_TPB;
   size_t smem = (size_t)2 * p->dev.N * sizeof(double) * threads;

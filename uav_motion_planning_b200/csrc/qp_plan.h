@@ -15,6 +15,9 @@ struct QpPlanHost {
   std::vector<int> Kp, Ki, Kkind, Kidx;                                 // permuted upper CSC of the KKT matrix
   std::vector<int> Lp, Li;                                              // pattern of L (strictly lower, CSC)
   std::vector<int> Rp, Rc, Rpos;                                        // per row k: reach columns and target slots
+  std::vector<int> Arp, Arj, Arx;                                       // CSR view of A: per row, column index and slot in Ax, by increasing column
+  std::vector<int> Psp, Psa, Psv;                                       // per element i of P*v: (slot in Px, index into v) in the CSC loop's order
+  std::vector<int> LevP, LevC; int nlev = 0;                            // L' solve: columns with entries grouped by elimination-tree level
   std::vector<int> Ltpos, LtR, LtEnd;                                   // L in the L' solve's consumption order: slot of L entry j, row index per slot, end slot per processed column
 };
 
@@ -27,13 +30,15 @@ struct QpPlanDev {
   const int *Ap, *Ai, *A_seg, *A_pow;
   const double *P_coef, *A_coef;
   const int *l_src, *perm, *Kp, *Ki, *Kkind, *Kidx, *Lp, *Li, *Rp, *Rc, *Rpos, *Ltpos, *LtR, *LtEnd;
+  const int *Arp, *Arj, *Arx, *Psp, *Psa, *Psv, *LevP, *LevC;
+  int nlev, ws_warp;  // ws_warp: doubles of the one-warp-per-problem workspace (everything except the LxT copy)
   // workspace layout (offsets in doubles)
   int o_Px, o_Ax, o_q, o_l, o_u, o_D, o_Dinv, o_E, o_Einv, o_rho, o_rhoinv, o_Lx, o_LxT, o_Dd, o_Ddinv, o_yw, o_x, o_xprev,
       o_dx, o_Pxv, o_Aty, o_z, o_zprev, o_y, o_dy, o_Axv, o_xz, o_bp, o_tn, o_tm, ws_doubles;
 };
 
 // flattening of a host plan into one int array + one double array (what is uploaded), and the view over it
-struct QpPlanOffsets { size_t Pp, Pi, P_seg, P_pow, Ap, Ai, A_seg, A_pow, l_src, perm, Kp, Ki, Kkind, Kidx, Lp, Li, Rp, Rc, Rpos, Ltpos, LtR, LtEnd, A_coef; };
+struct QpPlanOffsets { size_t Pp, Pi, P_seg, P_pow, Ap, Ai, A_seg, A_pow, l_src, perm, Kp, Ki, Kkind, Kidx, Lp, Li, Rp, Rc, Rpos, Ltpos, LtR, LtEnd, Arp, Arj, Arx, Psp, Psa, Psv, LevP, LevC, A_coef; };
 void qp_plan_pack(const QpPlanHost& H, std::vector<int>& ints, std::vector<double>& dbls, QpPlanOffsets& off);
 void qp_plan_bind(const QpPlanHost& H, const QpPlanOffsets& off, const int* ints, const double* dbls, QpPlanDev& D);
 

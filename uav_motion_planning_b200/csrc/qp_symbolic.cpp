@@ -229,6 +229,45 @@ QpPlanHost* qp_plan_build(int order, int S) {
     }
     P.LtEnd[N] = k;
   }
+  // ---- views for the warp-per-problem kernel ---------------------------------------------------------------------------
+  {  // CSR of A, entries of a row by increasing column (the order in which the CSC loop adds them to that row)
+    P.Arp.assign(m + 1, 0);
+    for (int e = 0; e < P.nnzA; e++) P.Arp[P.Ai[e] + 1]++;
+    for (int r = 0; r < m; r++) P.Arp[r + 1] += P.Arp[r];
+    P.Arj.assign(P.nnzA, 0); P.Arx.assign(P.nnzA, 0);
+    std::vector<int> nxt(P.Arp.begin(), P.Arp.end() - 1);
+    for (int c = 0; c < n; c++)
+      for (int e = P.Ap[c]; e < P.Ap[c + 1]; e++) { int r = P.Ai[e]; P.Arj[nxt[r]] = c; P.Arx[nxt[r]] = e; nxt[r]++; }
+  }
+  {  // P*v with the upper triangle: contributions to element i in the order of the CSC loop (qp_P_mul)
+    std::vector<std::vector<std::pair<int, int>>> lst(n);
+    for (int c = 0; c < n; c++)
+      for (int e = P.Pp[c]; e < P.Pp[c + 1]; e++) {
+        int r = P.Pi[e];
+        lst[r].push_back({e, c});
+        if (r != c) lst[c].push_back({e, r});
+      }
+    P.Psp.assign(n + 1, 0);
+    for (int i = 0; i < n; i++) {
+      for (auto& pr : lst[i]) { P.Psa.push_back(pr.first); P.Psv.push_back(pr.second); }
+      P.Psp[i + 1] = (int)P.Psa.size();
+    }
+  }
+  {  // L' solve levels: x_i needs x_r for every row r of column i (all r > i)
+    std::vector<int> lev(N, 0);
+    int mx = 0;
+    for (int i = N - 1; i >= 0; i--) {
+      int l = 0;
+      for (int j = P.Lp[i]; j < P.Lp[i + 1]; j++) l = std::max(l, lev[P.Li[j]] + 1);
+      lev[i] = l; mx = std::max(mx, l);
+    }
+    P.nlev = mx;  // level 0 (columns without entries) needs no work
+    P.LevP.assign(mx + 1, 0);
+    for (int l = 1; l <= mx; l++) {
+      for (int i = N - 1; i >= 0; i--) if (lev[i] == l) P.LevC.push_back(i);
+      P.LevP[l] = (int)P.LevC.size();
+    }
+  }
   return pl;
 }
 
@@ -240,6 +279,8 @@ void qp_plan_pack(const QpPlanHost& H, std::vector<int>& ints, std::vector<doubl
   o.l_src = push(H.l_src); o.perm = push(H.perm); o.Kp = push(H.Kp); o.Ki = push(H.Ki); o.Kkind = push(H.Kkind);
   o.Kidx = push(H.Kidx); o.Lp = push(H.Lp); o.Li = push(H.Li); o.Rp = push(H.Rp); o.Rc = push(H.Rc); o.Rpos = push(H.Rpos);
   o.Ltpos = push(H.Ltpos); o.LtR = push(H.LtR); o.LtEnd = push(H.LtEnd);
+  o.Arp = push(H.Arp); o.Arj = push(H.Arj); o.Arx = push(H.Arx); o.Psp = push(H.Psp); o.Psa = push(H.Psa); o.Psv = push(H.Psv);
+  o.LevP = push(H.LevP); o.LevC = push(H.LevC);
   dbls = H.P_coef;
   o.A_coef = dbls.size();
   dbls.insert(dbls.end(), H.A_coef.begin(), H.A_coef.end());
@@ -254,15 +295,19 @@ void qp_plan_bind(const QpPlanHost& H, const QpPlanOffsets& o, const int* I, con
   D.l_src = I + o.l_src; D.perm = I + o.perm; D.Kp = I + o.Kp; D.Ki = I + o.Ki; D.Kkind = I + o.Kkind; D.Kidx = I + o.Kidx;
   D.Lp = I + o.Lp; D.Li = I + o.Li; D.Rp = I + o.Rp; D.Rc = I + o.Rc; D.Rpos = I + o.Rpos;
   D.Ltpos = I + o.Ltpos; D.LtR = I + o.LtR; D.LtEnd = I + o.LtEnd;
+  D.Arp = I + o.Arp; D.Arj = I + o.Arj; D.Arx = I + o.Arx; D.Psp = I + o.Psp; D.Psa = I + o.Psa; D.Psv = I + o.Psv;
+  D.LevP = I + o.LevP; D.LevC = I + o.LevC; D.nlev = H.nlev;
   // workspace layout (offsets in doubles; element e of problem b lives at ws[e * stride + b])
   int at = 0;
   auto take = [&](int len) { int r = at; at += len; return r; };
   const int n = H.n, m = H.m, N = H.N;
   D.o_Px = take(H.nnzP); D.o_Ax = take(H.nnzA); D.o_q = take(n); D.o_l = take(m); D.o_u = take(m);
   D.o_D = take(n); D.o_Dinv = take(n); D.o_E = take(m); D.o_Einv = take(m); D.o_rho = take(m); D.o_rhoinv = take(m);
-  D.o_Lx = take(H.nnzL); D.o_LxT = take(H.nnzL); D.o_Dd = take(N); D.o_Ddinv = take(N); D.o_yw = take(N);
+  D.o_Lx = take(H.nnzL); D.o_Dd = take(N); D.o_Ddinv = take(N); D.o_yw = take(N);
   D.o_x = take(n); D.o_xprev = take(n); D.o_dx = take(n); D.o_Pxv = take(n); D.o_Aty = take(n);
   D.o_z = take(m); D.o_zprev = take(m); D.o_y = take(m); D.o_dy = take(m); D.o_Axv = take(m);
   D.o_xz = take(N); D.o_bp = take(N); D.o_tn = take(n); D.o_tm = take(m);
+  D.ws_warp = at;              // the warp-per-problem kernel keeps everything up to here in shared memory
+  D.o_LxT = take(H.nnzL);      // thread-per-problem kernel only: L in the L' solve's consumption order
   D.ws_doubles = at;
 }
