@@ -159,6 +159,7 @@ __global__ void qp_solve_warp_fused_kernel(QpPlanDev pl, QpIo io, uavmp_osqp_set
 // warps per CTA of the warp-per-problem kernels: as many problems as ~100 KB of shared memory hold (2 CTAs / SM); 0 = does not fit
 static int qpw_warps_per_cta(const QpPlanDev& pl) {
   if (getenv("UAVMP_QP_THREAD")) return 0;
+  if (!getenv("UAVMP_QP_WARP")) return 0;  // TODO(verify on GPU): opt-in until the device run has been checked against the oracle
   const size_t per = (size_t)pl.ws_warp * sizeof(double);
   if (per > 200 * 1024) return 0;
   int w = (int)((100 * 1024) / per);
