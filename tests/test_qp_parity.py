@@ -78,3 +78,19 @@ def test_eps_sweep_config5(gpu_ctx, eps):
 def test_ragged_batch_sizes(gpu_ctx):
     for B in (1, 31, 33, 257):
         compare(gpu_ctx, 5, 3, B, seed=B)
+
+
+def test_both_kernels_agree_bitwise(gpu_ctx, monkeypatch):
+    """The warp-per-problem kernel (default for small batches / the pipeline) and the thread-per-problem kernel (large batches)
+    are two schedules of the same arithmetic: identical bits, both identical to the reference OSQP."""
+    pos, bv, ba, bj, T = make_problems(96, 8, 5, unit_time=False)
+    mc = MinimumControl(gpu_ctx, order=7)
+    monkeypatch.setenv("UAVMP_QP_THREAD", "1")
+    a = {k: v.copy() for k, v in mc.solve_batch(pos, bv, ba, T, bound_jerk=bj).items()}
+    monkeypatch.delenv("UAVMP_QP_THREAD")
+    monkeypatch.setenv("UAVMP_QP_WARP", "1")
+    b = mc.solve_batch(pos, bv, ba, T, bound_jerk=bj)
+    for k in ("coef", "iters", "status", "solved"):
+        assert np.array_equal(a[k], b[k]), k
+    ok, coef, info = oracle_lib.minctrl_solve(7, 8, pos[0], bv[0], ba[0], T[0], bound_jerk=bj[0])
+    assert np.array_equal(coef, b["coef"][0]) and info["iter"] == b["iters"][0]

@@ -157,9 +157,12 @@ __global__ void qp_solve_warp_fused_kernel(QpPlanDev pl, QpIo io, uavmp_osqp_set
 }
 
 // warps per CTA of the warp-per-problem kernels: as many problems as ~100 KB of shared memory hold (2 CTAs / SM); 0 = does not fit
-static int qpw_warps_per_cta(const QpPlanDev& pl) {
+static int qpw_warps_per_cta(const QpPlanDev& pl, int B, bool overlapped) {
   if (getenv("UAVMP_QP_THREAD")) return 0;
-  if (!getenv("UAVMP_QP_WARP")) return 0;  // TODO(verify on GPU): opt-in until the device run has been checked against the oracle
+  // Measured on B200 (order 7, S 8): a problem takes ~7.6 ms on a warp and ~50 ms on a thread, but 12 288 threads run at once
+  // while only ~1 200 warps do (shared memory).  So: the overlapped pipeline always takes the warp kernel (latency after the
+  // last search is what counts there), a stand-alone batch takes it while it is small enough to win on wall time.
+  if (!overlapped && B > 6000 && !getenv("UAVMP_QP_WARP")) return 0;
   const size_t per = (size_t)pl.ws_warp * sizeof(double);
   if (per > 200 * 1024) return 0;
   int w = (int)((100 * 1024) / per);
@@ -262,7 +265,7 @@ int qp_solve_batch_dev(uavmp_ctx* ctx, int order, int S, int B, const double* d_
   QpIo io;
   io.pos = d_pos; io.bv = d_bv; io.ba = d_ba; io.bj = d_bj ? d_bj : d_ba; io.T = d_T;
   io.coef = d_coef; io.solved = d_solved; io.status = d_status; io.iters = d_iters; io.B = B; io.stride = stride;
-  if (const int wpc = qpw_warps_per_cta(p->dev)) {
+  if (const int wpc = qpw_warps_per_cta(p->dev, B, false)) {
     // one warp per problem, everything in shared memory: no global workspace at all
     const size_t smem = (size_t)wpc * p->dev.ws_warp * sizeof(double);
     if (smem > 48 * 1024) cudaFuncSetAttribute(qp_solve_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -316,7 +319,7 @@ int qp_launch_fused(uavmp_ctx* ctx, int order, int S, int B, double seg_time, co
     fu.dbg = d_dbg;
     ctx->dbg_ptr = d_dbg;
   }
-  if (const int wpc = qpw_warps_per_cta(p->dev)) {
+  if (const int wpc = qpw_warps_per_cta(p->dev, nB, true)) {
     const size_t smem_w = (size_t)wpc * p->dev.ws_warp * sizeof(double);
     if (smem_w > 48 * 1024) cudaFuncSetAttribute(qp_solve_warp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
     qp_solve_warp_fused_kernel<<<(nB + wpc - 1) / wpc, 32 * wpc, smem_w, ctx->stream2>>>(p->dev, io, *st, wpc, fu);
