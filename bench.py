@@ -39,7 +39,8 @@ def workload_config(B, n_gpus):
     return {"workload": "configs[1]: batch 4096 queries, 50x50x10 m random map @0.1 m, kino-A* + 8-seg 7th-order "
                         "min-snap, per GPU", "batch_per_gpu": B, "global_batch": B * n_gpus, "map": "500x500x100 int8, "
             "random_forest seed 1", "kino": "launch-file params, collision_check_type 1 (grid + ellipsoid)",
-            "qp": "order 7, S 8, T_i 1.0, OSQP eps 1e-3, 3 axes per plan", "l2": "flushed between steps (256 MiB write) "
+            "qp": "order 7, S 8, T_i 1.0, OSQP eps 1e-3, 3 axes per plan; QP kernel (one warp per problem) overlapped with the search "
+            "kernel on a second stream, per-query completion flags", "l2": "flushed between steps (256 MiB write) "
             "and a different query batch every step", "parallelism": f"queries sharded x{n_gpus}, map replicated"}
 
 
