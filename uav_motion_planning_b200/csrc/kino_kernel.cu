@@ -93,12 +93,9 @@ struct SearchSmem {
   // separable tables of one expansion
   double X[UAVMP_MAXK][3][UAVMP_MAXNA];
   int XI[UAVMP_MAXK][3][UAVMP_MAXNA];
-  uint8_t XOK[UAVMP_MAXK][3][UAVMP_MAXNA];
   double EX[3][UAVMP_MAXNA], EV[3][UAVMP_MAXNA];
   int EI[3][UAVMP_MAXNA];
   uint8_t axok[3][UAVMP_MAXNA];
-  int aimin[3][UAVMP_MAXNA], aimax[3][UAVMP_MAXNA];
-  double axmin[3][UAVMP_MAXNA], axmax[3][UAVMP_MAXNA];
   double xlo[3], xhi[3];
   int to[3], rc0[3], rc1[3];
   int any_ok, tile_ok, nT, npts, n_upd, last_ev, nq;
@@ -636,6 +633,8 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
           s.flag = (sqrt(dot3(dx, dy, dz, dx, dy, dz)) < P.goal_tol) ? 1 : 0;
           s.n1 = 0; s.n2 = 0; s.nT = 0; s.n_upd = 0; s.last_ev = -1;
         }
+      } else if (tid >= 32 && tid < 32 + 3 * UAVMP_MAXNA) {
+        (&s.axok[0][0])[tid - 32] = 1;  // reset the per-axis feasibility flags for this expansion's tables
       }
       __syncthreads();
       PH_MARK(0);
@@ -754,44 +753,11 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
         if (i < K) {
           const double lo = ax == 0 ? M.lox : (ax == 1 ? M.loy : M.loz), hi = ax == 0 ? M.hix : (ax == 1 ? M.hiy : M.hiz);
           const bool ok = !(x < lo) && !(x > hi) && !(v < -P.vmax) && !(v > P.vmax);
-          s.X[i][ax][a] = x; s.XI[i][ax][a] = idx; s.XOK[i][ax][a] = ok ? 1 : 0;
+          s.X[i][ax][a] = x; s.XI[i][ax][a] = idx;
+          if (!ok) s.axok[ax][a] = 0;  // feasible on this axis only if every checkpoint is (all writers store 0: benign)
         } else {
           s.EX[ax][a] = x; s.EV[ax][a] = v; s.EI[ax][a] = idx;
         }
-      }
-      __syncthreads();
-      // per-axis feasibility over all checkpoints + the voxel / position extent of the feasible part
-      if (tid < 3 * na) {
-        const int ax = tid / na, a = tid % na;
-        bool ok = true;
-        int imin = INT_MAX, imax = INT_MIN;
-        double xmin = 1e300, xmax = -1e300;
-        for (int i = 0; i < K; i++) {
-          ok = ok && s.XOK[i][ax][a];
-          imin = min(imin, s.XI[i][ax][a]); imax = max(imax, s.XI[i][ax][a]);
-          xmin = fmin(xmin, s.X[i][ax][a]); xmax = fmax(xmax, s.X[i][ax][a]);
-        }
-        s.axok[ax][a] = ok ? 1 : 0;
-        s.aimin[ax][a] = ok ? imin : INT_MAX; s.aimax[ax][a] = ok ? imax : INT_MIN;
-        s.axmin[ax][a] = ok ? xmin : 1e300;   s.axmax[ax][a] = ok ? xmax : -1e300;
-      }
-      __syncthreads();
-      if (warp == 0) {
-        // any feasible coordinate per axis? + the position extent of the feasible part (for the cloud staging region)
-        bool any = true;
-        if (lane < 3) {
-          const int ax = lane;
-          int lo = INT_MAX, hi = INT_MIN;
-          double xl = 1e300, xh = -1e300;
-          for (int a = 0; a < na; a++) {
-            lo = min(lo, s.aimin[ax][a]); hi = max(hi, s.aimax[ax][a]);
-            xl = fmin(xl, s.axmin[ax][a]); xh = fmax(xh, s.axmax[ax][a]);
-          }
-          if (lo > hi) any = false;
-          s.xlo[ax] = xl; s.xhi[ax] = xh;
-        }
-        any = __all_sync(FULL, any);
-        if (lane == 0) s.any_ok = any ? 1 : 0;
       }
       __syncthreads();
       const bool tile_ok = s.tile_ok != 0;
@@ -799,7 +765,7 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
 
       // ---- A1. grid + velocity + in-map for every primitive from shared memory (:172-211 minus the ellipsoid) ----
       int my_need = 0;
-      if (s.any_ok) {
+      {
         const int tx = s.to[0], ty = s.to[1], tz = s.to[2];
         for (int p = tid; p < nprim; p += KT) {
           const int a = p / (na * na), b = (p / na) % na, c = p % na;
@@ -827,15 +793,13 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
           s.a.need[p] = (st == ST_FEASIBLE) ? (uint16_t)need : (uint16_t)0;
           if (st == ST_FEASIBLE && need) my_need = 1;
         }
-      } else {
-        for (int p = tid; p < nprim; p += KT) s.state[p] = ST_REJECT;
       }
       const int any_need = __syncthreads_or(my_need);
       // work units of the cloud test: (checkpoint i, lattice column a, b) with the set of c whose checkpoint is flagged.
       // The nine centres of a unit share x and y, so one pass over the candidate points serves all of them.  Ordered
       // compaction keeps neighbouring units on neighbouring lanes (similar candidate sets -> similar trip counts).
       if (any_need) {
-        const int nU = s.any_ok ? K * na * na : 0;
+        const int nU = K * na * na;
         const int per = (nU + KT - 1) / KT;
         uint32_t mine[8];
         int cnt = 0;
@@ -867,10 +831,16 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
       if (nT > 0) {
         // stage the cell list of the region the feasible checkpoints can touch: cell_start entries, then the points
         if (tid < 3) {
+          // position extent of the feasible checkpoints on this axis -> cell range of the staging region
+          double xl = 1e300, xh = -1e300;
+          for (int a = 0; a < na; a++)
+            if (s.axok[tid][a])
+              for (int i = 0; i < K; i++) { xl = fmin(xl, s.X[i][tid][a]); xh = fmax(xh, s.X[i][tid][a]); }
+          s.xlo[tid] = xl; s.xhi[tid] = xh;
           const double co = tid == 0 ? M.cox : (tid == 1 ? M.coy : M.coz);
           const int cn = tid == 0 ? M.cnx : (tid == 1 ? M.cny : M.cnz);
-          s.rc0[tid] = max((int)floor((s.xlo[tid] - P.box_r - co) * M.inv_cell), 0);
-          s.rc1[tid] = min((int)floor((s.xhi[tid] + P.box_r - co) * M.inv_cell), cn - 1);
+          s.rc0[tid] = max((int)floor((xl - P.box_r - co) * M.inv_cell), 0);
+          s.rc1[tid] = min((int)floor((xh + P.box_r - co) * M.inv_cell), cn - 1);
         }
         __syncthreads();
         const int ncx = s.rc1[0] - s.rc0[0] + 1, ncy = s.rc1[1] - s.rc0[1] + 1, ncz1 = s.rc1[2] - s.rc0[2] + 2;
@@ -1066,24 +1036,6 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
         s.state[p] = st;
       }
       __syncthreads();
-      for (int e = tid; e < n1; e += KT) {
-        const int p = s.list1[e];
-        uint8_t st = s.state[p];
-        if (st == ST_FOLLOW_NOCAND) {
-          const int leader = (int)s.id[p];
-          const uint8_t ls = s.state[leader];
-          if (ls == ST_CLOSED) {
-            st = ST_CLOSED;
-          } else {
-            const double gp = s.cg + ginc_of(P, p);
-            if (gp < s.b.gcur[leader]) st = ST_FOLLOW_CAND;
-          }
-          s.state[p] = st;
-        }
-        if (st == ST_NEW || st == ST_OPEN_CAND || st == ST_FOLLOW_CAND) atomicAdd(&s.n2, 1);
-      }
-      __syncthreads();
-      const int n2 = s.n2;
       // ---- C. ordered id assignment for new nodes (== use_node_num_++ in lattice order) ----------------
       {
         const int p0 = tid * 3;
@@ -1092,7 +1044,13 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
         for (int j = 0; j < 3; j++) {
           const int p = p0 + j;
           if (p < nprim) {
-            const uint8_t st = s.state[p];
+            uint8_t st = s.state[p];
+            if (st == ST_FOLLOW_NOCAND) {  // a follower takes its verdict from its group leader (final since the probe)
+              const int leader = (int)s.id[p];
+              if (s.state[leader] == ST_CLOSED) st = ST_CLOSED;
+              else if (s.cg + ginc_of(P, p) < s.b.gcur[leader]) st = ST_FOLLOW_CAND;
+              s.state[p] = st;
+            }
             if (st == ST_NEW) c += 0x10001;
             else if (st == ST_OPEN_CAND || st == ST_FOLLOW_CAND) c += 0x10000;
           }
@@ -1119,11 +1077,12 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
             else if (st == ST_OPEN_CAND || st == ST_FOLLOW_CAND) s.list2[ec++] = (uint16_t)p;
           }
         }
-        if (tid == KT - 1) s.n_new = (woff + incl) & 0xffff;
+        if (tid == KT - 1) { s.n_new = (woff + incl) & 0xffff; s.n2 = (woff + incl) >> 16; }
       }
       __syncthreads();
       PH_MARK(4);
       const int n_new = s.n_new;
+      const int n2 = s.n2;
       if (s.use_num + n_new >= P.allocated) {
         // pool exhausted while committing this expansion (:243-247): the reference returns on the spot
         if (tid == 0) {
