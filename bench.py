@@ -311,8 +311,21 @@ def run_gpu(args, rank, world_size, local_rank):
             out["cpu_baseline"] = {"value": n_s / dt, "unit": "plans/s", "cores": threads, "kind": kind,
                                    "sample": f"first {n_s} queries of the first timed batch, {threads} threads; {how}"}
         print(json.dumps(out), flush=True)
+    # Orderly teardown.  The tensors above were allocated while the library's stream was torch's current stream: the caching
+    # allocator (and NCCL's record_stream) records events on that stream when they are freed, so they must go BEFORE the
+    # library context destroys the stream; a 2-GPU run crashed at exit ("context is destroyed") before this ordering existed.
+    del d_in, d_status, d_solved, d_coef, flush, h_in, h_status, h_solved, h_coef
     if world_size > 1:
+        del g_coef, g_stat
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    if world_size > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    ka = None
+    ctx.close()
+    sys.stdout.flush()
+    os._exit(0)  # skip interpreter finalisers: nothing left to do, and nothing may touch the destroyed stream afterwards
 
 
 def main():
