@@ -35,7 +35,9 @@
 #include "fpmath.h"
 #include "uavmp_internal.h"
 
+#ifndef KT
 #define KT 256
+#endif
 #define TAB_SIZE 2048
 #define PUSH_BATCH 256
 #define HC_CAP 640
@@ -233,7 +235,7 @@ __device__ __forceinline__ void pos_to_index(const MapDev& M, double x, double y
   iz = (int)floor((z - M.oz) * M.inv_res);
 }
 __device__ __forceinline__ unsigned map_flags(const MapDev& M, int ix, int iy, int iz) {
-  return __ldg(M.flags + ((size_t)ix * M.ny + iy) * M.nzp + iz);
+  return __ldg(M.flags + ((((size_t)ix * (M.nzp >> 4) + (iz >> 4)) * M.ny + iy) << 4) + (iz & 15));
 }
 
 __device__ __forceinline__ unsigned long long pack_key(int ix, int iy, int iz, bool& ok) {
@@ -256,49 +258,83 @@ __device__ __forceinline__ HeapSlot hload(const SearchSmem& s, const HeapSlot* H
 __device__ __forceinline__ void hstore(SearchSmem& s, HeapSlot* H, int i, const HeapSlot& v) { if (i < HTOP) s.htop[i] = v; else H[i] = v; }
 __device__ __forceinline__ void hstore_key(SearchSmem& s, HeapSlot* H, int i, double f) { if (i < HTOP) s.htop[i].f = f; else __stcg(&H[i].f, f); }
 
-__device__ void heap_pop_serial(SearchSmem& s, HeapSlot* H, HashSlot* table, int& len, HeapSlot& top) {
-  // std::pop_heap + pop_back (bits/stl_heap.h __pop_heap -> __adjust_heap -> __push_heap), comp(a,b) = f[a] > f[b]
-  top = hload(s, H, 1);
-  int old_len = len;
+// std::pop_heap + pop_back (bits/stl_heap.h __pop_heap -> __adjust_heap -> __push_heap), comp(a,b) = f[a] > f[b], executed
+// by warp 0.  Indices below are 1-based (slot j lives at H[j]): the hole starts at 1 and moves to the child with the
+// smaller key (the right one on ties) while both children exist (2h+1 <= n), a lone left child (2h == n) moves up
+// unconditionally, and the former last element is then pushed up from the final hole.
+// The sift-down is a chain of dependent loads, one L2 round trip per level once it leaves the shared-memory top of the
+// heap.  The warp therefore fetches the whole cone of the next three levels below the hole (2 + 4 + 8 slots, lanes
+// 0..13) in ONE round trip and resolves the three comparisons with shuffles; the lane that holds a chosen slot writes
+// it to its parent position.  No slot written during the sift-down is read again by it (writes go to ancestors of
+// the hole, reads to its descendants).
+__device__ void heap_pop_warp(SearchSmem& s, HeapSlot* H, HashSlot* table, int& len, HeapSlot& top, int lane) {
+  top = s.htop[1];
+  const int old_len = len;
   len = old_len - 1;
   if (old_len <= 1) return;
-  HeapSlot value = hload(s, H, old_len);  // last element
-  int n = len;
-  int hole = 0;
-  int second = 0;
-  while (second < (n - 1) / 2) {
-    second = 2 * (second + 1);
-    {  // the next hole is slot second or second-1: their child pairs are the two adjacent 32 B sectors at H[2*second]
-      const int g = 2 * second;
-      if (g >= HTOP && g + 3 <= n) {
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(H + g));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(H + g + 2));
+  const int n = len;
+  const HeapSlot value = hload(s, H, old_len);  // the last element (same address in every lane: one transaction)
+  __syncwarp();  // every lane has read the old top before lane 0 overwrites it
+  int hole = 1;
+  double moved_f = 0.0;   // key of the slot moved in the last step == the parent of the current hole
+  bool moved = false;
+  // levels whose children both live in shared memory: every lane walks the same path, lane 0 stores
+  while (2 * hole + 1 <= n && 2 * hole + 1 < HTOP) {
+    const HeapSlot l = s.htop[2 * hole], r = s.htop[2 * hole + 1];
+    const bool right = !(r.f > l.f);
+    const HeapSlot pick = right ? r : l;
+    if (lane == 0) { s.htop[hole] = pick; table[pick.hs].heap_pos = (uint32_t)(hole - 1); }
+    hole = 2 * hole + (right ? 1 : 0);
+    moved_f = pick.f; moved = true;
+  }
+  // deeper levels, three per round trip
+  const int lvl = lane < 2 ? 1 : (lane < 6 ? 2 : 3);
+  const int off = lane < 2 ? lane : (lane < 6 ? lane - 2 : lane - 6);
+  while (2 * hole + 1 <= n) {
+    const long long idx = ((long long)hole << lvl) + off;
+    HeapSlot e;
+    e.f = 0.0; e.id = 0; e.hs = 0;
+    if (lane < 14 && idx <= (long long)n) e = hload(s, H, (int)idx);
+    int cur = hole, rel = 0, lbase = 0;  // lbase: first lane of the level below `cur` (0, 2, 6)
+#pragma unroll
+    for (int step = 0; step < 3; step++) {
+      if (2 * cur + 1 > n) break;
+      const int lane_l = lbase + 2 * rel;
+      const double fl = __shfl_sync(FULL, e.f, lane_l), fr = __shfl_sync(FULL, e.f, lane_l + 1);
+      const bool right = !(fr > fl);
+      if (lane == lane_l + (right ? 1 : 0)) { hstore(s, H, cur, e); table[e.hs].heap_pos = (uint32_t)(cur - 1); }
+      moved_f = right ? fr : fl; moved = true;
+      cur = 2 * cur + (right ? 1 : 0);
+      rel = 2 * rel + (right ? 1 : 0);
+      lbase = 2 * lbase + 2;
+    }
+    hole = cur;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    if (2 * hole == n) {  // a lone left child
+      const HeapSlot l = hload(s, H, n);
+      hstore(s, H, hole, l);
+      table[l.hs].heap_pos = (uint32_t)(hole - 1);
+      hole = n;
+      moved_f = l.f; moved = true;
+    }
+    // __push_heap of the former last element from the hole; its first parent is the slot that was just moved
+    if (hole > 1 && (!moved || moved_f > value.f)) {
+      int parent = hole / 2;
+      while (hole > 1) {
+        const HeapSlot pe = hload(s, H, parent);
+        if (!(pe.f > value.f)) break;
+        hstore(s, H, hole, pe);
+        table[pe.hs].heap_pos = (uint32_t)(hole - 1);
+        hole = parent;
+        parent = hole / 2;
       }
     }
-    HeapSlot r = hload(s, H, second + 1), l = hload(s, H, second);  // right child = slot `second`, left = second-1
-    if (r.f > l.f) { second--; r = l; }
-    hstore(s, H, hole + 1, r);
-    table[r.hs].heap_pos = (uint32_t)hole;
-    hole = second;
+    hstore(s, H, hole, value);
+    table[value.hs].heap_pos = (uint32_t)(hole - 1);
   }
-  if ((n & 1) == 0 && second == (n - 2) / 2) {
-    second = 2 * (second + 1);
-    HeapSlot l = hload(s, H, second);  // slot second-1
-    hstore(s, H, hole + 1, l);
-    table[l.hs].heap_pos = (uint32_t)hole;
-    hole = second - 1;
-  }
-  int parent = (hole - 1) / 2;
-  while (hole > 0) {
-    HeapSlot pe = hload(s, H, parent + 1);
-    if (!(pe.f > value.f)) break;
-    hstore(s, H, hole + 1, pe);
-    table[pe.hs].heap_pos = (uint32_t)hole;
-    hole = parent;
-    parent = (hole - 1) / 2;
-  }
-  hstore(s, H, hole + 1, value);
-  table[value.hs].heap_pos = (uint32_t)hole;
+  __syncwarp();
 }
 
 // closure = the ancestors of leaves len0+1 .. len0+m (1-based heap indices), staged in shared memory by warp 0.
@@ -506,7 +542,7 @@ __device__ bool ellipsoid_hit_global(const MapDev& M, const KinoParamsDev& P, co
 }
 
 // =====================================================================================================
-__global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev* __restrict__ Pp, LatticeDev lat,
+__global__ void __launch_bounds__(KT, (KT <= 256 ? 2 : 1)) kino_search_kernel(const KinoParamsDev* __restrict__ Pp, LatticeDev lat,
                                                             const MapDev* __restrict__ Mp, KinoArena* arenas,
                                                             KinoBatchDev bt, int table_bits,
                                                             const __grid_constant__ CUtensorMap tmap, int use_tma) {
@@ -598,15 +634,29 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
     // ================================ main loop (kino_astar.cpp:101) ===============================
     for (;;) {
       // ---- pop --------------------------------------------------------------------------------------
-      if (tid == 0) {
-        if (s.heap_len == 0) {
-          s.status = UAVMP_NO_PATH_FOUND;  // open list exhausted (:270-271)
+      if (warp == 0) {
+        const int len0 = s.heap_len;
+        __syncwarp();
+        if (len0 == 0) {
+          if (lane == 0) s.status = UAVMP_NO_PATH_FOUND;  // open list exhausted (:270-271)
         } else {
           HeapSlot top;
-          int len = s.heap_len;
-          heap_pop_serial(s, H, table, len, top);
+          int len = len0;
+          // the popped node's record is only needed after the sift-down: lanes 16..24 fetch its nine words under it
+          unsigned long long nw = 0;
+          const uint32_t top_id = s.htop[1].id;
+          if (lane >= 16 && lane < 16 + (int)(sizeof(KinoNode) / 8))
+            nw = reinterpret_cast<const unsigned long long*>(nodes + top_id)[lane - 16];
+          __syncwarp();
+          heap_pop_warp(s, H, table, len, top, lane);
+          KinoNode nd;
+          nd.px = __longlong_as_double((long long)__shfl_sync(FULL, nw, 16)); nd.py = __longlong_as_double((long long)__shfl_sync(FULL, nw, 17));
+          nd.pz = __longlong_as_double((long long)__shfl_sync(FULL, nw, 18)); nd.vx = __longlong_as_double((long long)__shfl_sync(FULL, nw, 19));
+          nd.vy = __longlong_as_double((long long)__shfl_sync(FULL, nw, 20)); nd.vz = __longlong_as_double((long long)__shfl_sync(FULL, nw, 21));
+          nd.g = __longlong_as_double((long long)__shfl_sync(FULL, nw, 22));
+          nd.parent = (uint32_t)(__shfl_sync(FULL, nw, 23) & 0xffffffffull);
+          if (lane == 0) {
           s.heap_len = len;
-          KinoNode nd = nodes[top.id];
           nodes[top.id].closed = 1;
           table[top.hs].closed = 1;
           s.cur_id = top.id; s.cur_parent = nd.parent;
@@ -632,6 +682,7 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
           double dx = nd.px - s.gp[0], dy = nd.py - s.gp[1], dz = nd.pz - s.gp[2];
           s.flag = (sqrt(dot3(dx, dy, dz, dx, dy, dz)) < P.goal_tol) ? 1 : 0;
           s.n1 = 0; s.n2 = 0; s.nT = 0; s.n_upd = 0; s.last_ev = -1;
+          }
         }
       } else if (tid >= 32 && tid < 32 + 3 * UAVMP_MAXNA) {
         (&s.axok[0][0])[tid - 32] = 1;  // reset the per-axis feasibility flags for this expansion's tables
@@ -718,28 +769,50 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
 
       // ---- A0. separable tables: every checkpoint / end-state coordinate is (c + t v) + h u per axis, and u comes
       // from a tensor lattice, so there are only K * 3 * na distinct coordinates (StateTransit, :651-670) -----------
-      if (tid == KT - 1) {
+      if (warp == KT / 32 - 1) {
         // the flags box is requested first, from a conservative extent (all checkpoints, feasible or not: x is monotone in
-        // u, so the extremes sit at the two end values of the lattice), so that the TMA runs under the table computation
-        bool fits = use_tma != 0;
-        for (int ax = 0; ax < 3; ax++) {
+        // u, so the extremes sit at the two end values of the lattice), so that the TMA runs under the table computation.
+        // One lane per (axis, checkpoint), then a warp reduction per axis: the request leaves a few hundred cycles earlier
+        // than from a single thread.
+        int lo = INT_MAX, hi = INT_MIN;
+        for (int j = lane; j < 3 * K; j += 32) {
+          const int ax = j / K, i = j % K;
           const double org = ax == 0 ? M.ox : (ax == 1 ? M.oy : M.oz);
-          int lo = INT_MAX, hi = INT_MIN;
-          for (int i = 0; i < K; i++) {
-            const double b = s.cp[ax] + P.tk[i] * s.cv[ax];
-            const int i0 = (int)floor(((b + P.hk[i] * P.ua[0]) - org) * M.inv_res);
-            const int i1 = (int)floor(((b + P.hk[i] * P.ua[na - 1]) - org) * M.inv_res);
-            lo = min(lo, min(i0, i1)); hi = max(hi, max(i0, i1));
-          }
-          if (ax == 2) lo &= ~15;  // measured: UTMALDG faults unless inner coordinate * element size is 16 B aligned
-          if (hi - lo + 1 > (ax == 2 ? TBZ : TB)) fits = false;
-          s.to[ax] = lo;
+          const double b = s.cp[ax] + P.tk[i] * s.cv[ax];
+          const int i0 = (int)floor(((b + P.hk[i] * P.ua[0]) - org) * M.inv_res);
+          const int i1 = (int)floor(((b + P.hk[i] * P.ua[na - 1]) - org) * M.inv_res);
+          lo = min(lo, min(i0, i1)); hi = max(hi, max(i0, i1));
         }
-        s.tile_ok = fits ? 1 : 0;
-        if (fits) {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_expect_tx(&s.mbar, TB * TB * TBZ);
-          tma_load_3d(s.a.tile, &tmap, s.to[2], s.to[1], s.to[0], &s.mbar);
+        const int ax_l = (lane < 3 * K) ? lane / K : 3;  // with 3 K <= 32 every lane serves one axis
+        bool fits = use_tma != 0;
+        int org3[3];
+#pragma unroll
+        for (int ax = 0; ax < 3; ax++) {
+          int l = INT_MAX, h = INT_MIN;
+          if (3 * K <= 32) {
+            l = __reduce_min_sync(FULL, ax_l == ax ? lo : INT_MAX);
+            h = __reduce_max_sync(FULL, ax_l == ax ? hi : INT_MIN);
+          } else {  // lanes mix axes: recompute serially (not reached with the launch-file checkpoint count)
+            const double org = ax == 0 ? M.ox : (ax == 1 ? M.oy : M.oz);
+            for (int i = 0; i < K; i++) {
+              const double b = s.cp[ax] + P.tk[i] * s.cv[ax];
+              const int i0 = (int)floor(((b + P.hk[i] * P.ua[0]) - org) * M.inv_res);
+              const int i1 = (int)floor(((b + P.hk[i] * P.ua[na - 1]) - org) * M.inv_res);
+              l = min(l, min(i0, i1)); h = max(h, max(i0, i1));
+            }
+          }
+          if (ax == 2) l &= ~15;  // the copy is blocked by 16 voxels in z (and UTMALDG needs 16 B aligned inner coordinates)
+          if (h - l + 1 > (ax == 2 ? TBZ : TB)) fits = false;
+          org3[ax] = l;
+        }
+        if (lane == 0) {
+          s.to[0] = org3[0]; s.to[1] = org3[1]; s.to[2] = org3[2];
+          s.tile_ok = fits ? 1 : 0;
+          if (fits) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&s.mbar, TB * TB * TBZ);
+            tma_load_3d(s.a.tile, &tmap, org3[1] * 4, org3[2] >> 4, org3[0], &s.mbar);  // (y * 4 words, z block, x)
+          }
         }
       }
       for (int e = tid; e < (K + 1) * 3 * na; e += KT) {
@@ -775,7 +848,7 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
             bool ok = true;
             for (int i = 0; i < K; i++) {
               const int ix = s.XI[i][0][a], iy = s.XI[i][1][b], iz = s.XI[i][2][c];
-              const unsigned fl = tile_ok ? s.a.tile[((ix - tx) * TB + (iy - ty)) * TBZ + (iz - tz)] : map_flags(M, ix, iy, iz);
+              const unsigned fl = tile_ok ? s.a.tile[((((ix - tx) * (TBZ / 16) + ((iz - tz) >> 4)) * TB + (iy - ty)) << 4) + ((iz - tz) & 15)] : map_flags(M, ix, iy, iz);
               my_occ++;
               if (P.ctype == 1 && (fl & 1u)) { ok = false; break; }
               if (fl & 4u) need |= 1u << i;
@@ -881,15 +954,26 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
         unsigned my_hits = 0;
         (void)my_hits;
         if (staged) {
-          // Point-major sweep.  Every unit looks at (almost) the same few hundred staged points, so each thread keeps ONE
-          // unit's nine centres in registers and all threads stream through the staged points in the same order: the
-          // loads are shared-memory broadcasts and the instruction stream is uniform.  With few units, G lanes share a
-          // unit and split the points between them.
-          int G = 1;
-          while (G < 8 && nT * (G * 2) <= KT) G *= 2;
-          const int slots = KT / G, npts = s.npts;
+          // Unit-major sweep over the staged cell list.  Each thread keeps ONE unit's nine centres in registers and walks
+          // the staged points of the cell columns its bounding box (centre +- box_r, the cell walk of the reference-
+          // equivalent fallback below) touches, restricted to the z cells its centres can reach; neighbouring lanes hold
+          // neighbouring lattice columns of the same checkpoint, so a warp walks (almost) the same columns and the loads
+          // are shared-memory broadcasts.  With few units, G lanes share a unit and split each column's points.
           const float cullf = P.cullf;
-          for (int base = 0; base < nT; base += slots) {
+          const int rcx = s.rc0[0], rcy = s.rc0[1], rcz = s.rc0[2], rcx1 = s.rc1[0], rcy1 = s.rc1[1], rcz1 = s.rc1[2];
+          for (int base = 0, slots = 0; base < nT; base += slots) {
+            // G is chosen per round from the units that are left (a short last round spreads over the whole CTA): the
+            // largest split that fits them in one round, or twice that when the units it leaves over then fit a round
+            // of four times the split (1/(2G) + 1/(4G) < 1/G of a single round)
+            constexpr int GMAX = KT / 32;
+            const int rem = nT - base;
+            int G = 1;
+            while (G < GMAX && rem * (G * 2) <= KT) G *= 2;
+            if (4 * G <= GMAX) {
+              const int rem2 = rem - KT / (2 * G);
+              if (rem2 > 0 && rem2 * (4 * G) <= KT) G *= 2;
+            }
+            slots = KT / G;
             const int e = base + tid / G, r = tid % G;
             if (e >= nT) continue;
             const uint32_t un = s.units[e];
@@ -920,9 +1004,22 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
                 if (point_hits(t, q)) { s.state[ab * na + c] = ST_REJECT; mask &= ~(1u << c); }
               }
             };
+            if (!mask) continue;
             int trip = 0;
             constexpr int NP = 4;  // points per trip
-            for (int g = r; g < npts && mask; g += NP * G, trip++) {
+            double zl = 1e300, zh = -1e300;
+            for (int c = 0; c < na; c++)
+              if ((mask >> c) & 1u) { zl = fmin(zl, s.X[i][2][c]); zh = fmax(zh, s.X[i][2][c]); }
+            const int bx0 = max((int)floor((px - P.box_r - M.cox) * M.inv_cell), rcx), bx1 = min((int)floor((px + P.box_r - M.cox) * M.inv_cell), rcx1);
+            const int by0 = max((int)floor((py - P.box_r - M.coy) * M.inv_cell), rcy), by1 = min((int)floor((py + P.box_r - M.coy) * M.inv_cell), rcy1);
+            const int bz0 = max((int)floor((zl - P.box_r - M.coz) * M.inv_cell), rcz), bz1 = min((int)floor((zh + P.box_r - M.coz) * M.inv_cell), rcz1);
+            if (bz0 > bz1) continue;
+            for (int cx = bx0; cx <= bx1 && mask; cx++)
+            for (int cy = by0; cy <= by1 && mask; cy++) {
+            const int lcol = (cx - rcx) * ncy + (cy - rcy);
+            const int cdel = s.a.col_delta[lcol];
+            const int k1 = s.a.cstart[lcol * ncz1 + (bz1 + 1 - rcz)] + cdel;
+            for (int g = s.a.cstart[lcol * ncz1 + (bz0 - rcz)] + cdel + r; g < k1 && mask; g += NP * G, trip++) {
               if ((trip & 15) == 15) {  // somebody else may have rejected these primitives in the meantime
                 for (int c = 0; c < na; c++) if (s.state[ab * na + c] != ST_FEASIBLE) mask &= ~(1u << c);
               }
@@ -932,7 +1029,7 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
               bool any_in = false;
 #pragma unroll
               for (int k = 0; k < NP; k++) {
-                const bool ok = g + k * G < npts;
+                const bool ok = g + k * G < k1;
                 q[k] = s.a.pts[ok ? g + k * G : g];
                 dx[k] = q[k].x - fx; dy[k] = q[k].y - fy;
                 d2[k] = dx[k] * dx[k] + dy[k] * dy[k];
@@ -955,6 +1052,7 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
               for (int k = 0; k < NP; k++)
                 if (in[k]) { my_cloud += (unsigned)__popc(cm[k] & mask); decide(q[k], dx[k], dy[k], d2[k], cm[k] & mask); }
             }
+            }
           }
         } else {
           for (int e = tid; e < nT; e += KT) {
@@ -973,13 +1071,20 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
       }
       // survivors: end state -> voxel key (:216, posToIndex :302-310); the dedup table lives where the tile was
       for (int i = tid; i < TAB_SIZE; i += KT) s.b.tab[i] = 0;
-      for (int p = tid; p < nprim; p += KT) {
-        if (s.state[p] != ST_FEASIBLE) continue;
-        const int a = p / (na * na), b = (p / na) % na, c = p % na;
-        bool kok;
-        s.key[p] = pack_key(s.EI[0][a], s.EI[1][b], s.EI[2][c], kok);
-        if (!kok) atomicOr(bt.error_flag, 1);
-        s.list1[atomicAdd(&s.n1, 1)] = (uint16_t)p;
+      for (int pb = 0; pb < nprim; pb += KT) {  // one shared-memory atomic per warp, not per survivor
+        const int p = pb + tid;
+        const bool live = p < nprim && s.state[p] == ST_FEASIBLE;
+        if (live) {
+          const int a = p / (na * na), b = (p / na) % na, c = p % na;
+          bool kok;
+          s.key[p] = pack_key(s.EI[0][a], s.EI[1][b], s.EI[2][c], kok);
+          if (!kok) atomicOr(bt.error_flag, 1);
+        }
+        const unsigned m = __ballot_sync(FULL, live);
+        int at = 0;
+        if (lane == 0 && m) at = atomicAdd(&s.n1, __popc(m));
+        at = __shfl_sync(FULL, at, 0);
+        if (live) s.list1[at + __popc(m & ((1u << lane) - 1u))] = (uint16_t)p;
       }
       __syncthreads();
       PH_MARK(3);
@@ -1015,10 +1120,11 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
         s.b.inun[p] = 0;
         for (;;) {
           const uint4 w0 = __ldcg(reinterpret_cast<const uint4*>(&table[h]));      // key | id | heap_pos
+          const uint4 w1 = __ldcg(reinterpret_cast<const uint4*>(&table[h]) + 1);  // g | closed | pad (same sector: no
+                                                                                   // second round trip on a key match)
           const unsigned long long hk = ((unsigned long long)w0.y << 32) | w0.x;
           if ((uint32_t)(hk & EPOCH_MASK) != epoch) { st = ST_NEW; s.b.gcur[p] = gp; break; }
           if ((hk >> EPOCH_BITS) == k) {
-            const uint4 w1 = __ldcg(reinterpret_cast<const uint4*>(&table[h]) + 1);  // g | closed | pad
             if (w1.z) {
               st = ST_CLOSED;
             } else {
@@ -1139,6 +1245,7 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
       // depends only on the group's earlier candidates, the group's final state is its LAST improving candidate, and
       // `optimal_time` (Q2) is left by the last improving candidate / new node overall.  Only groups whose node is an
       // ancestor of a new leaf (or a new leaf itself) must still touch the open list in order, in phase D. -------------
+      int my_ev = -1;
       for (int e = tid; e < n2; e += KT) {
         const int p = s.list2[e];
         const uint8_t st = s.state[p];
@@ -1174,8 +1281,10 @@ __global__ void __launch_bounds__(KT, 2) kino_search_kernel(const KinoParamsDev*
             s.b.imp[p] = 0;
           }
         }
-        if (event && s.b.topt[p] >= 0.0) atomicMax(&s.last_ev, e);
+        if (event && s.b.topt[p] >= 0.0) my_ev = e;  // e grows with the trip count: the last one is this thread's maximum
       }
+      my_ev = __reduce_max_sync(FULL, my_ev);
+      if (lane == 0 && my_ev >= 0) atomicMax(&s.last_ev, my_ev);
       __syncthreads();
       PH_MARK(5);
 
@@ -1328,9 +1437,12 @@ __global__ void k_or_near(uint8_t* flags, const uint8_t* near, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) flags[i] = (uint8_t)((flags[i] & 3u) | (near[i] ? 4u : 0u));
 }
-__global__ void k_pad_flags(const uint8_t* in, uint8_t* out, int nz, int nzp, size_t n) {
+__global__ void k_pad_flags(const uint8_t* in, uint8_t* out, int ny, int nz, int nzp, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[(i / nz) * nzp + (i % nz)] = in[i];
+  if (i >= n) return;
+  const int z = (int)(i % nz), y = (int)((i / nz) % ny);
+  const size_t x = i / ((size_t)nz * ny);
+  out[(((x * (nzp >> 4) + (z >> 4)) * ny + y) << 4) + (z & 15)] = in[i];
 }
 __global__ void k_cell_ids(const float* cloud, int n, MapDev M, int* cell, int* idx) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1604,13 +1716,13 @@ int kino_build_map(uavmp_ctx* ctx) {
   } else {
     UAVMP_CUDA(ctx, cudaMemsetAsync(ctx->d_cell_start, 0, (size_t)(ncell + 2) * sizeof(int), st));
   }
-  // padded copy [nx][ny][nzp] (nzp multiple of 16: TMA needs 16 B strides) + the tensor map over it
+  // z-blocked copy [nx][nzp / 16][ny][16] (nzp = nz rounded up to 16) + the tensor map over it
   M.nzp = (M.nz + 15) & ~15;
   const size_t npad = (size_t)M.nx * M.ny * M.nzp;
   if (ctx->d_flags_pad) { cudaFree(ctx->d_flags_pad); ctx->d_flags_pad = nullptr; }
   UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_flags_pad, npad + 256));
   UAVMP_CUDA(ctx, cudaMemsetAsync(ctx->d_flags_pad, 0, npad + 256, st));
-  k_pad_flags<<<nblk(nvox, 256), 256, 0, st>>>(ctx->d_flags, ctx->d_flags_pad, M.nz, M.nzp, nvox);
+  k_pad_flags<<<nblk(nvox, 256), 256, 0, st>>>(ctx->d_flags, ctx->d_flags_pad, M.ny, M.nz, M.nzp, nvox);
   M.flags = ctx->d_flags_pad;
   M.cell_start = ctx->d_cell_start;
   M.pts = ctx->d_pts;
@@ -1629,13 +1741,15 @@ int kino_build_map(uavmp_ctx* ctx) {
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
         qres == cudaDriverEntryPointSuccess) {
       static_assert(sizeof(CUtensorMap) <= sizeof(ctx->tmap_bytes), "tensor map storage");
-      cuuint64_t dims[3] = {(cuuint64_t)M.nzp, (cuuint64_t)M.ny, (cuuint64_t)M.nx};
-      cuuint64_t strides[2] = {(cuuint64_t)M.nzp, (cuuint64_t)M.nzp * M.ny};
-      cuuint32_t box[3] = {TBZ, TB, TB};
+      // the copy is [x][z / 16][y][16]: seen as 32-bit words, dimension 0 runs over (y, 4 words) so that one box row is
+      // 32 y x 16 z = 512 contiguous bytes (a [x][y][z] box would be 1 024 rows of 48 B, measured ~4.5 k cycles per box)
+      cuuint64_t dims[3] = {(cuuint64_t)M.ny * 4, (cuuint64_t)(M.nzp >> 4), (cuuint64_t)M.nx};
+      cuuint64_t strides[2] = {(cuuint64_t)M.ny * 16, (cuuint64_t)(M.nzp >> 4) * M.ny * 16};
+      cuuint32_t box[3] = {TB * 4, TBZ / 16, TB};
       cuuint32_t estr[3] = {1, 1, 1};
-      CUresult r = ((EncodeFn)fn)((CUtensorMap*)ctx->tmap_bytes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ctx->d_flags_pad, dims,
+      CUresult r = ((EncodeFn)fn)((CUtensorMap*)ctx->tmap_bytes, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, ctx->d_flags_pad, dims,
                                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       ctx->have_tmap = (r == CUDA_SUCCESS);
     }
     if (!ctx->have_tmap) memset(ctx->tmap_bytes, 0, sizeof(ctx->tmap_bytes));

@@ -41,7 +41,7 @@ struct LatticeDev {
 
 struct MapDev {
   const uint8_t* flags;  // bit0: inflate==1, bit1: inflate!=0, bit2: a cloud point may lie within the ellipsoid box
-                         // layout [nx][ny][nzp], z fastest, nzp = nz rounded up to 16 (TMA needs 16 B row strides)
+                         // layout [nx][nzp / 16][ny][16] (16-voxel z blocks innermost), nzp = nz rounded up to 16
   int nx, ny, nz, nzp;
   double ox, oy, oz;                    // mp_.map_origin_
   double lox, loy, loz, hix, hiy, hiz;  // map_min_boundary_ + 1e-4, map_max_boundary_ - 1e-4
@@ -137,8 +137,8 @@ struct uavmp_ctx {
   float4* d_pts = nullptr;
   MapDev map_host;
   MapDev* d_map = nullptr;
-  uint8_t* d_flags_pad = nullptr;   // [nx][ny][nzp]
-  unsigned char tmap_bytes[128] __attribute__((aligned(64)));  // CUtensorMap over d_flags_pad, box 32^3
+  uint8_t* d_flags_pad = nullptr;   // [nx][nzp / 16][ny][16]
+  unsigned char tmap_bytes[128] __attribute__((aligned(64)));  // CUtensorMap over d_flags_pad, box 32 x 32 x 48
   bool have_tmap = false;
   bool flags_dirty = true;
 
