@@ -545,7 +545,7 @@ __device__ bool ellipsoid_hit_global(const MapDev& M, const KinoParamsDev& P, co
 __global__ void __launch_bounds__(KT, (KT <= 256 ? 2 : 1)) kino_search_kernel(const KinoParamsDev* __restrict__ Pp, LatticeDev lat,
                                                             const MapDev* __restrict__ Mp, KinoArena* arenas,
                                                             KinoBatchDev bt, int table_bits,
-                                                            const __grid_constant__ CUtensorMap tmap, int use_tma) {
+                                                            const __grid_constant__ CUtensorMap tmap, int use_tma, float slab_margin) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SearchSmem& s = *reinterpret_cast<SearchSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -993,11 +993,17 @@ __global__ void __launch_bounds__(KT, (KT <= 256 ? 2 : 1)) kino_search_kernel(co
                 const int c = __ffs(cand) - 1;
                 cand &= cand - 1;
                 if (!((mask >> c) & 1u)) continue;
-                {  // float slab test: || E^-1 d ||^2 = (|d|^2 - w^2)/r^2 + w^2/h^2, w = d . b3; 1 % margin >> float error
+                {  // float slab test: || E^-1 d ||^2 = (|d|^2 - w^2)/r^2 + w^2/h^2, w = d . b3; slab_margin >> float error
                   const float4 bf = __ldg(lat.b3f + (ab * na + c));
                   const float dz = q.z - fz[c];
                   const float w = (dx * bf.x + dy * bf.y) + dz * bf.z, w2 = w * w;
-                  if (((dxy2 + dz * dz) - w2) * P.inv_r2f + w2 * P.inv_h2f > 1.01f) continue;
+                  const float val = ((dxy2 + dz * dz) - w2) * P.inv_r2f + w2 * P.inv_h2f;
+                  if (val > 1.f + slab_margin) continue;
+                  // clearly inside: the float error of `val` is far below the margin (1 %, widened by the host for maps
+                  // whose coordinates are coarse in float), so the exact expression is < 1 as well.  Deciding it here
+                  // keeps the f64 path (table loads, executed by one lane at a time when lanes diverge) to the thin shell
+                  // around the surface.
+                  if (val < 1.f - slab_margin) { s.state[ab * na + c] = ST_REJECT; mask &= ~(1u << c); continue; }
                 }
                 EllipsoidTest t;
                 make_test(t, P, lat, ab * na + c, px, py, s.X[i][2][c]);
@@ -1881,8 +1887,20 @@ int kino_launch_search(uavmp_ctx* ctx, int B, const double* d_sp, const double* 
   CUtensorMap tm;
   memcpy(&tm, ctx->tmap_bytes, sizeof(tm));
   if (ctx->fuse_flags) cudaEventRecord(ctx->ev_fuse[0], st);  // flags zeroed, order sorted: the overlapped QP may start polling
+  // margin of the float ellipsoid filter: 1 %, or more when the map's coordinates are coarse in float (the filter subtracts
+  // float coordinates: error ~ 2 ulp of the largest |coordinate|, amplified by 2 R / min(r, h)^2 in the quadratic form)
+  float slab_margin = 0.01f;
+  {
+    double maxc = 0.0;
+    for (int ax = 0; ax < 3; ax++) maxc = std::max(maxc, std::max(std::fabs(ctx->origin[ax]), std::fabs(ctx->origin[ax] + ctx->map_size[ax])));
+    const double delta = 2.0 * maxc * 1.1920928955078125e-7;
+    const double R = std::max(ctx->kp.robot_r, ctx->kp.robot_h);
+    const double mn = std::min(ctx->kp.robot_r, ctx->kp.robot_h);
+    const double err = 2.0 * R * delta / (mn * mn);
+    slab_margin = (float)std::max(0.01, 4.0 * err + 1e-4);
+  }
   kino_search_kernel<<<grid, KT, sizeof(SearchSmem), st>>>(ctx->d_kparams, lat, ctx->d_map, ctx->d_arenas, bt, bits, tm,
-                                                          (ctx->have_tmap && !getenv("UAVMP_NO_TMA")) ? 1 : 0);
+                                                          (ctx->have_tmap && !getenv("UAVMP_NO_TMA")) ? 1 : 0, slab_margin);
   UAVMP_CUDA(ctx, cudaGetLastError());
   ctx->tm.search_launches = 1;
   return UAVMP_OK;
