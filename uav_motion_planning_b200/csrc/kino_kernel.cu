@@ -1689,7 +1689,9 @@ int kino_build_map(uavmp_ctx* ctx) {
   cudaStream_t st = ctx->stream;
   k_flags_base<<<nblk(nvox, 256), 256, 0, st>>>(ctx->d_occ, ctx->d_flags, nvox);
   UAVMP_CUDA(ctx, cudaMemsetAsync(t0, 0, nvox, st));
-  const int dil = (int)std::floor(box_r * M.inv_res) + 2;
+  // a checkpoint x in voxel i and a cloud point p in voxel j with |p - x| <= box_r on every axis satisfy
+  // (|j - i| - 1) res < box_r, i.e. |j - i| <= floor(box_r / res) + 1: that is the dilation the "near a cloud point" bit needs
+  const int dil = (int)std::floor(box_r * M.inv_res) + 1;
   if (ctx->n_cloud > 0) {
     k_mark_points<<<nblk(ctx->n_cloud, 256), 256, 0, st>>>(ctx->d_cloud, ctx->n_cloud, M, dil, t0);
     k_dilate<<<nblk(nvox, 256), 256, 0, st>>>(t0, t1, M.nx, M.ny, M.nz, 2, dil);
