@@ -1423,21 +1423,32 @@ __global__ void k_mark_points(const float* cloud, int n, MapDev M, int margin, u
   ix = min(max(ix, 0), M.nx - 1); iy = min(max(iy, 0), M.ny - 1); iz = min(max(iz, 0), M.nz - 1);
   mark[((size_t)ix * M.ny + iy) * M.nz + iz] = 1;
 }
-// out = max over [-r, r] along one axis (stride / extent given)
-__global__ void k_dilate(const uint8_t* in, uint8_t* out, int nx, int ny, int nz, int axis, int r) {
+// near[j] = 1 for every voxel j a checkpoint could sit in while a cloud point of marked voxel i is within `reach` of it:
+// a point in voxel i and a position in voxel j are farther apart than sum_a (max(|i_a - j_a| - 1, 0) res)^2, so voxels whose
+// gap vector is longer than reach (in voxels, squared: reach2) need no flag.  Roughly half the cube of the same half-width.
+__global__ void k_scatter_near(const uint8_t* mark, uint8_t* near, int nx, int ny, int nz, int r, double reach2) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t n = (size_t)nx * ny * nz;
-  if (i >= n) return;
-  int z = (int)(i % nz), y = (int)((i / nz) % ny), x = (int)(i / ((size_t)nz * ny));
-  int c = axis == 0 ? x : (axis == 1 ? y : z);
-  int ext = axis == 0 ? nx : (axis == 1 ? ny : nz);
-  size_t stride = axis == 0 ? (size_t)ny * nz : (axis == 1 ? (size_t)nz : 1);
-  uint8_t v = 0;
-  for (int d = -r; d <= r && !v; d++) {
-    int cc = c + d;
-    if (cc >= 0 && cc < ext) v |= in[i + (long long)d * (long long)stride];
+  if (i >= n || !mark[i]) return;
+  const int z = (int)(i % nz), y = (int)((i / nz) % ny), x = (int)(i / ((size_t)nz * ny));
+  for (int dx = -r; dx <= r; dx++) {
+    const int xx = x + dx;
+    if (xx < 0 || xx >= nx) continue;
+    const double gx = (double)max(abs(dx) - 1, 0);
+    for (int dy = -r; dy <= r; dy++) {
+      const int yy = y + dy;
+      if (yy < 0 || yy >= ny) continue;
+      const double gy = (double)max(abs(dy) - 1, 0);
+      if (gx * gx + gy * gy > reach2) continue;
+      for (int dz = -r; dz <= r; dz++) {
+        const int zz = z + dz;
+        if (zz < 0 || zz >= nz) continue;
+        const double gz = (double)max(abs(dz) - 1, 0);
+        if ((gx * gx + gy * gy) + gz * gz > reach2) continue;
+        near[((size_t)xx * ny + yy) * nz + zz] = 1;  // every writer stores 1
+      }
+    }
   }
-  out[i] = v;
 }
 __global__ void k_or_near(uint8_t* flags, const uint8_t* near, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1694,9 +1705,10 @@ int kino_build_map(uavmp_ctx* ctx) {
   const int dil = (int)std::floor(box_r * M.inv_res) + 1;
   if (ctx->n_cloud > 0) {
     k_mark_points<<<nblk(ctx->n_cloud, 256), 256, 0, st>>>(ctx->d_cloud, ctx->n_cloud, M, dil, t0);
-    k_dilate<<<nblk(nvox, 256), 256, 0, st>>>(t0, t1, M.nx, M.ny, M.nz, 2, dil);
-    k_dilate<<<nblk(nvox, 256), 256, 0, st>>>(t1, t0, M.nx, M.ny, M.nz, 1, dil);
-    k_dilate<<<nblk(nvox, 256), 256, 0, st>>>(t0, t1, M.nx, M.ny, M.nz, 0, dil);
+    // ... and, inside that cube, only the voxels whose gap to the point's voxel is within box_r (Euclidean)
+    UAVMP_CUDA(ctx, cudaMemsetAsync(t1, 0, nvox, st));
+    const double reach = box_r * M.inv_res;
+    k_scatter_near<<<nblk(nvox, 256), 256, 0, st>>>(t0, t1, M.nx, M.ny, M.nz, dil, reach * reach * (1.0 + 1e-9));
     k_or_near<<<nblk(nvox, 256), 256, 0, st>>>(ctx->d_flags, t1, nvox);
   }
   // cell list
