@@ -89,3 +89,24 @@ def test_pop_trace_matches(gpu_ctx, world_small):
         n = min(ref["n_pop"], 512)
         assert np.array_equal(ka.pop_trace(q, 512)[:n], ref["trace"][:n])
     ka.setTrace(0)
+
+
+def test_map_far_from_the_origin(gpu_ctx, world_small):
+    """Coordinates around 800 m are coarse in float (ulp 6e-5 m): the host widens the margin of the float ellipsoid filter
+    (kino_launch_search: slab_margin) and the decisions must stay those of the oracle, bit for bit."""
+    import ctypes as C
+    from uav_motion_planning_b200 import _lib
+    from uav_motion_planning_b200.mapgen import World
+    off = np.array([800.0, -640.0, 0.0])
+    cloud = (world_small.cloud.astype(np.float64) + off).astype(np.float32)
+    origin = np.ascontiguousarray(world_small.origin + off)
+    map_size = np.ascontiguousarray(world_small.map_size)
+    dims = tuple(world_small.dims)
+    occ = np.zeros(dims[0] * dims[1] * dims[2], np.int8)
+    rc = _lib.load().uavmp_grid_inflate_host(_lib.ptr(cloud), len(cloud), _lib.ptr(origin), _lib.ptr(map_size),
+                                             world_small.resolution, 0.099, _lib.ptr(occ), *dims)
+    assert rc == 0
+    far = World(occ, dims, origin, map_size, world_small.resolution, cloud)
+    bad, got, *_ = run_case(gpu_ctx, far, 24, seed=5, ctype=1, min_dist=8.0)
+    assert not bad, bad
+    assert (got["status"] == 1).mean() > 0.3
