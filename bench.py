@@ -1,19 +1,26 @@
 #!/usr/bin/env python
-"""bench.py — plans/sec of the batched kino-A* + minimum-snap QP hot path (BASELINE.json metric, configs[1]).
+"""bench.py — plans/sec of the batched kino-A* + minimum-snap QP hot path (BASELINE.json metric).
 
-  python bench.py --gpus N --steps K --warmup W            one rank per GPU (under torchrun for N > 1)
-  python bench.py --impl reference [...]                   the CPU path (oracle restatement of KinoAstar::search + the
-                                                           reference's own OSQP C code), all host threads, rank 0 only
+  python bench.py --gpus N --steps K --warmup W [--config C]   one rank per GPU (under torchrun for N > 1)
+  python bench.py --impl reference [...]                       the CPU path (oracle restatement of KinoAstar::search + the
+                                                               reference's own OSQP C code), all host threads, rank 0 only
 
-A "step" = one pass of the hot path over one batch of B = 4096 synthetic start->goal queries on the 50 x 50 x 10 m
-random-obstacle map @ 0.1 m: KinoAstar::search (launch-file parameters, collision_check_type 1) -> S+1 waypoints ->
-three 8-segment 7th-order minimum-snap QPs (x, y, z) per query.  Every step uses a different seeded batch and the L2
-is flushed (256 MiB write) between steps.  Weak scaling: every rank processes its own B queries per step, the map is
-replicated, and (N > 1) the solved trajectories are all-gathered with NCCL inside the timed region.
+--config 1 (default, BASELINE.json configs[1] — the configuration the metric is quoted on): a "step" = one pass of the hot path
+over one batch of B = 4096 synthetic start->goal queries on the 50 x 50 x 10 m random-obstacle map @ 0.1 m: KinoAstar::search
+(launch-file parameters, collision_check_type 1) -> S+1 waypoints -> three 8-segment 7th-order minimum-snap QPs per query.
+--config 2: configs[2], 32 768 queries per step with collision_check_type 2 (ellipsoid only), same map.
+--config 4: configs[4], QP only: 16 384 16-segment minimum-snap problems per step, eps_abs = eps_rel swept 1e-3 .. 1e-6.
 
-Keys beyond the base contract: `roofline` (the search kernel, algorithmic bytes of SURVEY.md §8(d) / CUDA-event
-duration), `cpu_baseline` (bounded sample of the same workload on the host cores), `e2e` (host buffers through
-uavmp_plan_batch, copies inside the timed region), `clocks`, `gpu_launches`.
+Every step uses a different seeded batch.  The K timed steps are issued through the library's asynchronous entry point
+(uavmp_plan_submit / uavmp_plan_wait) with up to uavmp_plan_max_in_flight() batches in flight: a batch is ONE kernel, and the
+CTAs of batch k + 1 take the SM slots the long tail of batch k leaves idle (cross-batch pipelining), so the timed region is
+K complete batches, first submit to last result, and nothing is skipped.  Weak scaling: every rank processes its own B
+queries per step, the map is replicated, and (N > 1) the solved trajectories of every step are all-gathered with NCCL on a
+side stream inside the timed region.
+
+Keys beyond the base contract: `roofline` (the search kernel: algorithmic bytes of SURVEY.md §8(d) over the timed region),
+`cpu_baseline` (bounded sample of the same workload on the host cores), `e2e` (pinned host buffers through
+uavmp_plan_submit / uavmp_plan_wait, copies inside the timed region), `clocks`, `gpu_launches`.
 """
 import argparse
 import ctypes as C
@@ -30,18 +37,29 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "plans/sec (kino-A* + min-snap QP) batched queries"
-ORDER, SEG, SEG_TIME = 7, 8, 1.0
-MAP = (50.0, 50.0, 10.0)
 NODE_BYTES, HASH_SLOT, HEAP_SLOT = 72, 16, 4  # DESIGN.md "algorithmic bytes"
 
+WORKLOADS = {
+    1: dict(tag="configs[1]", batch=4096, map=(50.0, 50.0, 10.0), map_type=0, ctype=1, order=7, S=8, seg_time=1.0,
+            text="batch 4096 queries, 50x50x10 m random map @0.1 m, kino-A* + 8-seg 7th-order min-snap, per GPU",
+            kino="launch-file params, collision_check_type 1 (grid + ellipsoid)"),
+    2: dict(tag="configs[2]", batch=32768, map=(50.0, 50.0, 10.0), map_type=0, ctype=2, order=7, S=8, seg_time=1.0,
+            text="batch 32768 queries, 50x50x10 m random map @0.1 m, SE(3) ellipsoid collision (r=0.4 h=0.1), kino-A* + 8-seg "
+                 "7th-order min-snap, per GPU",
+            kino="launch-file params, collision_check_type 2 (ellipsoid only)"),
+}
 
-def workload_config(B, n_gpus):
-    return {"workload": "configs[1]: batch 4096 queries, 50x50x10 m random map @0.1 m, kino-A* + 8-seg 7th-order "
-                        "min-snap, per GPU", "batch_per_gpu": B, "global_batch": B * n_gpus, "map": "500x500x100 int8, "
-            "random_forest seed 1", "kino": "launch-file params, collision_check_type 1 (grid + ellipsoid)",
-            "qp": "order 7, S 8, T_i 1.0, OSQP eps 1e-3, 3 axes per plan; QP kernel (one warp per problem) overlapped with the search "
-            "kernel on a second stream, per-query completion flags", "l2": "flushed between steps (256 MiB write) "
-            "and a different query batch every step", "parallelism": f"queries sharded x{n_gpus}, map replicated"}
+
+def workload_config(wl, B, n_gpus):
+    """identical on both arms (the driver compares them)"""
+    return {"workload": f"{wl['tag']}: {wl['text']}", "batch_per_gpu": B, "global_batch": B * n_gpus,
+            "map": "500x500x100 int8, random_forest seed 1", "kino": wl["kino"],
+            "qp": f"order {wl['order']}, S {wl['S']}, T_i {wl['seg_time']}, OSQP eps 1e-3, 3 axes per plan",
+            "batches": "a different seeded query batch every step; steps may overlap in time (GPU: up to 6 batches in flight, "
+                       "CPU: one work queue over all steps), every step's results are complete inside the timed region",
+            "l2": "256 MiB flush write before every step; the per-step working set (>= 5 GB of search arenas + a different "
+                  "query batch) exceeds the 126 MB L2",
+            "parallelism": f"queries sharded x{n_gpus}, map replicated"}
 
 
 def make_batches(world, B, n, rank):
@@ -54,6 +72,16 @@ def search_bytes(c):
     return (1 * c["n_occ_lookup"] + 12 * c["n_cloud_pts_tested"] + HASH_SLOT * c["n_hash_probe"] +
             (NODE_BYTES + HASH_SLOT + HEAP_SLOT) * c["n_insert"] + NODE_BYTES * c["n_update"] +
             (HEAP_SLOT + NODE_BYTES) * c["n_pop"])
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
 
 
 class ClockSampler:
@@ -102,175 +130,220 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------
 # CPU path (oracle): used ONLY by the cpu_baseline leg and by --impl reference
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_plans(world, params, queries, idx, threads):
-    """Run the CPU pipeline for queries[idx] on `threads` host threads; returns (seconds, n_reached, n_solved)."""
+def cpu_plans(world, params, wl, jobs, threads):
+    """Run the CPU pipeline for `jobs` = [(queries, index), ...] on `threads` host threads that pull from ONE queue in the given
+    order (no barrier between steps: a long query does not idle the other threads).  Returns (wall seconds, sum of the threads'
+    busy seconds, n_reached, n_solved)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
     from pipeline_ref import plan_one
-    sp, sv, ep, ev = queries
+    order, S, seg = wl["order"], wl["S"], wl["seg_time"]
     oracles = [oracle_lib.KinoOracle(world, params) for _ in range(threads)]
-    oracle_lib.minctrl_solve(ORDER, SEG, np.arange(SEG + 1.0), [0, 0], [0, 0], np.ones(SEG), bound_jerk=[0, 0])  # dlopen
-    nxt, lock, res = [0], threading.Lock(), []
+    oracle_lib.minctrl_solve(order, S, np.arange(S + 1.0), [0, 0], [0, 0], np.ones(S), bound_jerk=[0, 0])  # dlopen
+    nxt, lock, res, busy = [0], threading.Lock(), [], [0.0] * threads
 
-    def work(o):
+    def work(t):
+        o = oracles[t]
         while True:
             with lock:
                 k = nxt[0]
                 nxt[0] += 1
-            if k >= len(idx):
+            if k >= len(jobs):
                 return
-            q = idx[k]
-            res.append(plan_one(o, sp[q], sv[q], ep[q], ev[q], ORDER, SEG, SEG_TIME)[:2])
+            (sp, sv, ep, ev), q = jobs[k]
+            t0 = time.perf_counter()
+            r = plan_one(o, sp[q], sv[q], ep[q], ev[q], order, S, seg)[:2]
+            busy[t] += time.perf_counter() - t0
+            res.append(r)
 
     t0 = time.perf_counter()
-    ts = [threading.Thread(target=work, args=(o,)) for o in oracles]
+    ts = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
     [t.start() for t in ts]
     [t.join() for t in ts]
     dt = time.perf_counter() - t0
     for o in oracles:
         o.close()
-    return dt, sum(1 for s, _ in res if s == 1), sum(1 for _, k in res if k)
+    return dt, sum(busy), sum(1 for s, _ in res if s == 1), sum(1 for _, k in res if k)
+
+
+def lpt_jobs(batches, n_s):
+    """The first n_s queries of every batch, longest straight-line distance first within a batch (the order the GPU path uses)."""
+    jobs = []
+    for bt in batches:
+        d = np.linalg.norm(bt[0][:n_s] - bt[2][:n_s], axis=1)
+        jobs += [(bt, int(q)) for q in np.argsort(-d, kind="stable")]
+    return jobs
 
 
 def kind_of_cpu_path():
-    return ("port", "search: oracle/kino_ref.cpp (restatement; the reference's kino_astar.cpp needs ROS/Eigen/PCL); "
-            "QP: the reference's vendored OSQP C core compiled unmodified (oracle/_ref) + restated QDLDL")
+    return ("port", "search: oracle/kino_ref.cpp (restatement, pinned against the reference's kino_astar.cpp compiled in "
+            "oracle/_ref when that is built); QP: the reference's vendored OSQP C core compiled unmodified (oracle/_ref) + "
+            "restated QDLDL")
 
 
-def run_reference(args, rank, world_size):
+def cpu_summary(n, wall, busy, threads):
+    return {"plans_per_s_makespan": n / wall, "plans_per_s_busy": n * threads / busy if busy > 0 else None,
+            "thread_busy_frac": busy / (wall * threads), "cpu_model": cpu_model()}
+
+
+def run_reference(args, rank, world_size, wl):
     if rank != 0:
         return
     import uav_motion_planning_b200 as u
     from uav_motion_planning_b200 import _lib
-    world = u.make_world(*MAP, seed=1)  # host-side input generator only
-    params = _lib.KinoParams()
-    u.load().uavmp_kino_params_launch(C.byref(params))
+    world = u.make_world(*wl["map"], seed=1, map_type=wl["map_type"])  # host-only input generator (libuavmp_worldgen.so)
+    params = _lib.launch_params(collision_check_type=wl["ctype"])
     threads = os.cpu_count() or 1
-    n_s = args.cpu_sample or max(64, 4 * threads)
-    batches = make_batches(world, args.batch, args.steps + args.warmup, 0)
-    for i in range(args.warmup):
-        cpu_plans(world, params, batches[i], list(range(min(n_s, 2 * threads))), threads)
-    tot, cnt, reached = 0.0, 0, 0
-    for i in range(args.steps):
-        dt, nr, _ = cpu_plans(world, params, batches[args.warmup + i], list(range(n_s)), threads)
-        tot += dt; cnt += n_s; reached += nr
-    val = cnt / tot
+    # bounded sample: n_s queries of every step's batch, sized so that K steps are ~2-3 minutes of wall time on the host
+    # (mean cost ~0.9 core-seconds per query, p99.9 ~60 core-seconds: one queue over all steps keeps the tail amortised)
+    n_s = args.cpu_sample or int(min(wl["batch"], max(2 * threads, (150.0 * threads / 0.9) // max(args.steps, 1))))
+    batches = make_batches(world, wl["batch"], args.steps + args.warmup, 0)
+    if args.warmup:
+        cpu_plans(world, params, wl, lpt_jobs(batches[:1], min(n_s, 2 * threads)), threads)
+    jobs = lpt_jobs(batches[args.warmup:], n_s)
+    wall, busy, reached, _ = cpu_plans(world, params, wl, jobs, threads)
+    cnt = len(jobs)
+    val = cnt / wall
     kind, how = kind_of_cpu_path()
-    sample = f"first {n_s} queries of each step's 4096-query batch ({args.steps} steps), {threads} threads; {how}"
+    sample = (f"first {n_s} queries of each step's {wl['batch']}-query batch ({args.steps} steps = {cnt} plans), {threads} "
+              f"threads pulling from one queue (longest straight-line distance first within a step); {how}")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "plans/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.batch, args.gpus),
-        "cpu_baseline": {"value": val, "unit": "plans/s", "cores": threads, "kind": kind, "sample": sample,
-                         "reach_end_frac": reached / cnt},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / max(args.steps, 1) * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(wl, wl["batch"], args.gpus),
+        "cpu_baseline": dict({"value": val, "unit": "plans/s", "cores": threads, "kind": kind, "sample": sample,
+                              "reach_end_frac": reached / cnt}, **cpu_summary(cnt, wall, busy, threads)),
         "e2e": {"value": val, "unit": "plans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def run_gpu(args, rank, world_size, local_rank):
+def run_gpu(args, rank, world_size, local_rank, wl):
     import torch
     import torch.distributed as dist
     import uav_motion_planning_b200 as u
-    from uav_motion_planning_b200.planner import plan_batch_dev
+    from uav_motion_planning_b200 import planner
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference "
                          "for the CPU baseline)")
     torch.cuda.set_device(local_rank)
-    if world_size > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=dev)
     ctx = u.Context(local_rank)
-    lib = ctx.lib
-    B, K, W = args.batch, args.steps, args.warmup
-    n = (ORDER + 1) * SEG
-    world = u.make_world(*MAP, seed=1)
+    B, K, W = args.batch or wl["batch"], args.steps, args.warmup
+    order, S, seg = wl["order"], wl["S"], wl["seg_time"]
+    n = (order + 1) * S
+    world = u.make_world(*wl["map"], seed=1, map_type=wl["map_type"])
     ka = u.KinoAstar(ctx)
     ka.setLaunchParams()
+    ka.setParam(collision_check_type=wl["ctype"])
     ka.setGridMap(world)
     batches = make_batches(world, B, K + W, rank)
-    ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    depth = planner.max_in_flight(ctx)
+    lib_stream = torch.cuda.ExternalStream(ctx.stream, device=dev)  # the context's stream: device inputs are ordered after it
+    side = torch.cuda.Stream(device=dev)                            # all-gathers run here, behind each batch's completion
 
     def barrier():
         if world_size > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    with torch.cuda.stream(ext):
-        d_in = [[torch.from_numpy(a).to(dev) for a in bt] for bt in batches]  # resident in HBM before timing
-        d_status = torch.zeros(B, dtype=torch.int32, device=dev)
-        d_solved = torch.zeros(B, dtype=torch.int32, device=dev)
-        d_coef = torch.zeros(B, 3 * n, dtype=torch.float64, device=dev)
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-        if world_size > 1:
-            g_coef = torch.empty(world_size * B, 3 * n, dtype=torch.float64, device=dev)
-            g_stat = torch.empty(world_size * B, dtype=torch.int32, device=dev)
-        torch.cuda.synchronize()
+    # every tensor is allocated on torch's default stream (nothing the caching allocator tracks lives on the library's streams)
+    d_in = [[torch.from_numpy(a).to(dev) for a in bt] for bt in batches]  # resident in HBM before timing
+    ring = [dict(status=torch.zeros(B, dtype=torch.int32, device=dev), solved=torch.zeros(B, dtype=torch.int32, device=dev),
+                 coef=torch.zeros(B, 3 * n, dtype=torch.float64, device=dev)) for _ in range(depth)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    if world_size > 1:
+        for r in ring:
+            r["g_coef"] = torch.empty(world_size * B, 3 * n, dtype=torch.float64, device=dev)
+            r["g_solved"] = torch.empty(world_size * B, dtype=torch.int32, device=dev)
+            r["gathered"] = torch.cuda.Event()
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_in = [[pin(a) for a in bt] for bt in batches]
+    h_ring = [dict(status=torch.zeros(B, dtype=torch.int32).pin_memory(), solved=torch.zeros(B, dtype=torch.int32).pin_memory(),
+                   coef=torch.zeros(B, 3 * n, dtype=torch.float64).pin_memory()) for _ in range(depth)]
+    torch.cuda.synchronize()
 
-        def step_dev(i):
-            sp, sv, ep, ev = d_in[i]
-            flush.fill_(i & 0xff)  # evict the previous step's working set from L2
-            plan_batch_dev(ctx, B, sp.data_ptr(), sv.data_ptr(), ep.data_ptr(), ev.data_ptr(), d_status.data_ptr(),
-                           d_solved.data_ptr(), d_coef.data_ptr(), ORDER, SEG, SEG_TIME)
-            if world_size > 1:  # "all-gather of solved trajectories only"
-                dist.all_gather_into_tensor(g_coef, d_coef)
-                dist.all_gather_into_tensor(g_stat, d_solved)
+    def gather(r, src_coef, src_solved):
+        """"all-gather of solved trajectories only", on the side stream, ordered behind the batch that produced them"""
+        with torch.cuda.stream(side):
+            dist.all_gather_into_tensor(r["g_coef"], src_coef)
+            dist.all_gather_into_tensor(r["g_solved"], src_solved)
+            r["gathered"].record(side)
 
-        for i in range(W):
-            step_dev(i)
-        barrier()
-        clocks = ClockSampler(local_rank)
-        if rank == 0:
-            clocks.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        search_ms, qp_ms, bytes_a, pops, launches = [], [], [], [], 0
-        e0.record(ext)
-        for i in range(W, W + K):
-            step_dev(i)
-            t = ctx.timings()  # resolves the library's own CUDA events (search / QP) for this step
-            search_ms.append(t["search_ms"]); qp_ms.append(t["qp_ms"])
-            launches += t["search_launches"] + t["qp_launches"] + t["aux_launches"]
-            c = ka.counters()
-            bytes_a.append(search_bytes(c)); pops.append(c["n_pop"])
-        e1.record(ext)
-        barrier()
-        ms = e0.elapsed_time(e1)
-        reached = int((d_status == 1).sum().item())
-        solved = int(d_solved.sum().item())
-
-        # ---- e2e: host (pinned) buffers through uavmp_plan_batch, copies inside the timed region -------------
-        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        h_in = [[pin(a) for a in bt] for bt in batches]
-        h_status = torch.zeros(B, dtype=torch.int32).pin_memory()
-        h_solved = torch.zeros(B, dtype=torch.int32).pin_memory()
-        h_coef = torch.zeros(B, 3 * n, dtype=torch.float64).pin_memory()
-        vp = C.c_void_p
-
-        def step_host(i):
-            sp, sv, ep, ev = h_in[i]
-            flush.fill_(i & 0xff)
-            ctx.check(lib.uavmp_plan_batch(ctx.h, B, vp(sp.data_ptr()), vp(sv.data_ptr()), vp(ep.data_ptr()),
-                                           vp(ev.data_ptr()), ORDER, SEG, SEG_TIME, None, vp(h_status.data_ptr()),
-                                           vp(h_solved.data_ptr()), vp(h_coef.data_ptr())))
+    def run_steps(first, count, host_io):
+        """`count` batches through submit / wait with `depth` in flight; returns the uavmp_plan_info of every batch"""
+        live, infos = [], []
+        for i in range(first, first + count):
+            slot = (i - first) % depth
+            if len(live) == depth:
+                infos.append(planner.plan_wait(ctx, live.pop(0)))
+            with torch.cuda.stream(lib_stream):
+                flush.fill_(i & 0xff)  # evict the previous steps' working set from L2 (ordered before this batch)
+                if world_size > 1 and i - first >= depth:
+                    lib_stream.wait_event(ring[slot]["gathered"])  # the ring entry is free once its gather has read it
+            if host_io:
+                sp, sv, ep, ev = h_in[i]
+                o = h_ring[slot]
+            else:
+                sp, sv, ep, ev = d_in[i]
+                o = ring[slot]
+            t = planner.plan_submit(ctx, B, sp.data_ptr(), sv.data_ptr(), ep.data_ptr(), ev.data_ptr(), o["status"].data_ptr(),
+                                    o["solved"].data_ptr(), o["coef"].data_ptr(), order=order, S=S, seg_time=seg,
+                                    device_io=not host_io)
+            live.append(t)
             if world_size > 1:
-                d_coef.copy_(h_coef, non_blocking=True)
-                dist.all_gather_into_tensor(g_coef, d_coef)
+                if host_io:  # results land in pinned host memory: they go back up for the gather once the batch is complete
+                    planner.plan_stream_wait(ctx, t, side.cuda_stream)
+                    with torch.cuda.stream(side):
+                        ring[slot]["coef"].copy_(o["coef"], non_blocking=True)
+                        ring[slot]["solved"].copy_(o["solved"], non_blocking=True)
+                else:
+                    planner.plan_stream_wait(ctx, t, side.cuda_stream)
+                gather(ring[slot], ring[slot]["coef"], ring[slot]["solved"])
+        while live:
+            infos.append(planner.plan_wait(ctx, live.pop(0)))
+        side.synchronize()
+        return infos
 
-        for i in range(min(W, 2)):
-            step_host(i)
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(W, W + K):
-            step_host(i)
-        barrier()
-        e2e_s = time.perf_counter() - t0
+    # ---- value: inputs resident in HBM --------------------------------------------------------------------------
+    run_steps(0, W, False)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(lib_stream)          # the first batch is ordered after this event
+    t0 = time.perf_counter()
+    infos = run_steps(W, K, False)  # returns when every batch (and gather) of the K steps is complete
+    e1.record(lib_stream)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ms = e0.elapsed_time(e1)
+    last = ring[(K - 1) % depth]
+    reached = int((last["status"] == 1).sum().item())
+    solved = int(last["solved"].sum().item())
+    bytes_a = [search_bytes(i["counters"]) for i in infos]
+    pops = [i["counters"]["n_pop"] for i in infos]
+    launch_ms = [i["timings"]["search_ms"] for i in infos]
+    launches = sum(i["timings"]["search_launches"] + i["timings"]["qp_launches"] + i["timings"]["aux_launches"] for i in infos)
+    flags = [i["error_flags"] for i in infos]
+
+    # ---- e2e: pinned host buffers through uavmp_plan_submit / wait, copies inside the timed region ----------------
+    run_steps(0, min(W, 2), True)
+    barrier()
+    t0 = time.perf_counter()
+    run_steps(W, K, True)
+    barrier()
+    e2e_s = time.perf_counter() - t0
     clk = clocks.stop() if rank == 0 else None
 
-    t_ms = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    t_ms = torch.tensor([ms, e2e_s * 1e3, wall_ms], dtype=torch.float64, device=dev)
     if world_size > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = t_ms.tolist()
+    ms, e2e_ms, wall_ms = t_ms.tolist()
     total_q = B * world_size * K
     value = total_q / (ms / 1e3)
     e2e_val = total_q / (e2e_ms / 1e3)
@@ -281,8 +354,9 @@ def run_gpu(args, rank, world_size, local_rank):
             peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        s_ms = float(np.mean(search_ms))
-        achieved = float(np.mean(bytes_a)) / (s_ms * 1e-3) / 1e9
+        # the K launches overlap each other (that is the point): the kernel's achieved rate is all their algorithmic bytes over
+        # the timed region; `launch_ms_mean` is the CUDA-event duration of one launch on its own stream, neighbours included
+        achieved = float(np.sum(bytes_a)) / (ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
@@ -290,61 +364,130 @@ def run_gpu(args, rank, world_size, local_rank):
         out = {
             "metric": METRIC, "value": value, "unit": "plans/s", "n_gpus": world_size, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(B, world_size),
+            "data": "synthetic", "config": workload_config(wl, B, world_size),
+            "execution": f"uavmp_plan_submit / uavmp_plan_wait, {depth} batches in flight; the QP of a query is solved inside the search "
+                         "kernel by the CTA that finished it (one warp per 1-D problem)",
             "e2e": {"value": e2e_val, "unit": "plans/s", "h2d_bytes_per_step": B * 12 * 8,
                     "d2h_bytes_per_step": B * (3 * n * 8 + 8), "ms_per_step": e2e_ms / K},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "kino_search_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "roofline": {"kernel": "kino_search_kernel (search + in-kernel QP)", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel_ms": s_ms, "kernel_share_of_step": s_ms / (ms / K),
+                         "kernel_ms": ms / K, "launch_ms_mean": float(np.mean(launch_ms)),
+                         "launches_overlapping": float(np.mean(launch_ms)) / (ms / K),
+                         "kernel_share_of_step": 1.0,
                          "algorithmic_bytes_per_launch": float(np.mean(bytes_a)),
-                         "expansions_per_s": float(np.mean(pops)) / (s_ms * 1e-3), "qp_exposed_ms": float(np.mean(qp_ms))},
-            "clocks": clk,
-            "result_check": {"reach_end_frac_last_step": reached / B, "qp_solved_frac_last_step": solved / B},
+                         "expansions_per_s": float(np.sum(pops)) / (ms * 1e-3),
+                         "qp": {"problems_per_s": 3.0 * solved / B * total_q / world_size / (ms * 1e-3),
+                                "algorithmic_bytes_per_problem": 8 * ((S + 1) + 6 + S) + 8 * n,
+                                "note": "on-chip (one warp per problem, workspace in shared memory): the QP's HBM traffic is its "
+                                        "inputs and outputs only"}},
+            "clocks": clk, "wall_ms_per_step": wall_ms / K,
+            "result_check": {"reach_end_frac_last_step": reached / B, "qp_solved_frac_last_step": solved / B,
+                             "error_flags": int(np.bitwise_or.reduce(flags))},
         }
         if world_size == 1 and not args.no_cpu:
-            from uav_motion_planning_b200 import _lib
             threads = os.cpu_count() or 1
-            n_s = args.cpu_sample or max(64, 4 * threads)
-            dt, nr, _ = cpu_plans(world, ka.params, batches[W], list(range(n_s)), threads)
+            n_s = args.cpu_sample or min(B, 16 * threads)  # ~15 s of host time at ~0.9 core-seconds per query
+            jobs = lpt_jobs([batches[W]], n_s)
+            wall, busy, _, _ = cpu_plans(world, ka.params, wl, jobs, threads)
             kind, how = kind_of_cpu_path()
-            out["cpu_baseline"] = {"value": n_s / dt, "unit": "plans/s", "cores": threads, "kind": kind,
-                                   "sample": f"first {n_s} queries of the first timed batch, {threads} threads; {how}"}
+            out["cpu_baseline"] = dict({"value": len(jobs) / wall, "unit": "plans/s", "cores": threads, "kind": kind,
+                                        "sample": f"first {n_s} queries of the first timed batch, {threads} threads pulling "
+                                                  f"from one queue; {how}"}, **cpu_summary(len(jobs), wall, busy, threads))
         print(json.dumps(out), flush=True)
-    # Orderly teardown.  The tensors above were allocated while the library's stream was torch's current stream: the caching
-    # allocator (and NCCL's record_stream) records events on that stream when they are freed, so they must go BEFORE the
-    # library context destroys the stream; a 2-GPU run crashed at exit ("context is destroyed") before this ordering existed.
-    del d_in, d_status, d_solved, d_coef, flush, h_in, h_status, h_solved, h_coef
-    if world_size > 1:
-        del g_coef, g_stat
+    # Orderly teardown: tensors first, then NCCL, then the library context (its streams die with it).
+    del d_in, ring, flush, h_in, h_ring
     torch.cuda.synchronize()
-    torch.cuda.empty_cache()
     if world_size > 1:
         dist.barrier()
         dist.destroy_process_group()
+    del lib_stream
     ka = None
+    ctx.sync()
     ctx.close()
-    sys.stdout.flush()
-    os._exit(0)  # skip interpreter finalisers: nothing left to do, and nothing may touch the destroyed stream afterwards
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_qp_sweep(args, rank, world_size, local_rank):
+    """configs[4]: the solver-bound regime.  16 384 one-dimensional 16-segment minimum-snap QPs per step, random-walk waypoints,
+    T_i ~ U(0.5, 2), eps_abs = eps_rel in {1e-3, 1e-4, 1e-5, 1e-6}, adaptive_rho_interval 100."""
+    import torch
+    import uav_motion_planning_b200 as u
+    from uav_motion_planning_b200.minimum_control import MinimumControl, default_settings
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
+    if rank != 0:
+        return
+    torch.cuda.set_device(local_rank)
+    ctx = u.Context(local_rank)
+    B, S, order = args.batch or 16384, 16, 7
+    K, W = args.steps, args.warmup
+    mc = MinimumControl(ctx, order=order)
+    rng = np.random.default_rng(5)
+    z = np.zeros((B, 2))
+    sweep = []
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    for eps in (1e-3, 1e-4, 1e-5, 1e-6):
+        st = default_settings(eps_abs=eps, eps_rel=eps, adaptive_rho_interval=100)
+        ms, iters, solved = [], [], []
+        for i in range(W + K):
+            pos = np.cumsum(rng.normal(size=(B, S + 1)), axis=1)
+            T = rng.uniform(0.5, 2.0, size=(B, S))
+            r = mc.solve_batch(pos, z, z, T, bound_jerk=z, settings=st)
+            if i >= W:
+                ms.append(ctx.timings()["qp_ms"]); iters.append(float(r["iters"].mean())); solved.append(float(r["solved"].mean()))
+        sweep.append({"eps": eps, "kernel_ms": float(np.mean(ms)), "problems_per_s": B / (np.mean(ms) * 1e-3),
+                      "iters_mean": float(np.mean(iters)), "qp_iters_per_s": B * np.mean(iters) / (np.mean(ms) * 1e-3),
+                      "solved_frac": float(np.mean(solved))})
+    clk = clocks.stop()
+    base = sweep[0]
+    # SURVEY.md §8(d): flops per ADMM iteration ~ 4 nnz(L) + 2 nnz(A) + 12 (n + m); order 7, S 16: nnzL 1201, nnzA 786, n 128, m 83
+    flops_iter = 4 * 1201 + 2 * 786 + 12 * (128 + 83)
+    out = {"metric": "QP problems/sec (16-seg min-snap, one axis), ADMM sweep", "value": base["problems_per_s"], "unit": "problems/s",
+           "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": base["kernel_ms"], "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "configs[4]: ADMM iteration sweep, 16-seg 7th-order min-snap, eps_abs = eps_rel 1e-3 -> 1e-6, batch "
+                                  f"{B}, 1xB200 (solver-bound regime); random-walk waypoints N(0,1), T_i U(0.5,2), adaptive_rho_interval 100",
+                      "batch_per_gpu": B}, "sweep": sweep,
+           "roofline": {"kernel": "qp_solve_kernel / qp_solve_warp_kernel", "bound": "hbm",
+                        "achieved": B * (8 * ((S + 1) + 6 + S) + 8 * (order + 1) * S) / (base["kernel_ms"] * 1e-3) / 1e9,
+                        "peak": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0,
+                        "unit": "GB/s", "traffic": None,
+                        "fp64": {"achieved_gflops": [s["qp_iters_per_s"] * flops_iter / 1e9 for s in sweep],
+                                 "flops_per_iteration": flops_iter, "note": "latency-bound sparse triangular solves; FP64 peak of a B200 "
+                                 "is ~37 TFLOP/s nominal"}},
+           "clocks": clk, "gpu_launches": 4 * (K + W)}
+    out["roofline"]["frac"] = out["roofline"]["achieved"] / out["roofline"]["peak"]
+    print(json.dumps(out), flush=True)
+    ctx.close()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=4096, help="queries per GPU per step (configs[1]: 4096)")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (0: auto)")
+    ap.add_argument("--config", type=int, default=1, choices=[1, 2, 4], help="BASELINE.json configs[N] (default 1: the metric's)")
+    ap.add_argument("--batch", type=int, default=0, help="queries per GPU per step (0: the configuration's own)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="queries per step in the CPU sample (0: auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.config == 4:
+        if args.impl == "reference":
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "configs[4] is a kernel sweep; the reference arm times configs[1]"}))
+            return
+        return run_qp_sweep(args, rank, world_size, local_rank)
+    wl = WORKLOADS[args.config]
     if args.impl == "reference":
-        run_reference(args, rank, world_size)
+        run_reference(args, rank, world_size, wl)
     else:
-        run_gpu(args, rank, world_size, local_rank)
+        run_gpu(args, rank, world_size, local_rank, wl)
 
 
 if __name__ == "__main__":

@@ -70,18 +70,6 @@ typedef struct {
   double adaptive_rho_tolerance;
 } uavmp_osqp_settings;
 
-/* synthetic world generator parameters (host utility; random_forest.cpp:509-535, simulator.xml:16-41) */
-typedef struct {
-  int map_type; /* 0 random pillars + rings, 2 two-slab wall */
-  uint32_t seed;
-  double x_size, y_size, resolution;
-  double init_x, init_y, init_radius;
-  int polar_num, circle_num;
-  double w_l, w_h, h_l, h_h;
-  double radius_l, radius_h, z_l, z_h, theta;
-  double wall_x, wall_y, wall_w;
-} uavmp_mapgen_params;
-
 /* per-call device timings, milliseconds, CUDA events on the context's stream */
 typedef struct {
   float h2d_ms, search_ms, path_ms, qp_ms, d2h_ms, total_ms;
@@ -93,12 +81,20 @@ typedef struct {
   long long n_pop, n_occ_lookup, n_cloud_pts_tested, n_hash_probe, n_insert, n_update, n_heuristic, n_shot;
 } uavmp_kino_counters;
 
+/* what uavmp_plan_wait reports about one batch of the asynchronous pipeline */
+typedef struct {
+  int error_flags; /* 0, or bits: 1 voxel index outside the key range, 2 path with too many nodes, 4 path longer than path_cap */
+  uavmp_kino_counters counters;
+  uavmp_timings timings; /* CUDA events on the batch's own stream; batches in flight overlap, so their durations do too */
+} uavmp_plan_info;
+
 /* ---- context ------------------------------------------------------------------------------------- */
 int uavmp_ctx_create(uavmp_ctx** out, int device);
 void uavmp_ctx_destroy(uavmp_ctx* ctx);
 const char* uavmp_last_error(const uavmp_ctx* ctx);
 /* the cudaStream_t every kernel of this context is launched on (for external CUDA events) */
 void* uavmp_ctx_stream(uavmp_ctx* ctx);
+/* waits for everything issued so far, batches in flight included; returns the error of an asynchronous batch, if any */
 int uavmp_ctx_sync(uavmp_ctx* ctx);
 const char* uavmp_version(void);
 
@@ -135,7 +131,10 @@ int uavmp_kino_get_paths(uavmp_ctx* ctx, double* path_xyz, long long cap_points)
 /* ordered popped voxel indices of query q of the last batch (B*pop_cap*3 ints kept on device when tracing is on) */
 int uavmp_kino_set_trace(uavmp_ctx* ctx, int pop_cap);
 int uavmp_kino_get_trace(uavmp_ctx* ctx, int q, int32_t* pop_idx_xyz, int cap);
+/* counters of the most recently completed batch */
 int uavmp_kino_get_counters(uavmp_ctx* ctx, uavmp_kino_counters* out);
+/* capacity of the per-query path staging, in sampled points (default 1024; a longer path fails its batch with UAVMP_ECAP) */
+int uavmp_kino_set_path_cap(uavmp_ctx* ctx, int points);
 
 /* ---- hot path (b): batched MinimumControl::solve ---------------------------------------------------- */
 /* order: 5 (minimum jerk, the reference) or 7 (minimum snap, extension §9.3).  S segments.
@@ -155,10 +154,27 @@ int uavmp_minctrl_solve_batch(uavmp_ctx* ctx, int order, int S, int B, const dou
 int uavmp_plan_batch(uavmp_ctx* ctx, int B, const double* start_pt, const double* start_vel, const double* end_pt,
                      const double* end_vel, int order, int S, double seg_time, const uavmp_osqp_settings* settings,
                      int* search_status, int* qp_solved, double* coef);
-/* same, every pointer already in device memory (inputs resident in HBM; outputs stay there) */
+/* same, every pointer already in device memory (inputs resident in HBM; outputs stay there).  Asynchronous: ordered after the
+ * work already on the context's stream, and the context's stream waits for it; an error flag raised by the batch is returned by
+ * the next uavmp_plan_batch_dev / uavmp_ctx_sync / uavmp_get_timings call. */
 int uavmp_plan_batch_dev(uavmp_ctx* ctx, int B, const double* d_start_pt, const double* d_start_vel,
                          const double* d_end_pt, const double* d_end_vel, int order, int S, double seg_time,
                          const uavmp_osqp_settings* settings, int* d_search_status, int* d_qp_solved, double* d_coef);
+
+/* Asynchronous form with several batches in flight.  A batch is ONE kernel (the CTA that finishes a query also solves its three
+ * QPs), each batch runs on its own stream and its CTAs take search arenas from a shared pool, so the CTAs of batch k + 1 fill the
+ * SMs the long tail of batch k leaves idle.  uavmp_plan_submit returns at once with a ticket; the outputs (and, for host
+ * pointers, the copies into them) are complete when uavmp_plan_wait(ticket) returns.  At most uavmp_plan_max_in_flight()
+ * tickets may be outstanding.  Host buffers should be page-locked, otherwise the copies serialise the batches.
+ * flags: UAVMP_PLAN_DEVICE_IO = every pointer is device memory and the inputs are ordered after the work already on the
+ * context's stream; uavmp_plan_stream_wait makes a CUDA stream of the caller wait for the batch without blocking the host. */
+#define UAVMP_PLAN_DEVICE_IO 1u
+int uavmp_plan_submit(uavmp_ctx* ctx, int B, const double* start_pt, const double* start_vel, const double* end_pt,
+                      const double* end_vel, int order, int S, double seg_time, const uavmp_osqp_settings* settings,
+                      unsigned flags, int* search_status, int* qp_solved, double* coef, long long* ticket);
+int uavmp_plan_wait(uavmp_ctx* ctx, long long ticket, uavmp_plan_info* info /* nullable */);
+int uavmp_plan_stream_wait(uavmp_ctx* ctx, long long ticket, void* cuda_stream);
+int uavmp_plan_max_in_flight(void);
 
 /* ---- consumer of the coefficients: PolyTraj::evaluatePos / Vel / Acc (traj_utils/poly_traj.hpp:74-168), batched ------- */
 /* coef: B x 3 x S x (order+1) (axis-major per trajectory == uavmp_plan_batch's layout); times: B x S segment durations;
@@ -174,11 +190,7 @@ int uavmp_get_timings(uavmp_ctx* ctx, uavmp_timings* out);
 int uavmp_kino_set_profile(uavmp_ctx* ctx, int on);
 int uavmp_kino_get_profile(uavmp_ctx* ctx, unsigned long long phase_cycles[16], long long* query_cycles, int cap, int* grid);
 
-/* ---- host utilities (not on the hot path) ----------------------------------------------------------- */
-void uavmp_mapgen_params_default(uavmp_mapgen_params* p, double x_size, double y_size, uint32_t seed);
-int uavmp_mapgen_cloud(const uavmp_mapgen_params* p, float* cloud_xyz, int cap); /* returns point count */
-int uavmp_grid_inflate_host(const float* cloud_xyz, int n, const double origin[3], const double map_size[3],
-                            double resolution, double obstacles_inflation, int8_t* occ_inflate, int nx, int ny, int nz);
+/* ---- test support ------------------------------------------------------------------------------------ */
 /* device-evaluated csrc/fpmath.h (op 0 cbrt, 1 acos, 2 cos, 3 powi) for host/device bit-parity tests */
 int uavmp_fpmath_eval(uavmp_ctx* ctx, int op, int n_pow, const double* x, double* y, long long n);
 

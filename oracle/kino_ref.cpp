@@ -372,6 +372,14 @@ struct oracle_kino {
     std::unordered_map<I3, Node*, I3Hash> close_list, expanded_list;
     memset(&cnt, 0, sizeof(cnt));
     uint64_t pop_hash = 0xcbf29ce484222325ull;
+    // digest of every position the search itself passes to isInMap (kino_astar.cpp:176), in call order: the same fingerprint
+    // oracle/shim/plan_env/grid_map.h takes of the UNMODIFIED reference search compiled in oracle/_ref/libkino_ref.so
+    uint64_t lookup_digest = 0xcbf29ce484222325ull, n_in_map_calls = 0;
+    auto fold_lookup = [&](const V3& q) {
+      const double c[3] = {q.x, q.y, q.z};
+      for (int i = 0; i < 3; i++) { lookup_digest ^= fpm::to_bits(c[i]); lookup_digest *= 0x100000001b3ull; lookup_digest ^= lookup_digest >> 29; }
+      n_in_map_calls++;
+    };
     int n_pop = 0;
     auto finish = [&](int status) {
       res->status = status;
@@ -379,6 +387,8 @@ struct oracle_kino {
       res->n_pop = n_pop;
       res->pop_hash = pop_hash;
       res->counters = cnt;
+      res->lookup_digest = lookup_digest;
+      res->n_in_map_calls = (long long)n_in_map_calls;
       return status;
     };
 
@@ -450,6 +460,7 @@ struct oracle_kino {
               double t = i * p.time_step_size;
               StateTransit(x0, xt, ut, t);
               V3 tmp_pos{xt[0], xt[1], xt[2]};
+              fold_lookup(tmp_pos);
               if (isInMap(tmp_pos) == false) { flag = true; break; }
               switch (p.collision_check_type) {
                 case 1:

@@ -30,6 +30,8 @@ typedef struct {
   double shot_duration;
   uint64_t pop_hash; /* digest of the ordered pop sequence (voxel index + state bits) */
   oracle_kino_counters counters;
+  uint64_t lookup_digest;   /* digest of the positions the search passes to GridMap::isInMap, in call order */
+  long long n_in_map_calls;
 } oracle_kino_result;
 
 typedef struct oracle_kino oracle_kino;

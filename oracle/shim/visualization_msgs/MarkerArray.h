@@ -1,0 +1,4 @@
+// oracle/shim/visualization_msgs/MarkerArray.h — TEST INFRASTRUCTURE
+#pragma once
+#include <visualization_msgs/Marker.h>
+namespace visualization_msgs { struct MarkerArray { std::vector<Marker> markers; }; }

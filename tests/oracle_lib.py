@@ -25,7 +25,7 @@ class Counters(C.Structure):
 class Result(C.Structure):
     _fields_ = [("status", C.c_int), ("use_node_num", C.c_int), ("n_pop", C.c_int), ("n_path", C.c_int),
                 ("n_path_nodes", C.c_int), ("shot_duration", C.c_double), ("pop_hash", C.c_uint64),
-                ("counters", Counters)]
+                ("counters", Counters), ("lookup_digest", C.c_uint64), ("n_in_map_calls", C.c_longlong)]
 
 
 _lib = None
@@ -82,7 +82,8 @@ class KinoOracle:
         c = res.counters
         return dict(status=res.status, use_node_num=res.use_node_num, n_pop=res.n_pop, pop_hash=res.pop_hash,
                     path=path[:min(res.n_path, path_cap)].copy(), n_path=res.n_path,
-                    trace=trace[:min(res.n_pop, pop_cap)].copy(),
+                    trace=trace[:min(res.n_pop, pop_cap)].copy(), lookup_digest=res.lookup_digest,
+                    n_in_map_calls=res.n_in_map_calls,
                     counters={k: getattr(c, k) for k, _ in Counters._fields_})
 
     def close(self):

@@ -22,6 +22,30 @@ def test_header_and_binding_agree():
     assert declared_symbols() == sorted(_lib.SYMBOLS)
 
 
+def test_worldgen_library_is_separate_and_complete():
+    """The input generator lives in its own host-only library (include/uavmp_worldgen.h): the CPU reference arm of bench.py
+    must not need the product library for its inputs."""
+    hdr = open(os.path.join(ROOT, "include", "uavmp_worldgen.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    decl = sorted(set(re.findall(r"\b(uavmp_[a-z0-9_]+)\s*\(", hdr)))
+    assert decl == sorted(_lib.WORLDGEN_SYMBOLS)
+    wg = _lib.load_worldgen()
+    for s in decl:
+        assert hasattr(wg, s), s
+    import subprocess
+    out = subprocess.run(["ldd", _lib.WORLDGEN_PATH], capture_output=True, text=True).stdout
+    assert "cuda" not in out.lower()
+    assert not set(decl) & set(_lib.SYMBOLS)
+
+
+def test_python_parameter_tables_match_the_c_tables():
+    lib = u.load()
+    for fn, table in ((lib.uavmp_kino_params_launch, _lib.LAUNCH_PARAMS), (lib.uavmp_kino_params_default, _lib.DEFAULT_PARAMS)):
+        p = _lib.KinoParams()
+        fn(C.byref(p))
+        assert {k: getattr(p, k) for k, _ in _lib.KinoParams._fields_} == table
+
+
 def test_library_exports_every_declared_symbol():
     lib = u.load()
     for s in declared_symbols():

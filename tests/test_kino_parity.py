@@ -103,7 +103,7 @@ def test_map_far_from_the_origin(gpu_ctx, world_small):
     map_size = np.ascontiguousarray(world_small.map_size)
     dims = tuple(world_small.dims)
     occ = np.zeros(dims[0] * dims[1] * dims[2], np.int8)
-    rc = _lib.load().uavmp_grid_inflate_host(_lib.ptr(cloud), len(cloud), _lib.ptr(origin), _lib.ptr(map_size),
+    rc = _lib.load_worldgen().uavmp_grid_inflate_host(_lib.ptr(cloud), len(cloud), _lib.ptr(origin), _lib.ptr(map_size),
                                              world_small.resolution, 0.099, _lib.ptr(occ), *dims)
     assert rc == 0
     far = World(occ, dims, origin, map_size, world_small.resolution, cloud)

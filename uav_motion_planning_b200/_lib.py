@@ -9,6 +9,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libuavmp.so")
+WORLDGEN_PATH = os.path.join(_HERE, "libuavmp_worldgen.so")  # host-only input generator (include/uavmp_worldgen.h)
 
 
 class KinoParams(C.Structure):
@@ -47,18 +48,63 @@ class KinoCounters(C.Structure):
                                             "n_insert", "n_update", "n_heuristic", "n_shot")]
 
 
+class PlanInfo(C.Structure):
+    """uavmp_plan_info: what uavmp_plan_wait reports about one batch."""
+    _fields_ = [("error_flags", C.c_int), ("counters", KinoCounters), ("timings", Timings)]
+
+
 # every symbol include/uavmp.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = [
     "uavmp_ctx_create", "uavmp_ctx_destroy", "uavmp_last_error", "uavmp_ctx_stream", "uavmp_ctx_sync",
     "uavmp_version", "uavmp_kino_params_default", "uavmp_kino_params_launch", "uavmp_osqp_settings_default",
     "uavmp_kino_set_params", "uavmp_map_set", "uavmp_kino_search_batch", "uavmp_kino_get_paths",
     "uavmp_kino_set_trace", "uavmp_kino_get_trace", "uavmp_kino_get_counters", "uavmp_minctrl_solve_batch",
-    "uavmp_plan_batch", "uavmp_plan_batch_dev", "uavmp_get_timings", "uavmp_mapgen_params_default",
-    "uavmp_mapgen_cloud", "uavmp_grid_inflate_host", "uavmp_fpmath_eval", "uavmp_kino_set_profile",
+    "uavmp_plan_batch", "uavmp_plan_batch_dev", "uavmp_get_timings", "uavmp_fpmath_eval", "uavmp_kino_set_profile",
     "uavmp_kino_get_profile", "uavmp_map_set_from_cloud", "uavmp_map_get_occupancy", "uavmp_polytraj_eval_batch",
+    "uavmp_plan_submit", "uavmp_plan_wait", "uavmp_plan_stream_wait", "uavmp_plan_max_in_flight",
+    "uavmp_kino_set_path_cap",
 ]
 
+WORLDGEN_SYMBOLS = ["uavmp_mapgen_params_default", "uavmp_mapgen_cloud", "uavmp_grid_inflate_host"]
+
+# test/launch/test_kino_astar_searching.launch:44-57 and kino_astar.cpp:8-19 — the same tables uavmp_kino_params_launch /
+# uavmp_kino_params_default return (tests/test_abi.py keeps the two in step); here so that host-only code (the CPU reference
+# arm of bench.py) never has to map the CUDA library
+LAUNCH_PARAMS = dict(allocated_node_num=100000, collision_check_type=1, rou_time=50.0, lambda_heu=3.0, goal_tolerance=2.0,
+                     time_step_size=0.075, max_velocity=7.0, max_accelration=10.0, acc_resolution=4.0, sample_tau=0.3,
+                     robot_r=0.4, robot_h=0.1)
+DEFAULT_PARAMS = dict(allocated_node_num=100000, collision_check_type=1, rou_time=1.0, lambda_heu=2.0, goal_tolerance=2.0,
+                      time_step_size=0.1, max_velocity=5.0, max_accelration=7.0, acc_resolution=2.0, sample_tau=0.5,
+                      robot_r=0.2, robot_h=0.1)
+
+
+def launch_params(**overrides):
+    p = KinoParams(**LAUNCH_PARAMS)
+    for k, v in overrides.items():
+        setattr(p, k, v)
+    return p
+
+
 _lib = None
+_wg = None
+
+
+def load_worldgen():
+    """Load libuavmp_worldgen.so (host only, no CUDA): the synthetic-world generator of tests and bench.py."""
+    global _wg
+    if _wg is not None:
+        return _wg
+    if not os.path.exists(WORLDGEN_PATH):
+        raise RuntimeError(f"{WORLDGEN_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(WORLDGEN_PATH)
+    vp = C.c_void_p
+    lib.uavmp_mapgen_params_default.argtypes = [C.POINTER(MapgenParams), C.c_double, C.c_double, C.c_uint32]
+    lib.uavmp_mapgen_params_default.restype = None
+    lib.uavmp_mapgen_cloud.argtypes = [C.POINTER(MapgenParams), vp, C.c_int]
+    lib.uavmp_grid_inflate_host.argtypes = [vp, C.c_int, vp, vp, C.c_double, C.c_double, vp, C.c_int, C.c_int,
+                                            C.c_int]
+    _wg = lib
+    return lib
 
 
 def load():
@@ -97,12 +143,12 @@ def load():
                                      C.POINTER(OsqpSettings), vp, vp, vp]
     lib.uavmp_plan_batch_dev.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_double,
                                          C.POINTER(OsqpSettings), vp, vp, vp]
+    lib.uavmp_plan_submit.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_double,
+                                      C.POINTER(OsqpSettings), C.c_uint, vp, vp, vp, C.POINTER(C.c_longlong)]
+    lib.uavmp_plan_wait.argtypes = [vp, C.c_longlong, C.POINTER(PlanInfo)]
+    lib.uavmp_plan_stream_wait.argtypes = [vp, C.c_longlong, vp]
+    lib.uavmp_kino_set_path_cap.argtypes = [vp, C.c_int]
     lib.uavmp_get_timings.argtypes = [vp, C.POINTER(Timings)]
-    lib.uavmp_mapgen_params_default.argtypes = [C.POINTER(MapgenParams), C.c_double, C.c_double, C.c_uint32]
-    lib.uavmp_mapgen_params_default.restype = None
-    lib.uavmp_mapgen_cloud.argtypes = [C.POINTER(MapgenParams), vp, C.c_int]
-    lib.uavmp_grid_inflate_host.argtypes = [vp, C.c_int, vp, vp, C.c_double, C.c_double, vp, C.c_int, C.c_int,
-                                            C.c_int]
     lib.uavmp_fpmath_eval.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_longlong]
     lib.uavmp_map_set_from_cloud.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_double, C.c_double]
     lib.uavmp_map_get_occupancy.argtypes = [vp, vp, C.c_longlong]
@@ -129,7 +175,7 @@ class UavmpError(RuntimeError):
 
 
 class Context:
-    """Owns one uavmp_ctx (one CUDA device, one stream)."""
+    """Owns one uavmp_ctx (one CUDA device)."""
 
     def __init__(self, device=0):
         self.lib = load()
@@ -158,6 +204,9 @@ class Context:
     @property
     def stream(self):
         return self.lib.uavmp_ctx_stream(self.h)
+
+    def sync(self):
+        return self.check(self.lib.uavmp_ctx_sync(self.h))
 
     def timings(self):
         t = Timings()

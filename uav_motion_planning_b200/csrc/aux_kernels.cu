@@ -91,7 +91,13 @@ int uavmp_map_set_from_cloud(uavmp_ctx* ctx, const float* cloud_xyz, int n_cloud
                              const double map_size[3], double resolution, double obstacles_inflation) {
   if (!ctx || !cloud_xyz || n_cloud <= 0 || nx <= 0 || ny <= 0 || nz <= 0 || !(resolution > 0)) return UAVMP_EINVAL;
   if (nx >= (1 << 17) || ny >= (1 << 17) || nz >= (1 << 17)) return uavmp_fail(ctx, UAVMP_EINVAL, "grid dimension too large");
+  {
+    int r = uavmp_map_check_geometry(ctx, nx, ny, nz, origin, map_size, resolution);
+    if (r) return r;
+  }
   cudaSetDevice(ctx->device);
+  drain_all(ctx);
+  ctx->have_map = false;
   const size_t nvox = (size_t)nx * ny * nz;
   if (ctx->d_occ) { cudaFree(ctx->d_occ); ctx->d_occ = nullptr; }
   if (ctx->d_flags) { cudaFree(ctx->d_flags); ctx->d_flags = nullptr; }

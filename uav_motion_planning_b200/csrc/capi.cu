@@ -7,20 +7,20 @@
 #include <algorithm>
 #include <vector>
 
+#include "qp_plan.h"
 #include "uavmp_internal.h"
 
 int kino_fpmath_eval(uavmp_ctx* ctx, int op, int npow, const double* x, double* y, long long n);
 // qp_kernel.cu
-int qp_solve_batch_dev(uavmp_ctx* ctx, int order, int S, int B, const double* d_pos, const double* d_bv,
-                       const double* d_ba, const double* d_bj, const double* d_T, const uavmp_osqp_settings* st,
-                       double* d_coef, int* d_solved, int* d_status, int* d_iters);
-int qp_waypoints_from_paths(uavmp_ctx* ctx, int B, int S, double seg_time, const double* d_sv, const double* d_ev,
-                            int order, double** d_pos, double** d_bv, double** d_ba, double** d_bj, double** d_T);
-int qp_scatter_plan_outputs(uavmp_ctx* ctx, int B, int order, int S, const int* d_solved3, const double* d_coef3,
+int qp_solve_batch_dev(uavmp_ctx* ctx, cudaStream_t stream, QpScratch& scr, int* launches, int order, int S, int B,
+                       const double* d_pos, const double* d_bv, const double* d_ba, const double* d_bj, const double* d_T,
+                       const uavmp_osqp_settings* st, double* d_coef, int* d_solved, int* d_status, int* d_iters);
+int qp_waypoints_from_paths(uavmp_ctx* ctx, PlanSlot& sl, int B, int S, double seg_time, const double* d_sv, const double* d_ev,
+                            double** d_pos, double** d_bv, double** d_ba, double** d_bj, double** d_T);
+int qp_scatter_plan_outputs(uavmp_ctx* ctx, PlanSlot& sl, int B, int order, int S, const int* d_solved3, const double* d_coef3,
                             int* d_qp_solved, double* d_coef);
+int qp_get_plan_dev(uavmp_ctx* ctx, int order, int S, const QpPlanDev** out);
 void qp_free_plans(uavmp_ctx* ctx);
-int qp_launch_fused(uavmp_ctx* ctx, int order, int S, int B, double seg_time, const double* d_sv, const double* d_ev,
-                    const int* d_order, const uavmp_osqp_settings* st, double* d_coef, int* d_qp_solved, bool prepare_only);
 
 int ensure_bytes(uavmp_ctx* ctx, void** p, size_t* have, size_t want) {
   if (*have >= want) return UAVMP_OK;
@@ -29,6 +29,43 @@ int ensure_bytes(uavmp_ctx* ctx, void** p, size_t* have, size_t want) {
   UAVMP_CUDA(ctx, cudaMalloc(p, want));
   *have = want;
   return UAVMP_OK;
+}
+
+// ---- batches in flight -------------------------------------------------------------------------------------------------
+static int error_from_flag(uavmp_ctx* ctx, int flag) {
+  if (flag & 1) return uavmp_fail(ctx, UAVMP_ECAP, "voxel index outside the 18-bit key range");
+  if (flag & 2) return uavmp_fail(ctx, UAVMP_ECAP, "path has more than %d nodes", UAVMP_MAXPRIM);
+  if (flag & 4) return uavmp_fail(ctx, UAVMP_ECAP, "path longer than path_cap=%d points (uavmp_kino_set_path_cap)", ctx->path_cap);
+  return UAVMP_OK;
+}
+
+// block until the batch of `sl` is complete, publish its info as "the last call" and free the slot
+static int slot_finish(uavmp_ctx* ctx, PlanSlot& sl, uavmp_plan_info* info) {
+  if (!sl.in_flight) return UAVMP_OK;
+  UAVMP_CUDA(ctx, cudaEventSynchronize(sl.ev[4]));
+  sl.in_flight = false;
+  uavmp_timings& t = ctx->tm;
+  memset(&t, 0, sizeof(t));
+  cudaEventElapsedTime(&t.h2d_ms, sl.ev[0], sl.ev[1]);
+  cudaEventElapsedTime(&t.search_ms, sl.ev[1], sl.ev[2]);
+  cudaEventElapsedTime(&t.d2h_ms, sl.ev[2], sl.ev[3]);
+  cudaEventElapsedTime(&t.total_ms, sl.ev[0], sl.ev[4]);
+  t.search_launches = sl.launches_search; t.qp_launches = sl.launches_qp; t.aux_launches = sl.launches_aux;
+  const unsigned long long* c = sl.h_info->counters;
+  uavmp_kino_counters& k = ctx->last_counters;
+  k.n_pop = c[0]; k.n_occ_lookup = c[1]; k.n_cloud_pts_tested = c[2]; k.n_hash_probe = c[3];
+  k.n_insert = c[4]; k.n_update = c[5]; k.n_heuristic = c[6]; k.n_shot = c[7];
+  ctx->last_error_flag = sl.h_info->flag;
+  ctx->last_slot = (int)(&sl - ctx->slots);
+  if (info) { info->error_flags = sl.h_info->flag; info->counters = k; info->timings = t; }
+  return error_from_flag(ctx, sl.h_info->flag);
+}
+
+// every batch complete (results of un-waited tickets are in the caller's buffers; their info is dropped)
+int drain_all(uavmp_ctx* ctx) {
+  int rc = UAVMP_OK;
+  for (PlanSlot& sl : ctx->slots) { int r = slot_finish(ctx, sl, nullptr); if (r && !rc) rc = r; }
+  return rc;
 }
 
 // d_occ / d_cloud are in place: record the geometry and build the derived structures (flag grid, cell list, tensor map)
@@ -42,9 +79,24 @@ int uavmp_map_commit(uavmp_ctx* ctx, int nx, int ny, int nz, const double origin
   return kino_build_map(ctx);
 }
 
+// geometry the lookups rely on: in_map() bounds positions by origin + map_size, indexing uses nx / ny / nz
+int uavmp_map_check_geometry(uavmp_ctx* ctx, int nx, int ny, int nz, const double origin[3], const double map_size[3], double resolution) {
+  if (!origin || !map_size) return uavmp_fail(ctx, UAVMP_EINVAL, "origin / map_size is NULL");
+  const int n[3] = {nx, ny, nz};
+  for (int i = 0; i < 3; i++) {
+    if (!(map_size[i] > 0)) return uavmp_fail(ctx, UAVMP_EINVAL, "map_size must be > 0");
+    // the reference derives voxel_num = ceil(map_size / resolution) (grid_map.cpp:56-58): fewer voxels than that would let an
+    // in-map position index past the grid
+    if (map_size[i] > n[i] * resolution * (1.0 + 1e-9))
+      return uavmp_fail(ctx, UAVMP_EINVAL, "axis %d: %d voxels of %g m do not cover map_size %g (expect ceil(map_size / resolution))", i,
+                        n[i], resolution, map_size[i]);
+  }
+  return UAVMP_OK;
+}
+
 extern "C" {
 
-const char* uavmp_version(void) { return "uavmp-b200 0.1 (sm_100a)"; }
+const char* uavmp_version(void) { return "uavmp-b200 0.2 (sm_100a)"; }
 
 void uavmp_kino_params_default(uavmp_kino_params* p) {  // kino_astar.cpp:8-19
   p->allocated_node_num = 100000; p->collision_check_type = 1; p->rou_time = 1.0; p->lambda_heu = 2.0;
@@ -79,16 +131,16 @@ int uavmp_ctx_create(uavmp_ctx** out, int device) {
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);
   ctx->sm_count = prop.multiProcessorCount;
-  {
-    // the context's stream gets the highest priority so that the overlapped QP kernel (lowest priority, second stream) only
-    // takes SM space the persistent search CTAs have given up
-    int least = 0, greatest = 0;
-    cudaDeviceGetStreamPriorityRange(&least, &greatest);
-    if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, greatest) != cudaSuccess) { delete ctx; return UAVMP_ECUDA; }
+  bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+  for (PlanSlot& sl : ctx->slots) {
+    ok = ok && cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 5; i++) ok = ok && cudaEventCreate(&sl.ev[i]) == cudaSuccess;
   }
-  for (int i = 0; i < 8; i++) cudaEventCreate(&ctx->ev[i]);
+  for (int i = 0; i < 8; i++) ok = ok && cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+  if (!ok) { fprintf(stderr, "uavmp: cannot create CUDA streams / events\n"); delete ctx; return UAVMP_ECUDA; }
   uavmp_kino_params_launch(&ctx->kp);
   memset(&ctx->tm, 0, sizeof(ctx->tm));
+  memset(&ctx->last_counters, 0, sizeof(ctx->last_counters));
   memset(&ctx->map_host, 0, sizeof(ctx->map_host));
   *out = ctx;
   return UAVMP_OK;
@@ -97,16 +149,21 @@ int uavmp_ctx_create(uavmp_ctx** out, int device) {
 void uavmp_ctx_destroy(uavmp_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  for (PlanSlot& sl : ctx->slots) cudaStreamSynchronize(sl.stream);
   cudaStreamSynchronize(ctx->stream);
   void* ptrs[] = {ctx->d_kparams, ctx->d_lattice, ctx->d_occ, ctx->d_flags, ctx->d_tmp, ctx->d_cloud, ctx->d_cell_start,
-                  ctx->d_pts, ctx->d_map, ctx->d_arena_mem, ctx->d_arenas, ctx->d_q, ctx->d_order, ctx->d_status,
-                  ctx->d_use, ctx->d_npop, ctx->d_hash, ctx->d_npath, ctx->d_path_stage, ctx->d_trace, ctx->d_offsets,
-                  ctx->d_path_packed, ctx->d_misc, ctx->d_counters, ctx->d_cub_tmp, ctx->d_qp_ws, ctx->d_qp_in,
-                  ctx->d_qp_out, ctx->d_qp_int, ctx->d_plan_out, ctx->d_plan_io, ctx->d_wp, ctx->d_phase, ctx->d_query_cycles, ctx->d_flags_pad, ctx->d_b3f, ctx->d_done_flags};
+                  ctx->d_pts, ctx->d_map, ctx->d_arena_mem, ctx->d_arenas, ctx->d_arena_busy, ctx->d_path_packed,
+                  ctx->qp_scr.ws, ctx->d_qp_in, ctx->d_qp_out, ctx->d_qp_int, ctx->d_phase, ctx->d_query_cycles,
+                  ctx->d_flags_pad, ctx->d_b3f};
   for (void* p : ptrs) if (p) cudaFree(p);
+  for (PlanSlot& sl : ctx->slots) {
+    kino_free_slot(sl);
+    if (sl.h_info) cudaFreeHost(sl.h_info);
+    for (int i = 0; i < 5; i++) cudaEventDestroy(sl.ev[i]);
+    cudaStreamDestroy(sl.stream);
+  }
   qp_free_plans(ctx);
   for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->ev[i]);
-  if (ctx->fuse_ready) { cudaStreamSynchronize(ctx->stream2); cudaEventDestroy(ctx->ev_fuse[0]); cudaEventDestroy(ctx->ev_fuse[1]); cudaStreamDestroy(ctx->stream2); }
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -114,17 +171,29 @@ void uavmp_ctx_destroy(uavmp_ctx* ctx) {
 const char* uavmp_last_error(const uavmp_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 void* uavmp_ctx_stream(uavmp_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int uavmp_ctx_sync(uavmp_ctx* ctx) {
+  // everything issued so far — including batches still in flight — is complete when this returns; an error flag raised by
+  // an asynchronous batch (uavmp_plan_batch_dev / an un-waited uavmp_plan_submit ticket) is reported here
   if (!ctx) return UAVMP_EINVAL;
+  cudaSetDevice(ctx->device);
+  int rc = drain_all(ctx);
   UAVMP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return UAVMP_OK;
+  return rc;
 }
 
 int uavmp_kino_set_params(uavmp_ctx* ctx, const uavmp_kino_params* p) {
   if (!ctx || !p) return UAVMP_EINVAL;
   cudaSetDevice(ctx->device);
+  drain_all(ctx);  // the parameter block and the lattice tables are shared by every batch in flight
   ctx->kp = *p;
   ctx->params_dirty = true;
   return kino_upload_params(ctx);
+}
+
+int uavmp_kino_set_path_cap(uavmp_ctx* ctx, int points) {
+  if (!ctx || points < 16) return UAVMP_EINVAL;
+  drain_all(ctx);
+  ctx->path_cap = points;  // the slots re-allocate their path stage on the next call
+  return UAVMP_OK;
 }
 
 int uavmp_map_set(uavmp_ctx* ctx, const int8_t* occ, int nx, int ny, int nz, const double origin[3],
@@ -132,12 +201,16 @@ int uavmp_map_set(uavmp_ctx* ctx, const int8_t* occ, int nx, int ny, int nz, con
   if (!ctx || !occ || nx <= 0 || ny <= 0 || nz <= 0 || !(resolution > 0) || n_cloud < 0) return UAVMP_EINVAL;
   if (n_cloud > 0 && !cloud_xyz) return UAVMP_EINVAL;
   if (nx >= (1 << 17) || ny >= (1 << 17) || nz >= (1 << 17)) return uavmp_fail(ctx, UAVMP_EINVAL, "grid dimension too large");
+  int r = uavmp_map_check_geometry(ctx, nx, ny, nz, origin, map_size, resolution);
+  if (r) return r;
   cudaSetDevice(ctx->device);
+  drain_all(ctx);
   const size_t nvox = (size_t)nx * ny * nz;
   if (ctx->d_occ) { cudaFree(ctx->d_occ); ctx->d_occ = nullptr; }
   if (ctx->d_flags) { cudaFree(ctx->d_flags); ctx->d_flags = nullptr; }
   if (ctx->d_tmp) { cudaFree(ctx->d_tmp); ctx->d_tmp = nullptr; }
   if (ctx->d_cloud) { cudaFree(ctx->d_cloud); ctx->d_cloud = nullptr; }
+  ctx->have_map = false;
   UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_occ, nvox));
   UAVMP_CUDA(ctx, cudaMemcpyAsync(ctx->d_occ, occ, nvox, cudaMemcpyHostToDevice, ctx->stream));
   if (n_cloud > 0) {
@@ -147,24 +220,20 @@ int uavmp_map_set(uavmp_ctx* ctx, const int8_t* occ, int nx, int ny, int nz, con
   return uavmp_map_commit(ctx, nx, ny, nz, origin, map_size, resolution, n_cloud);
 }
 
-static int prepare_search(uavmp_ctx* ctx, int B) {
+static int prepare_search(uavmp_ctx* ctx) {
   if (!ctx->have_map) return uavmp_fail(ctx, UAVMP_ESTATE, "uavmp_map_set has not been called");
-  if (ctx->params_dirty) { int r = kino_upload_params(ctx); if (r) return r; }
-  if (ctx->flags_dirty) { int r = kino_build_map(ctx); if (r) return r; }
+  if (ctx->params_dirty) { drain_all(ctx); int r = kino_upload_params(ctx); if (r) return r; }
+  if (ctx->flags_dirty) { drain_all(ctx); int r = kino_build_map(ctx); if (r) return r; }
   if (ctx->kp.collision_check_type == 2 && ctx->n_cloud == 0)
     return uavmp_fail(ctx, UAVMP_ESTATE, "collision_check_type 2 needs a cloud");
-  int r = kino_ensure_arenas(ctx); if (r) return r;
-  return kino_ensure_batch(ctx, B);
+  return kino_ensure_arenas(ctx);
 }
 
-static int check_error_flag(uavmp_ctx* ctx) {
-  int flag = 0;
-  UAVMP_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->d_misc, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  UAVMP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  if (flag & 1) return uavmp_fail(ctx, UAVMP_ECAP, "voxel index outside the 18-bit key range");
-  if (flag & 2) return uavmp_fail(ctx, UAVMP_ECAP, "path has more than %d nodes", UAVMP_MAXPRIM);
-  if (flag & 4) return uavmp_fail(ctx, UAVMP_ECAP, "path longer than path_cap=%d points", ctx->path_cap);
-  if (flag & 8) return uavmp_fail(ctx, UAVMP_ECUDA, "overlapped QP gave up waiting for a search to finish");
+// the batch's error flag and counters travel to pinned host memory at the end of the slot's stream work
+static int slot_record_info(uavmp_ctx* ctx, PlanSlot& sl) {
+  UAVMP_CUDA(ctx, cudaMemcpyAsync(&sl.h_info->flag, sl.d_misc, sizeof(int), cudaMemcpyDeviceToHost, sl.stream));
+  UAVMP_CUDA(ctx, cudaMemcpyAsync(sl.h_info->counters, sl.d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sl.stream));
+  UAVMP_CUDA(ctx, cudaEventRecord(sl.ev[4], sl.stream));
   return UAVMP_OK;
 }
 
@@ -173,38 +242,41 @@ long long uavmp_kino_search_batch(uavmp_ctx* ctx, int B, const double* start_pt,
                                   long long* path_offsets, uint64_t* pop_hash, int* n_pop) {
   if (!ctx || B <= 0 || !start_pt || !start_vel || !end_pt || !end_vel || !status) return UAVMP_EINVAL;
   cudaSetDevice(ctx->device);
-  int r = prepare_search(ctx, B);
+  int r = prepare_search(ctx);
   if (r) return r;
-  cudaStream_t st = ctx->stream;
+  PlanSlot& sl = ctx->slots[0];
+  slot_finish(ctx, sl, nullptr);
+  r = kino_ensure_slot(ctx, sl, B);
+  if (r) return r;
+  cudaStream_t st = sl.stream;
   const size_t nb = (size_t)B * 3 * sizeof(double);
-  double* d = ctx->d_q;
-  cudaEventRecord(ctx->ev[0], st);
+  double* d = sl.d_q;
+  cudaEventRecord(sl.ev[0], st);
   UAVMP_CUDA(ctx, cudaMemcpyAsync(d, start_pt, nb, cudaMemcpyHostToDevice, st));
   UAVMP_CUDA(ctx, cudaMemcpyAsync(d + 3 * (size_t)B, start_vel, nb, cudaMemcpyHostToDevice, st));
   UAVMP_CUDA(ctx, cudaMemcpyAsync(d + 6 * (size_t)B, end_pt, nb, cudaMemcpyHostToDevice, st));
   UAVMP_CUDA(ctx, cudaMemcpyAsync(d + 9 * (size_t)B, end_vel, nb, cudaMemcpyHostToDevice, st));
+  cudaEventRecord(sl.ev[1], st);
+  sl.launches_qp = 0;
+  r = kino_launch_search(ctx, sl, B, d, d + 3 * (size_t)B, d + 6 * (size_t)B, d + 9 * (size_t)B, true, ctx->profile_phases,
+                         nullptr, nullptr, nullptr);
+  if (r) return r;
+  cudaEventRecord(sl.ev[2], st);
+  cudaEventRecord(ctx->ev[0], st);
+  r = kino_pack_paths(ctx, sl, B);
+  if (r) return r;
   cudaEventRecord(ctx->ev[1], st);
-  r = kino_launch_search(ctx, B, d, d + 3 * (size_t)B, d + 6 * (size_t)B, d + 9 * (size_t)B, true);
+  UAVMP_CUDA(ctx, cudaMemcpyAsync(status, sl.d_status, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (use_node_num) UAVMP_CUDA(ctx, cudaMemcpyAsync(use_node_num, sl.d_use, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (path_offsets) UAVMP_CUDA(ctx, cudaMemcpyAsync(path_offsets, sl.d_offsets, (size_t)(B + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  if (pop_hash) UAVMP_CUDA(ctx, cudaMemcpyAsync(pop_hash, sl.d_hash, (size_t)B * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  if (n_pop) UAVMP_CUDA(ctx, cudaMemcpyAsync(n_pop, sl.d_npop, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  cudaEventRecord(sl.ev[3], st);
+  r = slot_record_info(ctx, sl);
   if (r) return r;
-  cudaEventRecord(ctx->ev[2], st);
-  r = kino_pack_paths(ctx, B);
-  if (r) return r;
-  cudaEventRecord(ctx->ev[3], st);
-  UAVMP_CUDA(ctx, cudaMemcpyAsync(status, ctx->d_status, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
-  if (use_node_num) UAVMP_CUDA(ctx, cudaMemcpyAsync(use_node_num, ctx->d_use, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
-  if (path_offsets) UAVMP_CUDA(ctx, cudaMemcpyAsync(path_offsets, ctx->d_offsets, (size_t)(B + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
-  if (pop_hash) UAVMP_CUDA(ctx, cudaMemcpyAsync(pop_hash, ctx->d_hash, (size_t)B * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-  if (n_pop) UAVMP_CUDA(ctx, cudaMemcpyAsync(n_pop, ctx->d_npop, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
-  cudaEventRecord(ctx->ev[4], st);
-  UAVMP_CUDA(ctx, cudaStreamSynchronize(st));
-  cudaEventElapsedTime(&ctx->tm.h2d_ms, ctx->ev[0], ctx->ev[1]);
-  cudaEventElapsedTime(&ctx->tm.search_ms, ctx->ev[1], ctx->ev[2]);
-  cudaEventElapsedTime(&ctx->tm.path_ms, ctx->ev[2], ctx->ev[3]);
-  cudaEventElapsedTime(&ctx->tm.d2h_ms, ctx->ev[3], ctx->ev[4]);
-  cudaEventElapsedTime(&ctx->tm.total_ms, ctx->ev[0], ctx->ev[4]);
-  ctx->tm.qp_ms = 0; ctx->tm.qp_launches = 0;
-  ctx->last_B = B;
-  r = check_error_flag(ctx);
+  sl.in_flight = true; sl.B = B; sl.ticket = -1;
+  r = slot_finish(ctx, sl, nullptr);
+  cudaEventElapsedTime(&ctx->tm.path_ms, ctx->ev[0], ctx->ev[1]);
   if (r) return r;
   return ctx->last_total_path;
 }
@@ -213,38 +285,37 @@ int uavmp_kino_get_paths(uavmp_ctx* ctx, double* path_xyz, long long cap_points)
   if (!ctx || !path_xyz) return UAVMP_EINVAL;
   cudaSetDevice(ctx->device);
   if (cap_points < ctx->last_total_path) return uavmp_fail(ctx, UAVMP_ECAP, "path buffer too small");
+  cudaStream_t st = ctx->slots[0].stream;
   if (ctx->last_total_path > 0)
-    UAVMP_CUDA(ctx, cudaMemcpyAsync(path_xyz, ctx->d_path_packed, (size_t)ctx->last_total_path * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  UAVMP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    UAVMP_CUDA(ctx, cudaMemcpyAsync(path_xyz, ctx->d_path_packed, (size_t)ctx->last_total_path * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  UAVMP_CUDA(ctx, cudaStreamSynchronize(st));
   return UAVMP_OK;
 }
 
 int uavmp_kino_set_trace(uavmp_ctx* ctx, int pop_cap) {
   if (!ctx || pop_cap < 0) return UAVMP_EINVAL;
   cudaSetDevice(ctx->device);
-  ctx->pop_cap = pop_cap;
-  ctx->batch_cap = 0;  // force re-allocation of the batch buffers
+  drain_all(ctx);
+  ctx->pop_cap = pop_cap;  // the slots re-allocate their buffers on the next call
   return UAVMP_OK;
 }
 
 int uavmp_kino_get_trace(uavmp_ctx* ctx, int q, int32_t* pop_idx_xyz, int cap) {
-  if (!ctx || !pop_idx_xyz || q < 0 || q >= ctx->last_B) return UAVMP_EINVAL;
-  if (!ctx->d_trace || ctx->pop_cap <= 0) return uavmp_fail(ctx, UAVMP_ESTATE, "tracing is off");
+  if (!ctx || !pop_idx_xyz) return UAVMP_EINVAL;
+  PlanSlot& sl = ctx->slots[0];
+  if (q < 0 || q >= sl.B) return UAVMP_EINVAL;
+  if (!sl.d_trace || sl.pop_cap <= 0) return uavmp_fail(ctx, UAVMP_ESTATE, "tracing is off");
   cudaSetDevice(ctx->device);
-  int n = std::min(cap, ctx->pop_cap);
-  UAVMP_CUDA(ctx, cudaMemcpyAsync(pop_idx_xyz, ctx->d_trace + (size_t)q * ctx->pop_cap * 3, (size_t)n * 3 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  UAVMP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int n = std::min(cap, sl.pop_cap);
+  UAVMP_CUDA(ctx, cudaMemcpyAsync(pop_idx_xyz, sl.d_trace + (size_t)q * sl.pop_cap * 3, (size_t)n * 3 * sizeof(int), cudaMemcpyDeviceToHost, sl.stream));
+  UAVMP_CUDA(ctx, cudaStreamSynchronize(sl.stream));
   return UAVMP_OK;
 }
 
 int uavmp_kino_get_counters(uavmp_ctx* ctx, uavmp_kino_counters* out) {
-  if (!ctx || !out || !ctx->d_counters) return UAVMP_EINVAL;
-  cudaSetDevice(ctx->device);
-  unsigned long long c[8];
-  UAVMP_CUDA(ctx, cudaMemcpyAsync(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
-  UAVMP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  out->n_pop = c[0]; out->n_occ_lookup = c[1]; out->n_cloud_pts_tested = c[2]; out->n_hash_probe = c[3];
-  out->n_insert = c[4]; out->n_update = c[5]; out->n_heuristic = c[6]; out->n_shot = c[7];
+  // counters of the most recently COMPLETED batch (a synchronous call, or the last ticket uavmp_plan_wait returned)
+  if (!ctx || !out) return UAVMP_EINVAL;
+  *out = ctx->last_counters;
   return UAVMP_OK;
 }
 
@@ -258,36 +329,23 @@ int uavmp_kino_get_profile(uavmp_ctx* ctx, unsigned long long phase_cycles[16], 
   if (!ctx || !phase_cycles) return UAVMP_EINVAL;
   if (!ctx->d_phase) return uavmp_fail(ctx, UAVMP_ESTATE, "profiling was off for the last search");
   cudaSetDevice(ctx->device);
-  UAVMP_CUDA(ctx, cudaMemcpyAsync(phase_cycles, ctx->d_phase, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  PlanSlot& sl = ctx->slots[0];
+  UAVMP_CUDA(ctx, cudaMemcpyAsync(phase_cycles, ctx->d_phase, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sl.stream));
   // cap >= 17 * B: the B per-query totals followed by the B x 16 per-query phase cycles; else only the totals
   if (query_cycles && cap > 0) {
-    const size_t nq = (cap >= 17 * ctx->last_B) ? (size_t)17 * ctx->last_B : (size_t)std::min(cap, ctx->last_B);
-    UAVMP_CUDA(ctx, cudaMemcpyAsync(query_cycles, ctx->d_query_cycles, nq * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    const size_t nq = (cap >= 17 * sl.B) ? (size_t)17 * sl.B : (size_t)std::min(cap, sl.B);
+    UAVMP_CUDA(ctx, cudaMemcpyAsync(query_cycles, ctx->d_query_cycles, nq * sizeof(long long), cudaMemcpyDeviceToHost, sl.stream));
   }
-  UAVMP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  UAVMP_CUDA(ctx, cudaStreamSynchronize(sl.stream));
   if (grid) *grid = ctx->last_grid;
-  return UAVMP_OK;
-}
-
-int uavmp_debug_overlap(uavmp_ctx* ctx, unsigned long long out[4]) {
-  if (!ctx || !ctx->dbg_ptr) return UAVMP_ESTATE;
-  cudaDeviceSynchronize();
-  cudaMemcpy(out, ctx->dbg_ptr, 32, cudaMemcpyDeviceToHost);
   return UAVMP_OK;
 }
 
 int uavmp_get_timings(uavmp_ctx* ctx, uavmp_timings* out) {
   if (!ctx || !out) return UAVMP_EINVAL;
-  if (ctx->tm_pending_dev) {
-    // uavmp_plan_batch_dev is asynchronous: resolve its events (search start / search end / pipeline end) now
-    cudaSetDevice(ctx->device);
-    UAVMP_CUDA(ctx, cudaEventSynchronize(ctx->ev[7]));
-    cudaEventElapsedTime(&ctx->tm.search_ms, ctx->ev[5], ctx->ev[6]);
-    cudaEventElapsedTime(&ctx->tm.qp_ms, ctx->ev[6], ctx->ev[7]);
-    cudaEventElapsedTime(&ctx->tm.total_ms, ctx->ev[5], ctx->ev[7]);
-    ctx->tm.h2d_ms = 0; ctx->tm.d2h_ms = 0; ctx->tm.path_ms = 0;
-    ctx->tm_pending_dev = false;
-  }
+  cudaSetDevice(ctx->device);
+  // uavmp_plan_batch_dev is asynchronous: its batch (slot 0) is resolved here
+  if (ctx->slots[0].in_flight && ctx->slots[0].ticket < 0) slot_finish(ctx, ctx->slots[0], nullptr);
   *out = ctx->tm;
   return UAVMP_OK;
 }
@@ -326,8 +384,9 @@ int uavmp_minctrl_solve_batch(uavmp_ctx* ctx, int order, int S, int B, const dou
   UAVMP_CUDA(ctx, cudaMemcpyAsync(d_T, time_vec, (size_t)B * S * sizeof(double), cudaMemcpyHostToDevice, st));
   cudaEventRecord(ctx->ev[1], st);
   int* d_solved = ctx->d_qp_int; int* d_stat = d_solved + B; int* d_it = d_stat + B;
-  r = qp_solve_batch_dev(ctx, order, S, B, d_pos, d_bv, d_ba, order == 7 ? d_bj : nullptr, d_T, settings, ctx->d_qp_out,
-                         d_solved, d_stat, d_it);
+  int launches = 0;
+  r = qp_solve_batch_dev(ctx, st, ctx->qp_scr, &launches, order, S, B, d_pos, d_bv, d_ba, order == 7 ? d_bj : nullptr, d_T,
+                         settings, ctx->d_qp_out, d_solved, d_stat, d_it);
   if (r) return r;
   cudaEventRecord(ctx->ev[2], st);
   UAVMP_CUDA(ctx, cudaMemcpyAsync(coef, ctx->d_qp_out, (size_t)B * n * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -336,88 +395,162 @@ int uavmp_minctrl_solve_batch(uavmp_ctx* ctx, int order, int S, int B, const dou
   if (iters) UAVMP_CUDA(ctx, cudaMemcpyAsync(iters, d_it, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
   cudaEventRecord(ctx->ev[3], st);
   UAVMP_CUDA(ctx, cudaStreamSynchronize(st));
+  memset(&ctx->tm, 0, sizeof(ctx->tm));
   cudaEventElapsedTime(&ctx->tm.h2d_ms, ctx->ev[0], ctx->ev[1]);
   cudaEventElapsedTime(&ctx->tm.qp_ms, ctx->ev[1], ctx->ev[2]);
   cudaEventElapsedTime(&ctx->tm.d2h_ms, ctx->ev[2], ctx->ev[3]);
   cudaEventElapsedTime(&ctx->tm.total_ms, ctx->ev[0], ctx->ev[3]);
-  ctx->tm.search_ms = 0; ctx->tm.path_ms = 0; ctx->tm.search_launches = 0;
+  ctx->tm.qp_launches = launches;
   return UAVMP_OK;
 }
 
 // ---- pipeline ---------------------------------------------------------------------------------------------
+// Issue one batch of the search -> waypoints -> 3 x QP pipeline on slot `sl` (asynchronous).  host_io: the pointers are host
+// memory and the copies are part of the batch; otherwise they are device memory and the batch is ordered after everything
+// submitted to the context's stream so far.
+static int plan_issue(uavmp_ctx* ctx, PlanSlot& sl, int B, const double* sp, const double* sv, const double* ep, const double* ev,
+                      int order, int S, double seg_time, const uavmp_osqp_settings* settings, bool host_io, int* status,
+                      int* qp_solved, double* coef) {
+  if (order != 5 && order != 7) return uavmp_fail(ctx, UAVMP_EINVAL, "order must be 5 or 7");
+  if (S <= 0) return uavmp_fail(ctx, UAVMP_EINVAL, "S must be > 0");
+  uavmp_osqp_settings def;
+  if (!settings) { uavmp_osqp_settings_default(&def); settings = &def; }
+  if (settings->max_iter <= 0 || settings->check_termination < 0 || settings->scaling < 0)
+    return uavmp_fail(ctx, UAVMP_EINVAL, "bad OSQP settings");
+  int r = prepare_search(ctx);
+  if (r) return r;
+  r = kino_ensure_slot(ctx, sl, B);
+  if (r) return r;
+  const QpPlanDev* plan = nullptr;
+  r = qp_get_plan_dev(ctx, order, S, &plan);
+  if (r) return r;
+  const int n = (order + 1) * S;
+  const size_t nB = (size_t)3 * B;
+  r = ensure_bytes(ctx, (void**)&sl.d_wp, &sl.wp_bytes, nB * ((S + 1) + 6 + S) * sizeof(double)); if (r) return r;
+  r = ensure_bytes(ctx, (void**)&sl.d_qp_int, &sl.qp_int_bytes, nB * 3 * sizeof(int)); if (r) return r;
+  if (host_io) {
+    r = ensure_bytes(ctx, (void**)&sl.d_plan_out, &sl.plan_out_bytes, (size_t)B * 3 * n * sizeof(double)); if (r) return r;
+    r = ensure_bytes(ctx, (void**)&sl.d_plan_io, &sl.plan_io_bytes, (size_t)B * 2 * sizeof(int)); if (r) return r;
+  }
+  // in-kernel QP: how many warp workspaces fit in the shared memory the search gives up between two queries
+  const int ws_bytes = plan->ws_warp * (int)sizeof(double);
+  int warps = std::min(8, kino_qp_overlay_bytes() / ws_bytes);
+  if (getenv("UAVMP_NO_FUSE")) warps = 0;
+  if (warps == 0) { r = ensure_bytes(ctx, (void**)&sl.d_qp_out, &sl.qp_out_bytes, nB * n * sizeof(double)); if (r) return r; }
+
+  cudaStream_t st = sl.stream;
+  const double *d_sp = sp, *d_sv = sv, *d_ep = ep, *d_ev = ev;
+  double* d_coef = coef; int* d_solved = qp_solved;
+  cudaEventRecord(sl.ev[0], st);
+  if (host_io) {
+    const size_t nb = (size_t)B * 3 * sizeof(double);
+    double* d = sl.d_q;
+    UAVMP_CUDA(ctx, cudaMemcpyAsync(d, sp, nb, cudaMemcpyHostToDevice, st));
+    UAVMP_CUDA(ctx, cudaMemcpyAsync(d + 3 * (size_t)B, sv, nb, cudaMemcpyHostToDevice, st));
+    UAVMP_CUDA(ctx, cudaMemcpyAsync(d + 6 * (size_t)B, ep, nb, cudaMemcpyHostToDevice, st));
+    UAVMP_CUDA(ctx, cudaMemcpyAsync(d + 9 * (size_t)B, ev, nb, cudaMemcpyHostToDevice, st));
+    d_sp = d; d_sv = d + 3 * (size_t)B; d_ep = d + 6 * (size_t)B; d_ev = d + 9 * (size_t)B;
+    d_coef = sl.d_plan_out; d_solved = sl.d_plan_io + B;
+  } else {
+    // device inputs: ordered after the work already submitted to the context's stream
+    UAVMP_CUDA(ctx, cudaEventRecord(ctx->ev[7], ctx->stream));
+    UAVMP_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[7], 0));
+  }
+  cudaEventRecord(sl.ev[1], st);
+  double* pos = sl.d_wp; double* bv = pos + nB * (S + 1); double* ba = bv + nB * 2; double* bj = ba + nB * 2; double* T = bj + nB * 2;
+  int* d_solved3 = sl.d_qp_int; int* d_stat3 = d_solved3 + nB; int* d_it3 = d_stat3 + nB;
+  if (warps > 0) {
+    KinoQpDev qp;
+    qp.enabled = 1; qp.warps = warps; qp.Sg = S; qp.n = n; qp.seg_time = seg_time;
+    qp.pos = pos; qp.bv = bv; qp.ba = ba; qp.bj = bj; qp.T = T;
+    qp.coef = d_coef; qp.solved3 = d_solved3; qp.status3 = d_stat3; qp.iters3 = d_it3; qp.qp_solved = d_solved;
+    r = kino_launch_search(ctx, sl, B, d_sp, d_sv, d_ep, d_ev, true, false, &qp, plan, settings);
+    if (r) return r;
+    sl.launches_qp = 0;  // the QP runs inside the search kernel
+  } else {
+    // sequential fallback (the QP workspace does not fit next to the search, or UAVMP_NO_FUSE): three more kernels on the stream
+    r = kino_launch_search(ctx, sl, B, d_sp, d_sv, d_ep, d_ev, true, false, nullptr, nullptr, nullptr);
+    if (r) return r;
+    double *w_pos, *w_bv, *w_ba, *w_bj, *w_T;
+    r = qp_waypoints_from_paths(ctx, sl, B, S, seg_time, d_sv, d_ev, &w_pos, &w_bv, &w_ba, &w_bj, &w_T);
+    if (r) return r;
+    int launches = 0;
+    r = qp_solve_batch_dev(ctx, st, sl.qp_scr, &launches, order, S, 3 * B, w_pos, w_bv, w_ba, order == 7 ? w_bj : nullptr, w_T,
+                           settings, sl.d_qp_out, d_solved3, d_stat3, d_it3);
+    if (r) return r;
+    r = qp_scatter_plan_outputs(ctx, sl, B, order, S, d_solved3, sl.d_qp_out, d_solved, d_coef);
+    if (r) return r;
+    sl.launches_qp = launches; sl.launches_aux += 2;  // k_waypoints, k_scatter_plan
+  }
+  cudaEventRecord(sl.ev[2], st);
+  if (host_io) {
+    UAVMP_CUDA(ctx, cudaMemcpyAsync(status, sl.d_status, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    UAVMP_CUDA(ctx, cudaMemcpyAsync(qp_solved, d_solved, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    UAVMP_CUDA(ctx, cudaMemcpyAsync(coef, d_coef, (size_t)B * 3 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  } else {
+    UAVMP_CUDA(ctx, cudaMemcpyAsync(status, sl.d_status, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  }
+  cudaEventRecord(sl.ev[3], st);
+  r = slot_record_info(ctx, sl);
+  if (r) return r;
+  sl.in_flight = true; sl.B = B; sl.host_io = host_io;
+  return UAVMP_OK;
+}
+
+int uavmp_plan_max_in_flight(void) { return UAVMP_NSLOT - 1; }
+
+int uavmp_plan_submit(uavmp_ctx* ctx, int B, const double* start_pt, const double* start_vel, const double* end_pt,
+                      const double* end_vel, int order, int S, double seg_time, const uavmp_osqp_settings* settings,
+                      unsigned flags, int* search_status, int* qp_solved, double* coef, long long* ticket) {
+  if (!ctx || B <= 0 || !start_pt || !start_vel || !end_pt || !end_vel || !search_status || !qp_solved || !coef || !ticket) return UAVMP_EINVAL;
+  cudaSetDevice(ctx->device);
+  PlanSlot& sl = ctx->slots[1 + ctx->next_ticket % (UAVMP_NSLOT - 1)];  // slot 0 serves the synchronous entry points
+  if (sl.in_flight)
+    return uavmp_fail(ctx, UAVMP_ESTATE, "%d batches are in flight: collect the oldest ticket with uavmp_plan_wait first", UAVMP_NSLOT - 1);
+  int r = plan_issue(ctx, sl, B, start_pt, start_vel, end_pt, end_vel, order, S, seg_time, settings,
+                     !(flags & UAVMP_PLAN_DEVICE_IO), search_status, qp_solved, coef);
+  if (r) return r;
+  sl.ticket = ctx->next_ticket++;
+  *ticket = sl.ticket;
+  return UAVMP_OK;
+}
+
+static PlanSlot* find_ticket(uavmp_ctx* ctx, long long ticket) {
+  if (ticket < 0) return nullptr;
+  PlanSlot& sl = ctx->slots[1 + ticket % (UAVMP_NSLOT - 1)];
+  return (sl.in_flight && sl.ticket == ticket) ? &sl : nullptr;
+}
+
+int uavmp_plan_wait(uavmp_ctx* ctx, long long ticket, uavmp_plan_info* info) {
+  if (!ctx) return UAVMP_EINVAL;
+  cudaSetDevice(ctx->device);
+  PlanSlot* sl = find_ticket(ctx, ticket);
+  if (!sl) return uavmp_fail(ctx, UAVMP_EINVAL, "unknown or already collected ticket %lld", ticket);
+  return slot_finish(ctx, *sl, info);
+}
+
+int uavmp_plan_stream_wait(uavmp_ctx* ctx, long long ticket, void* cuda_stream) {
+  if (!ctx) return UAVMP_EINVAL;
+  cudaSetDevice(ctx->device);
+  PlanSlot* sl = find_ticket(ctx, ticket);
+  if (!sl) return uavmp_fail(ctx, UAVMP_EINVAL, "unknown or already collected ticket %lld", ticket);
+  UAVMP_CUDA(ctx, cudaStreamWaitEvent((cudaStream_t)cuda_stream, sl->ev[4], 0));
+  return UAVMP_OK;
+}
+
 int uavmp_plan_batch_dev(uavmp_ctx* ctx, int B, const double* d_sp, const double* d_sv, const double* d_ep,
                          const double* d_ev, int order, int S, double seg_time, const uavmp_osqp_settings* settings,
                          int* d_search_status, int* d_qp_solved, double* d_coef) {
   if (!ctx || B <= 0 || !d_sp || !d_sv || !d_ep || !d_ev || !d_search_status || !d_qp_solved || !d_coef) return UAVMP_EINVAL;
-  if (order != 5 && order != 7) return uavmp_fail(ctx, UAVMP_EINVAL, "order must be 5 or 7");
   cudaSetDevice(ctx->device);
-  uavmp_osqp_settings def;
-  if (!settings) { uavmp_osqp_settings_default(&def); settings = &def; }
-  int r = prepare_search(ctx, B);
+  PlanSlot& sl = ctx->slots[0];
+  int r = slot_finish(ctx, sl, nullptr);  // surfaces the error flag of the previous asynchronous batch on this slot
   if (r) return r;
-  cudaStream_t st = ctx->stream;
-  const bool overlap = !getenv("UAVMP_NO_OVERLAP");
-  if (overlap) {
-    // overlapped pipeline: search on the context's stream, the QP kernel on a second low-priority stream; every QP thread
-    // waits for its own query's completion flag, so the QP runs on the SMs the search's long tail leaves idle
-    if (!ctx->fuse_ready) {
-      int lo = 0, hi = 0;
-      cudaDeviceGetStreamPriorityRange(&lo, &hi);
-      UAVMP_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, lo));
-      cudaEventCreateWithFlags(&ctx->ev_fuse[0], cudaEventDisableTiming);
-      cudaEventCreateWithFlags(&ctx->ev_fuse[1], cudaEventDisableTiming);
-      ctx->fuse_ready = true;
-    }
-    if (ctx->done_flags_cap < B) {
-      if (ctx->d_done_flags) cudaFree(ctx->d_done_flags);
-      ctx->d_done_flags = nullptr;
-      UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_done_flags, (size_t)B * sizeof(int)));
-      ctx->done_flags_cap = B;
-    }
-    r = qp_launch_fused(ctx, order, S, B, seg_time, d_sv, d_ev, nullptr, settings, d_coef, d_qp_solved, /*prepare_only=*/true);
-    if (r) return r;
-    cudaEventRecord(ctx->ev[5], st);
-    UAVMP_CUDA(ctx, cudaMemsetAsync(ctx->d_done_flags, 0, (size_t)B * sizeof(int), st));
-    // kino_launch_search records ev_fuse[0] right before the search kernel (after the flags are zero and the processing order
-    // is sorted): the QP stream waits for that event, NOT for the search kernel
-    ctx->fuse_flags = ctx->d_done_flags; ctx->fuse_qp_solved = d_qp_solved;
-    r = kino_launch_search(ctx, B, d_sp, d_sv, d_ep, d_ev, true);
-    ctx->fuse_flags = nullptr; ctx->fuse_qp_solved = nullptr;
-    if (r) return r;
-    cudaEventRecord(ctx->ev[6], st);
-    UAVMP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fuse[0], 0));
-    r = qp_launch_fused(ctx, order, S, B, seg_time, d_sv, d_ev, B > 1 ? ctx->d_order + B : nullptr, settings, d_coef, d_qp_solved, false);
-    if (r) return r;
-    cudaEventRecord(ctx->ev_fuse[1], ctx->stream2);
-    UAVMP_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_fuse[1], 0));  // everything after this call on `st` sees the QP's results
-    UAVMP_CUDA(ctx, cudaMemcpyAsync(d_search_status, ctx->d_status, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, st));
-    cudaEventRecord(ctx->ev[7], st);
-    ctx->last_B = B;
-    ctx->tm_pending_dev = true;
-    ctx->tm.aux_launches = 1;  // k_dist_keys (+ cub's radix-sort kernels, library code)
-    return UAVMP_OK;
-  }
-  cudaEventRecord(ctx->ev[5], st);
-  r = kino_launch_search(ctx, B, d_sp, d_sv, d_ep, d_ev, true);
+  r = plan_issue(ctx, sl, B, d_sp, d_sv, d_ep, d_ev, order, S, seg_time, settings, false, d_search_status, d_qp_solved, d_coef);
   if (r) return r;
-  cudaEventRecord(ctx->ev[6], st);
-  double *w_pos, *w_bv, *w_ba, *w_bj, *w_T;
-  r = qp_waypoints_from_paths(ctx, B, S, seg_time, d_sv, d_ev, order, &w_pos, &w_bv, &w_ba, &w_bj, &w_T);
-  if (r) return r;
-  const int n = (order + 1) * S;
-  r = ensure_bytes(ctx, (void**)&ctx->d_qp_out, &ctx->qp_out_bytes, (size_t)3 * B * n * sizeof(double)); if (r) return r;
-  r = ensure_bytes(ctx, (void**)&ctx->d_qp_int, &ctx->qp_int_bytes, (size_t)3 * B * 3 * sizeof(int)); if (r) return r;
-  int* d_solved3 = ctx->d_qp_int; int* d_stat3 = d_solved3 + 3 * B; int* d_it3 = d_stat3 + 3 * B;
-  r = qp_solve_batch_dev(ctx, order, S, 3 * B, w_pos, w_bv, w_ba, order == 7 ? w_bj : nullptr, w_T, settings,
-                         ctx->d_qp_out, d_solved3, d_stat3, d_it3);
-  if (r) return r;
-  r = qp_scatter_plan_outputs(ctx, B, order, S, d_solved3, ctx->d_qp_out, d_qp_solved, d_coef);
-  if (r) return r;
-  UAVMP_CUDA(ctx, cudaMemcpyAsync(d_search_status, ctx->d_status, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, st));
-  cudaEventRecord(ctx->ev[7], st);
-  ctx->last_B = B;
-  ctx->tm_pending_dev = true;
-  ctx->tm.aux_launches = 3;  // k_dist_keys, k_waypoints, k_scatter_plan (+ cub's radix-sort kernels, library code)
+  sl.ticket = -1;
+  // everything submitted to the context's stream after this call sees the results
+  UAVMP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, sl.ev[4], 0));
   return UAVMP_OK;
 }
 
@@ -426,38 +559,12 @@ int uavmp_plan_batch(uavmp_ctx* ctx, int B, const double* start_pt, const double
                      int* search_status, int* qp_solved, double* coef) {
   if (!ctx || B <= 0 || !start_pt || !start_vel || !end_pt || !end_vel || !search_status || !qp_solved || !coef) return UAVMP_EINVAL;
   cudaSetDevice(ctx->device);
-  int r = prepare_search(ctx, B);
+  PlanSlot& sl = ctx->slots[0];
+  slot_finish(ctx, sl, nullptr);
+  int r = plan_issue(ctx, sl, B, start_pt, start_vel, end_pt, end_vel, order, S, seg_time, settings, true, search_status, qp_solved, coef);
   if (r) return r;
-  cudaStream_t st = ctx->stream;
-  const size_t nb = (size_t)B * 3 * sizeof(double);
-  const int n = (order + 1) * S;
-  double* d = ctx->d_q;
-  r = ensure_bytes(ctx, (void**)&ctx->d_plan_out, &ctx->plan_out_bytes, (size_t)B * 3 * n * sizeof(double)); if (r) return r;
-  r = ensure_bytes(ctx, (void**)&ctx->d_plan_io, &ctx->plan_io_bytes, (size_t)B * 2 * sizeof(int)); if (r) return r;
-  double* d_out = ctx->d_plan_out;
-  int* d_io = ctx->d_plan_io;
-  cudaEventRecord(ctx->ev[0], st);
-  UAVMP_CUDA(ctx, cudaMemcpyAsync(d, start_pt, nb, cudaMemcpyHostToDevice, st));
-  UAVMP_CUDA(ctx, cudaMemcpyAsync(d + 3 * (size_t)B, start_vel, nb, cudaMemcpyHostToDevice, st));
-  UAVMP_CUDA(ctx, cudaMemcpyAsync(d + 6 * (size_t)B, end_pt, nb, cudaMemcpyHostToDevice, st));
-  UAVMP_CUDA(ctx, cudaMemcpyAsync(d + 9 * (size_t)B, end_vel, nb, cudaMemcpyHostToDevice, st));
-  cudaEventRecord(ctx->ev[1], st);
-  r = uavmp_plan_batch_dev(ctx, B, d, d + 3 * (size_t)B, d + 6 * (size_t)B, d + 9 * (size_t)B, order, S, seg_time, settings,
-                           d_io, d_io + B, d_out);
-  if (r) return r;
-  UAVMP_CUDA(ctx, cudaMemcpyAsync(search_status, d_io, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
-  UAVMP_CUDA(ctx, cudaMemcpyAsync(qp_solved, d_io + B, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
-  UAVMP_CUDA(ctx, cudaMemcpyAsync(coef, d_out, (size_t)B * 3 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
-  cudaEventRecord(ctx->ev[4], st);
-  UAVMP_CUDA(ctx, cudaStreamSynchronize(st));
-  cudaEventElapsedTime(&ctx->tm.h2d_ms, ctx->ev[0], ctx->ev[1]);
-  cudaEventElapsedTime(&ctx->tm.search_ms, ctx->ev[5], ctx->ev[6]);
-  cudaEventElapsedTime(&ctx->tm.qp_ms, ctx->ev[6], ctx->ev[7]);
-  cudaEventElapsedTime(&ctx->tm.d2h_ms, ctx->ev[7], ctx->ev[4]);
-  cudaEventElapsedTime(&ctx->tm.total_ms, ctx->ev[0], ctx->ev[4]);
-  ctx->tm.path_ms = 0;
-  ctx->tm_pending_dev = false;
-  return check_error_flag(ctx);
+  sl.ticket = -1;
+  return slot_finish(ctx, sl, nullptr);
 }
 
 }  // extern "C"

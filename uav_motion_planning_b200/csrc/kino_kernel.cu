@@ -33,6 +33,8 @@
 #include <numeric>
 
 #include "fpmath.h"
+#include "qp_body_warp.h"
+#include "qp_plan.h"
 #include "uavmp_internal.h"
 
 #ifndef KT
@@ -101,11 +103,7 @@ struct SearchSmem {
   double xlo[3], xhi[3];
   int to[3], rc0[3], rc1[3];
   int any_ok, tile_ok, nT, npts, n_upd, last_ev, nq;
-  unsigned dmax, dsum, dhit;
-  unsigned long long mbar;
   HeapSlot htop[HTOP];
-  KinoParamsDev P;
-  MapDev M;
   double cp[3], cv[3], cg;
   double gp[3], gv[3];
   double sp[3], sv[3];
@@ -113,13 +111,22 @@ struct SearchSmem {
   double shot[12];
   unsigned long long pop_hash;
   unsigned long long cnt[8];
+  uint32_t cur_id, cur_parent, epoch;
+  int heap_len, use_num, n_pop, n1, n2, n_new, status, flag, q, trunc;
+  int wsum[KT / 32];
+  // ---- everything above is per-query scratch: between two queries the in-kernel QP overlays it with its workspaces.
+  // ---- everything below survives a QP round.
+  unsigned long long mbar;
+  KinoParamsDev P;
+  MapDev M;
   unsigned long long ph[16];  // per-phase SM cycles [0..7] + diagnostics [8..15] of this CTA (thread 0's clock), only when bt.phase_cycles != nullptr
   long long ph_t;
   unsigned long long phq[16];
-  uint32_t cur_id, cur_parent, epoch;
-  int heap_len, use_num, n_pop, n1, n2, n_new, status, flag, q;
-  int wsum[KT / 32];
+  int arena;                  // index of the arena this CTA took from the pool
+  int npend;                  // finished queries' QP problems (3 q + axis) waiting for a round
+  int pend[16];
 };
+#define QP_OVERLAY_BYTES (offsetof(SearchSmem, mbar))
 
 __device__ __forceinline__ double dot3(double ax, double ay, double az, double bx, double by, double bz) {
   return (ax * bx + ay * by) + az * bz;  // Eigen fixed-size-3 reduction order
@@ -542,20 +549,73 @@ __device__ bool ellipsoid_hit_global(const MapDev& M, const KinoParamsDev& P, co
 }
 
 // =====================================================================================================
+// One in-kernel QP round: warps 0 .. cnt-1 each take one pending 1-D problem (id = 3 q + axis) of a query this CTA has
+// finished, build its waypoints from the staged path (the rule of uav_motion_planning_b200/planner.py: waypoint k =
+// path[floor(k (n - 1) / S)], T_i = seg_time, boundary velocity = start / end velocity, acceleration and jerk 0) and run
+// qp_warp_solve_one on a workspace that overlays the search's per-query shared memory.
+__device__ __forceinline__ void qp_round(SearchSmem& s, unsigned char* smem_raw, const QpPlanDev& pl, const KinoQpDev& qp,
+                                         const uavmp_osqp_settings& S, const KinoBatchDev& bt, int tid) {
+  const int warp = tid >> 5, lane = tid & 31;
+  const int cnt = min(s.npend, qp.warps);
+  __syncthreads();  // every thread has left the scratch area and has read npend
+  if (warp < cnt) {
+    const int b = s.pend[s.npend - 1 - warp];
+    const int q = b / 3, ax = b - 3 * q;
+    const int Sg = qp.Sg;
+    const int np = bt.n_path[q];
+    const double* path = bt.path_stage + (size_t)q * bt.path_cap * 3;
+    for (int k = lane; k <= Sg; k += 32) qp.pos[(size_t)b * (Sg + 1) + k] = path[3 * (((long long)k * (np - 1)) / Sg) + ax];
+    for (int sgm = lane; sgm < Sg; sgm += 32) qp.T[(size_t)b * Sg + sgm] = qp.seg_time;
+    if (lane == 0) {
+      qp.bv[(size_t)b * 2] = bt.start_vel[3 * q + ax]; qp.bv[(size_t)b * 2 + 1] = bt.end_vel[3 * q + ax];
+      qp.ba[(size_t)b * 2] = 0.0; qp.ba[(size_t)b * 2 + 1] = 0.0;
+      qp.bj[(size_t)b * 2] = 0.0; qp.bj[(size_t)b * 2 + 1] = 0.0;
+    }
+    __syncwarp();
+    QpIo io;
+    io.pos = qp.pos; io.bv = qp.bv; io.ba = qp.ba; io.bj = qp.bj; io.T = qp.T;
+    io.coef = qp.coef; io.solved = qp.solved3; io.status = qp.status3; io.iters = qp.iters3; io.B = 3 * bt.B; io.stride = 0;
+    qp_warp_solve_one(pl, io, S, reinterpret_cast<double*>(smem_raw) + (size_t)warp * pl.ws_warp, b);
+    if (lane == 0 && !qp.solved3[b]) atomicAnd(qp.qp_solved + q, 0);
+  }
+  __syncthreads();
+  if (tid == 0) s.npend -= cnt;
+  __syncthreads();
+}
+
+// =====================================================================================================
 __global__ void __launch_bounds__(KT, (KT <= 256 ? 2 : 1)) kino_search_kernel(const KinoParamsDev* __restrict__ Pp, LatticeDev lat,
-                                                            const MapDev* __restrict__ Mp, KinoArena* arenas,
-                                                            KinoBatchDev bt, int table_bits,
-                                                            const __grid_constant__ CUtensorMap tmap, int use_tma, float slab_margin) {
+                                                            const MapDev* __restrict__ Mp, KinoArena* arenas, int* arena_busy,
+                                                            int n_arenas, const __grid_constant__ KinoBatchDev bt, int table_bits,
+                                                            const __grid_constant__ CUtensorMap tmap, int use_tma, float slab_margin, float cullf_arg,
+                                                            const __grid_constant__ KinoQpDev qp, const __grid_constant__ QpPlanDev pl,
+                                                            const __grid_constant__ uavmp_osqp_settings qps) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SearchSmem& s = *reinterpret_cast<SearchSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // parameter blocks live in shared memory: every hot loop reads them
   for (int i = tid; i < (int)(sizeof(KinoParamsDev) / 4); i += KT) reinterpret_cast<uint32_t*>(&s.P)[i] = reinterpret_cast<const uint32_t*>(Pp)[i];
   for (int i = tid; i < (int)(sizeof(MapDev) / 4); i += KT) reinterpret_cast<uint32_t*>(&s.M)[i] = reinterpret_cast<const uint32_t*>(Mp)[i];
+  if (tid == 0) {
+    // Take a free arena from the pool.  Search kernels of several batches run concurrently (cross-batch pipelining: the
+    // CTAs of batch k + 1 become resident as the CTAs of batch k retire), so an arena belongs to a CTA, not to a block index.
+    // At most n_arenas search CTAs are ever resident (occupancy), so a free one exists unless the pool was cut for memory.
+    int a = (int)(blockIdx.x % (unsigned)n_arenas);
+    for (;;) {
+      if (atomicCAS(arena_busy + a, 0, 1) == 0) break;
+      a = (a + 1 == n_arenas) ? 0 : a + 1;
+    }
+    // acquire: the previous owner's writes (epoch word, hash table, possibly made on another SM) are visible to the loads
+    // below, including the L1-cached ones
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    s.arena = a;
+  }
+  __syncthreads();
+  if (tid == 0) s.P.cullf = cullf_arg;  // the float pre-cull's margin depends on the map's coordinate magnitude (host: float_filter_margins)
   __syncthreads();
   const KinoParamsDev& P = s.P;
   const MapDev& M = s.M;
-  KinoArena ar = arenas[blockIdx.x];
+  KinoArena ar = arenas[s.arena];
   KinoNode* nodes = ar.nodes;
   HeapSlot* H = ar.heap;
   HashSlot* table = ar.table;
@@ -564,7 +624,7 @@ __global__ void __launch_bounds__(KT, (KT <= 256 ? 2 : 1)) kino_search_kernel(co
   const int na = P.na, K = P.K, nprim = P.nprim;
   if (tid < 16) { s.ph[tid] = 0; s.phq[tid] = 0; }
   if (tid == 0) {
-    s.ph_t = clock64(); s.dmax = 0; s.dsum = 0; s.dhit = 0;
+    s.ph_t = clock64(); s.npend = 0;
     mbar_init(&s.mbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -580,7 +640,10 @@ __global__ void __launch_bounds__(KT, (KT <= 256 ? 2 : 1)) kino_search_kernel(co
     }
     __syncthreads();
     const int q = s.q;
-    if (q < 0) break;
+    if (q < 0) {
+      while (qp.enabled && s.npend > 0) qp_round(s, smem_raw, pl, qp, qps, bt, tid);  // (uniform: npend is re-read after barriers)
+      break;
+    }
 
     if (tid < 8) s.cnt[tid] = 0;
     if (tid == 0) {
@@ -622,7 +685,7 @@ __global__ void __launch_bounds__(KT, (KT <= 256 ? 2 : 1)) kino_search_kernel(co
       nodes[0] = nd;
       HeapSlot hs; hs.f = P.lambda * h; hs.id = 0; hs.hs = hh;
       hstore(s, H, 1, hs);
-      s.heap_len = 1; s.use_num = 1; s.n_pop = 0; s.status = 0;
+      s.heap_len = 1; s.use_num = 1; s.n_pop = 0; s.status = 0; s.trunc = 0;
       s.pop_hash = 0xcbf29ce484222325ull;
       s.cnt[3] += 1; s.cnt[4] += 1; s.cnt[6] += 1;  // hash probe, insert, heuristic of the start node
     }
@@ -730,7 +793,7 @@ __global__ void __launch_bounds__(KT, (KT <= 256 ? 2 : 1)) kino_search_kernel(co
             int n = 0;
             uint32_t c = s.cur_id;
             while (c != UAVMP_NONE && n < UAVMP_MAXPRIM) { s.id[n++] = c; c = nodes[c].parent; }
-            if (c != UAVMP_NONE) atomicOr(bt.error_flag, 2);
+            if (c != UAVMP_NONE) { atomicOr(bt.error_flag, 2); s.trunc = 1; }
             s.n1 = n;
           }
           __syncthreads();
@@ -738,7 +801,7 @@ __global__ void __launch_bounds__(KT, (KT <= 256 ? 2 : 1)) kino_search_kernel(co
           const int segk = P.K - 1;  // floor(duration / step) samples per primitive, duration == sample_tau
           const long long shot_n = seg + 1;
           const long long total = (long long)(nn - 1) * segk + shot_n;
-          if (total > bt.path_cap) { if (tid == 0) atomicOr(bt.error_flag, 4); }
+          if (total > bt.path_cap) { if (tid == 0) { atomicOr(bt.error_flag, 4); s.trunc = 1; } }
           const long long lim = total < bt.path_cap ? total : bt.path_cap;
           double* out = bt.path_stage + (size_t)q * bt.path_cap * 3;
           for (long long i = tid; i < lim; i += KT) {
@@ -1392,15 +1455,23 @@ __global__ void __launch_bounds__(KT, (KT <= 256 ? 2 : 1)) kino_search_kernel(co
     }
     __syncthreads();
     if (tid < 8) atomicAdd(&bt.counters[tid], s.cnt[tid]);
-    if (bt.done_flag) {
-      // every thread's writes of this query (path points, status, n_path) become visible before the flag: the QP
-      // kernel running on the second stream picks the query up from here
-      __threadfence();
+    if (qp.enabled) {
+      // a truncated path (error bit 4) never reaches the QP: the batch call reports ECAP and the query is left unsolved
+      const bool go = (s.status == UAVMP_REACH_END) && bt.n_path[q] >= 1 && !s.trunc;
+      if (!go) {
+        double* out = qp.coef + (size_t)q * 3 * qp.n;
+        for (int j = tid; j < 3 * qp.n; j += KT) out[j] = 0.0;
+      }
+      if (tid == 0) {
+        qp.qp_solved[q] = go ? 1 : 0;
+        if (go) { s.pend[s.npend] = 3 * q; s.pend[s.npend + 1] = 3 * q + 1; s.pend[s.npend + 2] = 3 * q + 2; s.npend += 3; }
+      }
       __syncthreads();
-      if (tid == 0) { if (bt.qp_solved) bt.qp_solved[q] = (s.status == UAVMP_REACH_END) ? 1 : 0; __threadfence(); atomicExch(&bt.done_flag[q], 1); }
+      while (s.npend >= qp.warps) qp_round(s, smem_raw, pl, qp, qps, bt, tid);
     }
   }
-  if (bt.dbg && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); atomicMin(&bt.dbg[2], t); atomicMax(&bt.dbg[3], t); }
+  __syncthreads();
+  if (tid == 0) { __threadfence(); atomicExch(arena_busy + s.arena, 0); }  // release: the next owner sees this CTA's arena writes
   PH_MARK(7);
   __syncthreads();
   if (prof && tid < 16) atomicAdd(&bt.phase_cycles[tid], s.ph[tid]);
@@ -1785,6 +1856,8 @@ static int kino_ctas_per_sm() {
   return n;
 }
 
+int kino_qp_overlay_bytes() { return (int)QP_OVERLAY_BYTES; }
+
 int kino_ensure_arenas(uavmp_ctx* ctx) {
   const int nodes = ctx->kp.allocated_node_num;
   int per_sm = kino_ctas_per_sm();
@@ -1795,8 +1868,12 @@ int kino_ensure_arenas(uavmp_ctx* ctx) {
   if (bits < 12) bits = 12;
   const int tsize = 1 << bits;
   if (ctx->d_arenas && ctx->n_arenas == want && ctx->arena_nodes == nodes && ctx->table_size == tsize) return UAVMP_OK;
+  // the pool is shared by every batch in flight: nothing may be running while it is rebuilt
+  UAVMP_CUDA(ctx, cudaDeviceSynchronize());
   if (ctx->d_arena_mem) { cudaFree(ctx->d_arena_mem); ctx->d_arena_mem = nullptr; }
   if (ctx->d_arenas) { cudaFree(ctx->d_arenas); ctx->d_arenas = nullptr; }
+  if (ctx->d_arena_busy) { cudaFree(ctx->d_arena_busy); ctx->d_arena_busy = nullptr; }
+  ctx->n_arenas = 0;
   auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
   const size_t sz_nodes = up((size_t)nodes * sizeof(KinoNode));
   const size_t sz_heap = up((size_t)(nodes + 4) * sizeof(HeapSlot));
@@ -1820,68 +1897,103 @@ int kino_ensure_arenas(uavmp_ctx* ctx) {
     UAVMP_CUDA(ctx, cudaMemsetAsync(b + sz_nodes + sz_heap, 0, sz_tab + sz_ep, ctx->stream));
   }
   UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_arenas, sizeof(KinoArena) * want));
+  UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_arena_busy, sizeof(int) * want));
+  UAVMP_CUDA(ctx, cudaMemsetAsync(ctx->d_arena_busy, 0, sizeof(int) * want, ctx->stream));
   UAVMP_CUDA(ctx, cudaMemcpyAsync(ctx->d_arenas, ha.data(), sizeof(KinoArena) * want, cudaMemcpyHostToDevice, ctx->stream));
   UAVMP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->n_arenas = want; ctx->arena_nodes = nodes; ctx->table_size = tsize;
   return UAVMP_OK;
 }
 
-int kino_ensure_batch(uavmp_ctx* ctx, int B) {
-  if (B <= ctx->batch_cap) return UAVMP_OK;
-  auto fr = [](void* p) { if (p) cudaFree(p); };
-  fr(ctx->d_q); fr(ctx->d_order); fr(ctx->d_status); fr(ctx->d_use); fr(ctx->d_npop); fr(ctx->d_hash);
-  fr(ctx->d_npath); fr(ctx->d_path_stage); fr(ctx->d_trace); fr(ctx->d_offsets);
-  ctx->d_trace = nullptr;
-  int cap = B;
-  UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_q, (size_t)cap * 12 * sizeof(double)));
-  UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_order, (size_t)cap * 4 * sizeof(int)));  // idx | idx_sorted | key | key_sorted
-  UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_status, (size_t)cap * sizeof(int)));
-  UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_use, (size_t)cap * sizeof(int)));
-  UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_npop, (size_t)cap * sizeof(int)));
-  UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_hash, (size_t)cap * sizeof(unsigned long long)));
-  UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_npath, (size_t)cap * sizeof(int)));
-  UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_path_stage, (size_t)cap * ctx->path_cap * 3 * sizeof(double)));
-  UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_offsets, (size_t)(cap + 1) * sizeof(long long)));
-  if (ctx->pop_cap > 0) UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_trace, (size_t)cap * ctx->pop_cap * 3 * sizeof(int)));
-  if (!ctx->d_misc) UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_misc, 64));
-  if (!ctx->d_counters) UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)));
-  ctx->batch_cap = cap;
+void kino_free_slot(PlanSlot& sl) {
+  void* ptrs[] = {sl.d_q, sl.d_order, sl.d_status, sl.d_use, sl.d_npop, sl.d_hash, sl.d_npath, sl.d_path_stage, sl.d_trace,
+                  sl.d_offsets, sl.d_misc, sl.d_counters, sl.d_cub_tmp, sl.d_wp, sl.d_qp_int, sl.d_qp_out, sl.d_plan_out,
+                  sl.d_plan_io, sl.qp_scr.ws};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  sl.d_q = nullptr; sl.d_order = nullptr; sl.d_status = nullptr; sl.d_use = nullptr; sl.d_npop = nullptr; sl.d_hash = nullptr;
+  sl.d_npath = nullptr; sl.d_path_stage = nullptr; sl.d_trace = nullptr; sl.d_offsets = nullptr; sl.d_misc = nullptr;
+  sl.d_counters = nullptr; sl.d_cub_tmp = nullptr; sl.d_wp = nullptr; sl.d_qp_int = nullptr; sl.d_qp_out = nullptr;
+  sl.d_plan_out = nullptr; sl.d_plan_io = nullptr; sl.qp_scr.ws = nullptr;
+  sl.cub_tmp_bytes = sl.wp_bytes = sl.qp_int_bytes = sl.qp_out_bytes = sl.plan_out_bytes = sl.plan_io_bytes = sl.qp_scr.ws_bytes = 0;
+  sl.cap = 0;
+}
+
+// (re)allocate the search buffers of a slot for B queries; a failed allocation leaves the slot empty, never dangling
+int kino_ensure_slot(uavmp_ctx* ctx, PlanSlot& sl, int B) {
+  if (B <= sl.cap && sl.path_cap == ctx->path_cap && sl.pop_cap == ctx->pop_cap) return UAVMP_OK;
+  const int cap = std::max(B, sl.cap);
+  auto fr = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
+  fr(sl.d_q); fr(sl.d_order); fr(sl.d_status); fr(sl.d_use); fr(sl.d_npop); fr(sl.d_hash); fr(sl.d_npath); fr(sl.d_path_stage);
+  fr(sl.d_trace); fr(sl.d_offsets);
+  sl.cap = 0;
+  UAVMP_CUDA(ctx, cudaMalloc(&sl.d_q, (size_t)cap * 12 * sizeof(double)));
+  UAVMP_CUDA(ctx, cudaMalloc(&sl.d_order, (size_t)cap * 4 * sizeof(int)));  // idx | idx_sorted | key | key_sorted
+  UAVMP_CUDA(ctx, cudaMalloc(&sl.d_status, (size_t)cap * sizeof(int)));
+  UAVMP_CUDA(ctx, cudaMalloc(&sl.d_use, (size_t)cap * sizeof(int)));
+  UAVMP_CUDA(ctx, cudaMalloc(&sl.d_npop, (size_t)cap * sizeof(int)));
+  UAVMP_CUDA(ctx, cudaMalloc(&sl.d_hash, (size_t)cap * sizeof(unsigned long long)));
+  UAVMP_CUDA(ctx, cudaMalloc(&sl.d_npath, (size_t)cap * sizeof(int)));
+  UAVMP_CUDA(ctx, cudaMalloc(&sl.d_path_stage, (size_t)cap * ctx->path_cap * 3 * sizeof(double)));
+  UAVMP_CUDA(ctx, cudaMalloc(&sl.d_offsets, (size_t)(cap + 1) * sizeof(long long)));
+  if (ctx->pop_cap > 0) UAVMP_CUDA(ctx, cudaMalloc(&sl.d_trace, (size_t)cap * ctx->pop_cap * 3 * sizeof(int)));
+  if (!sl.d_misc) UAVMP_CUDA(ctx, cudaMalloc(&sl.d_misc, 64));
+  if (!sl.d_counters) UAVMP_CUDA(ctx, cudaMalloc(&sl.d_counters, 8 * sizeof(unsigned long long)));
+  if (!sl.h_info) UAVMP_CUDA(ctx, cudaHostAlloc((void**)&sl.h_info, sizeof(*sl.h_info), cudaHostAllocDefault));
+  {  // radix-sort scratch for the processing order
+    int* idx = sl.d_order; int* idx_s = idx + cap; float* key = (float*)(idx_s + cap); float* key_s = key + cap;
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, key, key_s, idx, idx_s, cap, 0, 32, sl.stream);
+    if (tb > sl.cub_tmp_bytes) {
+      fr(sl.d_cub_tmp); sl.cub_tmp_bytes = 0;
+      UAVMP_CUDA(ctx, cudaMalloc(&sl.d_cub_tmp, tb));
+      sl.cub_tmp_bytes = tb;
+    }
+  }
+  sl.cap = cap; sl.path_cap = ctx->path_cap; sl.pop_cap = ctx->pop_cap;
   return UAVMP_OK;
 }
 
-int kino_launch_search(uavmp_ctx* ctx, int B, const double* d_sp, const double* d_sv, const double* d_ep,
-                       const double* d_ev, bool sort_order) {
-  cudaStream_t st = ctx->stream;
+// margin of the float ellipsoid filters: 1 % (2 mm for the distance cull), or more when the map's coordinates are coarse in float
+// (the filters subtract float coordinates: error ~ 2 ulp of the largest |coordinate|, amplified by 2 R / min(r, h)^2 in the
+// quadratic form)
+static void float_filter_margins(const uavmp_ctx* ctx, float& slab_margin, double& delta) {
+  double maxc = 0.0;
+  for (int ax = 0; ax < 3; ax++) maxc = std::max(maxc, std::max(std::fabs(ctx->origin[ax]), std::fabs(ctx->origin[ax] + ctx->map_size[ax])));
+  delta = 2.0 * maxc * 1.1920928955078125e-7;
+  const double R = std::max(ctx->kp.robot_r, ctx->kp.robot_h);
+  const double mn = std::min(ctx->kp.robot_r, ctx->kp.robot_h);
+  const double err = 2.0 * R * delta / (mn * mn);
+  slab_margin = (float)std::max(0.01, 4.0 * err + 1e-4);
+}
+
+int kino_launch_search(uavmp_ctx* ctx, PlanSlot& sl, int B, const double* d_sp, const double* d_sv, const double* d_ep,
+                       const double* d_ev, bool sort_order, bool profile, const KinoQpDev* qp_in, const QpPlanDev* plan,
+                       const uavmp_osqp_settings* settings) {
+  cudaStream_t st = sl.stream;
   int* order = nullptr;
+  sl.launches_aux = 0;
   if (sort_order && B > 1) {
-    int* idx = ctx->d_order; int* idx_s = idx + B; float* key = (float*)(idx_s + B); float* key_s = key + B;
+    int* idx = sl.d_order; int* idx_s = idx + B; float* key = (float*)(idx_s + B); float* key_s = key + B;
     k_dist_keys<<<nblk(B, 256), 256, 0, st>>>(d_sp, d_ep, B, key, idx);
-    size_t tb = 0;
-    cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, key, key_s, idx, idx_s, B, 0, 32, st);
-    if (tb > ctx->cub_tmp_bytes) {
-      if (ctx->d_cub_tmp) cudaFree(ctx->d_cub_tmp);
-      UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_cub_tmp, tb));
-      ctx->cub_tmp_bytes = tb;
-    }
-    cub::DeviceRadixSort::SortPairsDescending(ctx->d_cub_tmp, tb, key, key_s, idx, idx_s, B, 0, 32, st);
+    size_t tb = sl.cub_tmp_bytes;
+    cub::DeviceRadixSort::SortPairsDescending(sl.d_cub_tmp, tb, key, key_s, idx, idx_s, B, 0, 32, st);
     order = idx_s;
+    sl.launches_aux = 1;  // k_dist_keys (+ cub's radix-sort kernels, library code)
   }
-  UAVMP_CUDA(ctx, cudaMemsetAsync(ctx->d_misc, 0, 64, st));
-  UAVMP_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), st));
+  UAVMP_CUDA(ctx, cudaMemsetAsync(sl.d_misc, 0, 64, st));
+  UAVMP_CUDA(ctx, cudaMemsetAsync(sl.d_counters, 0, 8 * sizeof(unsigned long long), st));
   KinoBatchDev bt;
   bt.B = B; bt.start_pt = d_sp; bt.start_vel = d_sv; bt.end_pt = d_ep; bt.end_vel = d_ev; bt.order = order;
-  bt.status = ctx->d_status; bt.use_node_num = ctx->d_use; bt.n_pop = ctx->d_npop; bt.pop_hash = ctx->d_hash;
-  bt.n_path = ctx->d_npath; bt.path_stage = ctx->d_path_stage; bt.path_cap = ctx->path_cap;
-  bt.pop_trace = ctx->d_trace; bt.pop_cap = ctx->pop_cap;
-  bt.error_flag = ctx->d_misc; bt.next_query = ctx->d_misc + 1; bt.counters = ctx->d_counters;
+  bt.status = sl.d_status; bt.use_node_num = sl.d_use; bt.n_pop = sl.d_npop; bt.pop_hash = sl.d_hash;
+  bt.n_path = sl.d_npath; bt.path_stage = sl.d_path_stage; bt.path_cap = sl.path_cap;
+  bt.pop_trace = sl.d_trace; bt.pop_cap = sl.pop_cap;
+  bt.error_flag = sl.d_misc; bt.next_query = sl.d_misc + 1; bt.counters = sl.d_counters;
   bt.phase_cycles = nullptr; bt.query_cycles = nullptr; bt.query_phase = nullptr;
-  bt.done_flag = ctx->fuse_flags; bt.qp_solved = ctx->fuse_qp_solved;
-  bt.dbg = (ctx->fuse_flags && ctx->dbg_ptr) ? ctx->dbg_ptr : nullptr;
-  if (bt.dbg) { unsigned long long init2[2] = {~0ull, 0ull}; cudaMemcpyAsync(ctx->dbg_ptr + 2, init2, sizeof(init2), cudaMemcpyHostToDevice, st); }
-  if (ctx->profile_phases) {
+  if (profile) {
     if (!ctx->d_phase) UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_phase, 16 * sizeof(unsigned long long)));
     if (ctx->query_cycles_cap < B) {
       if (ctx->d_query_cycles) cudaFree(ctx->d_query_cycles);
+      ctx->d_query_cycles = nullptr; ctx->query_cycles_cap = 0;
       UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_query_cycles, (size_t)B * 17 * sizeof(long long)));
       ctx->query_cycles_cap = B;
     }
@@ -1900,43 +2012,41 @@ int kino_launch_search(uavmp_ctx* ctx, int B, const double* d_sp, const double* 
   cudaFuncSetAttribute(kino_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SearchSmem));
   CUtensorMap tm;
   memcpy(&tm, ctx->tmap_bytes, sizeof(tm));
-  if (ctx->fuse_flags) cudaEventRecord(ctx->ev_fuse[0], st);  // flags zeroed, order sorted: the overlapped QP may start polling
-  // margin of the float ellipsoid filter: 1 %, or more when the map's coordinates are coarse in float (the filter subtracts
-  // float coordinates: error ~ 2 ulp of the largest |coordinate|, amplified by 2 R / min(r, h)^2 in the quadratic form)
   float slab_margin = 0.01f;
-  {
-    double maxc = 0.0;
-    for (int ax = 0; ax < 3; ax++) maxc = std::max(maxc, std::max(std::fabs(ctx->origin[ax]), std::fabs(ctx->origin[ax] + ctx->map_size[ax])));
-    const double delta = 2.0 * maxc * 1.1920928955078125e-7;
-    const double R = std::max(ctx->kp.robot_r, ctx->kp.robot_h);
-    const double mn = std::min(ctx->kp.robot_r, ctx->kp.robot_h);
-    const double err = 2.0 * R * delta / (mn * mn);
-    slab_margin = (float)std::max(0.01, 4.0 * err + 1e-4);
-  }
-  kino_search_kernel<<<grid, KT, sizeof(SearchSmem), st>>>(ctx->d_kparams, lat, ctx->d_map, ctx->d_arenas, bt, bits, tm,
-                                                          (ctx->have_tmap && !getenv("UAVMP_NO_TMA")) ? 1 : 0, slab_margin);
+  double delta = 0.0;
+  float_filter_margins(ctx, slab_margin, delta);
+  const double box_r = std::max(ctx->kp.robot_r, ctx->kp.robot_h) * 1.001 + 1e-6;
+  const float cullf = (float)((box_r + 2e-3 + 4.0 * delta) * (box_r + 2e-3 + 4.0 * delta));
+  KinoQpDev qp;
+  QpPlanDev pl;
+  uavmp_osqp_settings qs;
+  memset(&qp, 0, sizeof(qp)); memset(&pl, 0, sizeof(pl)); memset(&qs, 0, sizeof(qs));
+  if (qp_in && qp_in->enabled) { qp = *qp_in; pl = *plan; qs = *settings; }
+  kino_search_kernel<<<grid, KT, sizeof(SearchSmem), st>>>(ctx->d_kparams, lat, ctx->d_map, ctx->d_arenas, ctx->d_arena_busy,
+                                                          ctx->n_arenas, bt, bits, tm,
+                                                          (ctx->have_tmap && !getenv("UAVMP_NO_TMA")) ? 1 : 0, slab_margin, cullf, qp, pl, qs);
   UAVMP_CUDA(ctx, cudaGetLastError());
-  ctx->tm.search_launches = 1;
+  sl.launches_search = 1;
   return UAVMP_OK;
 }
 
-int kino_pack_paths(uavmp_ctx* ctx, int B) {
-  cudaStream_t st = ctx->stream;
-  k_offsets<<<1, 1024, 0, st>>>(ctx->d_npath, B, ctx->d_offsets);
+int kino_pack_paths(uavmp_ctx* ctx, PlanSlot& sl, int B) {
+  cudaStream_t st = sl.stream;
+  k_offsets<<<1, 1024, 0, st>>>(sl.d_npath, B, sl.d_offsets);
   long long total = 0;
-  UAVMP_CUDA(ctx, cudaMemcpyAsync(&total, ctx->d_offsets + B, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  UAVMP_CUDA(ctx, cudaMemcpyAsync(&total, sl.d_offsets + B, sizeof(long long), cudaMemcpyDeviceToHost, st));
   UAVMP_CUDA(ctx, cudaStreamSynchronize(st));
   if (total > ctx->path_packed_cap) {
     if (ctx->d_path_packed) cudaFree(ctx->d_path_packed);
-    ctx->d_path_packed = nullptr;
+    ctx->d_path_packed = nullptr; ctx->path_packed_cap = 0;
     long long cap = std::max(total, (long long)1024);
     UAVMP_CUDA(ctx, cudaMalloc(&ctx->d_path_packed, (size_t)cap * 3 * sizeof(double)));
     ctx->path_packed_cap = cap;
   }
-  if (total > 0) k_pack_paths<<<B, 128, 0, st>>>(ctx->d_path_stage, ctx->d_npath, ctx->d_offsets, ctx->path_cap, ctx->d_path_packed);
+  if (total > 0) k_pack_paths<<<B, 128, 0, st>>>(sl.d_path_stage, sl.d_npath, sl.d_offsets, sl.path_cap, ctx->d_path_packed);
   UAVMP_CUDA(ctx, cudaGetLastError());
   ctx->last_total_path = total;
-  ctx->tm.aux_launches = 2;
+  sl.launches_aux += 2;
   return UAVMP_OK;
 }
 

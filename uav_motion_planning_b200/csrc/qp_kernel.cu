@@ -15,8 +15,13 @@
 // index lists (uniform, read-only loads) while its own numbers live in a batch-interleaved workspace:
 // element e of problem b is ws[e * stride + b].  A warp therefore touches 32 consecutive doubles per access
 // (fully coalesced 256 B) and never diverges on structure — only on the data-dependent iteration count.
-// The LDL' uses our own minimum-degree order, not OSQP's AMD, so results agree with the reference to rounding
-// (~1e-9 relative), not bit for bit; the parity gate is 1e-5 relative plus identical status / iteration counts.
+// The fill-reducing order is the one the reference's own AMD returns for this pattern (csrc/amd_perm_table.inc, order 5 / 7,
+// S <= 40), so the ADMM iterates are bit-identical to the reference's OSQP; other (order, S) fall back to a plain
+// minimum-degree order and agree to rounding only (the parity gate there is 1e-5 relative + identical status / iterations).
+//
+// Three executions of the same restatement: qp_solve_kernel (one thread per problem, batch-interleaved workspace),
+// qp_solve_warp_kernel (one warp per problem, workspace in shared memory) and — for the search -> QP pipeline — the same
+// warp body called from inside kino_search_kernel by the CTA that finished the query (kino_kernel.cu: qp_round).
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -29,7 +34,6 @@
 #include "qp_plan.h"
 #include "uavmp_internal.h"
 
-int ensure_bytes(uavmp_ctx* ctx, void** p, size_t* have, size_t want);
 
 struct QpPlan {
   QpPlanHost* host = nullptr;
@@ -56,113 +60,13 @@ __global__ void qp_solve_warp_kernel(QpPlanDev pl, QpIo io, uavmp_osqp_settings 
   qp_warp_solve_one(pl, io, S, qpw_sm + (size_t)warp * pl.ws_warp, b);
 }
 
-// ---- overlapped pipeline: the QP of a query starts as soon as ITS search has finished ---------------------------------------
-// Launched on a second, low-priority stream right after the search kernel.  Its CTAs become resident as the persistent search
-// CTAs retire (the search kernel's tail is a handful of very long queries on otherwise idle SMs), wait for their query's
-// completion flag, build the waypoints themselves and write straight into the caller's coefficient array.
-struct QpFuse {
-  int B, path_cap, Sg, n;
-  double seg_time;
-  const int* done_flag; const int* order; const int* search_status; const int* n_path; const double* path_stage;
-  const double* sv; const double* ev;
-  double* pos; double* bv; double* ba; double* bj; double* T;
-  double* coef_out; int* qp_solved; int* error_flag;
-  unsigned long long* dbg;
-};
-
-__global__ void __launch_bounds__(QP_TPB) qp_solve_fused_kernel(QpPlanDev pl, QpIo io, uavmp_osqp_settings S, double* ws, int use_smem,
-                                                                QpFuse fu) {
-  extern __shared__ __align__(16) double qp_sv[];
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= io.B) return;
-  if (fu.dbg && threadIdx.x == 0) {  // diagnostics: when did this CTA become resident / finish (globaltimer, ns)
-    unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    atomicMin(&fu.dbg[0], t); atomicMax(&fu.dbg[1], t);
-  }
-  const int ax = b / fu.B, w = b % fu.B;
-  const int q = fu.order ? fu.order[w] : w;   // neighbouring lanes = queries dispatched at about the same time
-  {
-    const volatile int* flag = fu.done_flag + q;
-    long long spins = 0;
-    while (*flag == 0) {
-      __nanosleep(2000);
-      if (++spins > 4000000ll) { atomicOr(fu.error_flag, 8); return; }  // ~8 s: the search never finished; do not hang the GPU
-    }
-    __threadfence();
-  }
-  const int np = fu.n_path[q];
-  const bool ok = (fu.search_status[q] == UAVMP_REACH_END) && np >= 1;
-  double* out = fu.coef_out + ((size_t)q * 3 + ax) * fu.n;
-  if (!ok) {
-    for (int j = 0; j < fu.n; j++) out[j] = 0.0;
-    return;
-  }
-  const int Sg = fu.Sg;
-  const double* path = fu.path_stage + (size_t)q * fu.path_cap * 3;
-  for (int k = 0; k <= Sg; k++) fu.pos[(size_t)b * (Sg + 1) + k] = path[3 * (((long long)k * (np - 1)) / Sg) + ax];
-  fu.bv[(size_t)b * 2] = fu.sv[3 * q + ax]; fu.bv[(size_t)b * 2 + 1] = fu.ev[3 * q + ax];
-  fu.ba[(size_t)b * 2] = 0.0; fu.ba[(size_t)b * 2 + 1] = 0.0;
-  fu.bj[(size_t)b * 2] = 0.0; fu.bj[(size_t)b * 2 + 1] = 0.0;
-  for (int sgm = 0; sgm < Sg; sgm++) fu.T[(size_t)b * Sg + sgm] = fu.seg_time;
-  qp_solve_one(pl, io, S, ws, b, use_smem ? qp_sv : nullptr);
-  const double* mine = io.coef + (size_t)b * fu.n;
-  for (int j = 0; j < fu.n; j++) out[j] = mine[j];
-  if (!io.solved[b]) atomicAnd(fu.qp_solved + q, 0);
-}
-
-__global__ void qp_solve_warp_fused_kernel(QpPlanDev pl, QpIo io, uavmp_osqp_settings S, int warps_per_cta, QpFuse fu) {
-  extern __shared__ __align__(16) double qpw_sm[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * warps_per_cta + warp;
-  if (b >= io.B) return;
-  if (fu.dbg && lane == 0) {
-    unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    atomicMin(&fu.dbg[0], t); atomicMax(&fu.dbg[1], t);
-  }
-  const int ax = b / fu.B, wq = b % fu.B;
-  const int q = fu.order ? fu.order[wq] : wq;
-  int gave_up = 0;
-  if (lane == 0) {
-    const volatile int* flag = fu.done_flag + q;
-    long long spins = 0;
-    while (*flag == 0) {
-      __nanosleep(1000);
-      if (++spins > 8000000ll) { atomicOr(fu.error_flag, 8); gave_up = 1; break; }  // ~8 s: never hang the GPU
-    }
-    __threadfence();
-  }
-  gave_up = __shfl_sync(0xffffffffu, gave_up, 0);
-  if (gave_up) return;
-  const int np = fu.n_path[q];
-  const bool ok = (fu.search_status[q] == UAVMP_REACH_END) && np >= 1;
-  double* out = fu.coef_out + ((size_t)q * 3 + ax) * fu.n;
-  if (!ok) {
-    for (int j = lane; j < fu.n; j += 32) out[j] = 0.0;
-    return;
-  }
-  const int Sg = fu.Sg;
-  const double* path = fu.path_stage + (size_t)q * fu.path_cap * 3;
-  for (int k = lane; k <= Sg; k += 32) fu.pos[(size_t)b * (Sg + 1) + k] = path[3 * (((long long)k * (np - 1)) / Sg) + ax];
-  for (int sgm = lane; sgm < Sg; sgm += 32) fu.T[(size_t)b * Sg + sgm] = fu.seg_time;
-  if (lane == 0) {
-    fu.bv[(size_t)b * 2] = fu.sv[3 * q + ax]; fu.bv[(size_t)b * 2 + 1] = fu.ev[3 * q + ax];
-    fu.ba[(size_t)b * 2] = 0.0; fu.ba[(size_t)b * 2 + 1] = 0.0;
-    fu.bj[(size_t)b * 2] = 0.0; fu.bj[(size_t)b * 2 + 1] = 0.0;
-  }
-  __syncwarp();
-  qp_warp_solve_one(pl, io, S, qpw_sm + (size_t)warp * pl.ws_warp, b);
-  const double* mine = io.coef + (size_t)b * fu.n;
-  for (int j = lane; j < fu.n; j += 32) out[j] = mine[j];
-  if (lane == 0 && !io.solved[b]) atomicAnd(fu.qp_solved + q, 0);
-}
-
 // warps per CTA of the warp-per-problem kernels: as many problems as ~100 KB of shared memory hold (2 CTAs / SM); 0 = does not fit
-static int qpw_warps_per_cta(const QpPlanDev& pl, int B, bool overlapped) {
+static int qpw_warps_per_cta(const QpPlanDev& pl, int B) {
   if (getenv("UAVMP_QP_THREAD")) return 0;
   // Measured on B200 (order 7, S 8): a problem takes ~7.6 ms on a warp and ~50 ms on a thread, but 12 288 threads run at once
-  // while only ~1 200 warps do (shared memory).  So: the overlapped pipeline always takes the warp kernel (latency after the
-  // last search is what counts there), a stand-alone batch takes it while it is small enough to win on wall time.
-  if (!overlapped && B > 6000 && !getenv("UAVMP_QP_WARP")) return 0;
+  // while only ~1 200 warps do (shared memory).  A stand-alone batch takes the warp kernel while it is small enough to win
+  // on wall time.
+  if (B > 6000 && !getenv("UAVMP_QP_WARP")) return 0;
   const size_t per = (size_t)pl.ws_warp * sizeof(double);
   if (per > 200 * 1024) return 0;
   int w = (int)((100 * 1024) / per);
@@ -243,6 +147,14 @@ void qp_free_plans(uavmp_ctx* ctx) {
   ctx->qp_plans.clear();
 }
 
+// device view of the (order, S) plan, for the in-kernel QP of the search kernel
+int qp_get_plan_dev(uavmp_ctx* ctx, int order, int S, const QpPlanDev** out) {
+  QpPlan* p = get_plan(ctx, order, S);
+  if (!p) return uavmp_fail(ctx, UAVMP_ECUDA, "cannot build the QP plan");
+  *out = &p->dev;
+  return UAVMP_OK;
+}
+
 int qp_plan_stats(uavmp_ctx* ctx, int order, int S, int* out6) {
   QpPlan* p = get_plan(ctx, order, S);
   if (!p) return UAVMP_ECUDA;
@@ -251,28 +163,30 @@ int qp_plan_stats(uavmp_ctx* ctx, int order, int S, int* out6) {
   return UAVMP_OK;
 }
 
-int qp_solve_batch_dev(uavmp_ctx* ctx, int order, int S, int B, const double* d_pos, const double* d_bv,
-                       const double* d_ba, const double* d_bj, const double* d_T, const uavmp_osqp_settings* st,
-                       double* d_coef, int* d_solved, int* d_status, int* d_iters) {
+int qp_solve_batch_dev(uavmp_ctx* ctx, cudaStream_t stream, QpScratch& scr, int* launches, int order, int S, int B,
+                       const double* d_pos, const double* d_bv, const double* d_ba, const double* d_bj, const double* d_T,
+                       const uavmp_osqp_settings* st, double* d_coef, int* d_solved, int* d_status, int* d_iters) {
   QpPlan* p = get_plan(ctx, order, S);
   if (!p) return uavmp_fail(ctx, UAVMP_ECUDA, "cannot build the QP plan");
   if (st->max_iter <= 0 || st->check_termination < 0 || st->scaling < 0)
     return uavmp_fail(ctx, UAVMP_EINVAL, "bad OSQP settings");
   const int stride = (B + 31) & ~31;
-  const size_t need = (size_t)p->dev.ws_doubles * stride * sizeof(double);
-  int r = ensure_bytes(ctx, &ctx->d_qp_ws, &ctx->qp_ws_bytes, need);
-  if (r) return r;
   QpIo io;
   io.pos = d_pos; io.bv = d_bv; io.ba = d_ba; io.bj = d_bj ? d_bj : d_ba; io.T = d_T;
   io.coef = d_coef; io.solved = d_solved; io.status = d_status; io.iters = d_iters; io.B = B; io.stride = stride;
-  if (const int wpc = qpw_warps_per_cta(p->dev, B, false)) {
+  if (launches) *launches = 1;
+  if (const int wpc = qpw_warps_per_cta(p->dev, B)) {
     // one warp per problem, everything in shared memory: no global workspace at all
     const size_t smem = (size_t)wpc * p->dev.ws_warp * sizeof(double);
     if (smem > 48 * 1024) cudaFuncSetAttribute(qp_solve_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    qp_solve_warp_kernel<<<(B + wpc - 1) / wpc, 32 * wpc, smem, ctx->stream>>>(p->dev, io, *st, wpc);
+    qp_solve_warp_kernel<<<(B + wpc - 1) / wpc, 32 * wpc, smem, stream>>>(p->dev, io, *st, wpc);
     UAVMP_CUDA(ctx, cudaGetLastError());
-    ctx->tm.qp_launches = 1;
     return UAVMP_OK;
+  }
+  {
+    const size_t need = (size_t)p->dev.ws_doubles * stride * sizeof(double);
+    int r = ensure_bytes(ctx, &scr.ws, &scr.ws_bytes, need);
+    if (r) return r;
   }
   const int threads = QP_TPB;
   // bp and xz in shared memory when they fit (2 N doubles per thread); otherwise everything stays in the workspace
@@ -280,84 +194,27 @@ int qp_solve_batch_dev(uavmp_ctx* ctx, int order, int S, int B, const double* d_
   const int use_smem = smem <= 200 * 1024 ? 1 : 0;
   if (!use_smem) smem = 0;
   if (smem > 48 * 1024) cudaFuncSetAttribute(qp_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  qp_solve_kernel<<<(B + threads - 1) / threads, threads, smem, ctx->stream>>>(p->dev, io, *st, (double*)ctx->d_qp_ws, use_smem);
+  qp_solve_kernel<<<(B + threads - 1) / threads, threads, smem, stream>>>(p->dev, io, *st, (double*)scr.ws, use_smem);
   UAVMP_CUDA(ctx, cudaGetLastError());
-  ctx->tm.qp_launches = 1;
   return UAVMP_OK;
 }
 
-// issue the overlapped QP of a plan batch on ctx->stream2 (the caller has already launched the search on ctx->stream)
-int qp_launch_fused(uavmp_ctx* ctx, int order, int S, int B, double seg_time, const double* d_sv, const double* d_ev,
-                    const int* d_order, const uavmp_osqp_settings* st, double* d_coef, int* d_qp_solved, bool prepare_only) {
-  QpPlan* p = get_plan(ctx, order, S);
-  if (!p) return uavmp_fail(ctx, UAVMP_ECUDA, "cannot build the QP plan");
-  const int nB = 3 * B, n = (order + 1) * S;
-  const int stride = (nB + 31) & ~31;
-  int r = ensure_bytes(ctx, &ctx->d_qp_ws, &ctx->qp_ws_bytes, (size_t)p->dev.ws_doubles * stride * sizeof(double)); if (r) return r;
-  r = ensure_bytes(ctx, (void**)&ctx->d_wp, &ctx->wp_bytes, (size_t)nB * ((S + 1) + 6 + S) * sizeof(double)); if (r) return r;
-  r = ensure_bytes(ctx, (void**)&ctx->d_qp_out, &ctx->qp_out_bytes, (size_t)nB * n * sizeof(double)); if (r) return r;
-  r = ensure_bytes(ctx, (void**)&ctx->d_qp_int, &ctx->qp_int_bytes, (size_t)nB * 3 * sizeof(int)); if (r) return r;
-  if (prepare_only) return UAVMP_OK;  // allocations (which synchronise the device) are done before the search is launched
-  double* pos = ctx->d_wp; double* bv = pos + (size_t)nB * (S + 1); double* ba = bv + (size_t)nB * 2; double* bj = ba + (size_t)nB * 2;
-  double* T = bj + (size_t)nB * 2;
-  QpIo io;
-  io.pos = pos; io.bv = bv; io.ba = ba; io.bj = bj; io.T = T;
-  io.coef = ctx->d_qp_out; io.solved = ctx->d_qp_int; io.status = ctx->d_qp_int + nB; io.iters = ctx->d_qp_int + 2 * nB;
-  io.B = nB; io.stride = stride;
-  QpFuse fu;
-  fu.B = B; fu.path_cap = ctx->path_cap; fu.Sg = S; fu.n = n; fu.seg_time = seg_time;
-  fu.done_flag = ctx->d_done_flags; fu.order = d_order; fu.search_status = ctx->d_status; fu.n_path = ctx->d_npath;
-  fu.path_stage = ctx->d_path_stage; fu.sv = d_sv; fu.ev = d_ev;
-  fu.pos = pos; fu.bv = bv; fu.ba = ba; fu.bj = bj; fu.T = T;
-  fu.coef_out = d_coef; fu.qp_solved = d_qp_solved; fu.error_flag = ctx->d_misc;
-  fu.dbg = nullptr;
-  if (getenv("UAVMP_DBG_OVERLAP")) {
-    static unsigned long long* d_dbg = nullptr;
-    if (!d_dbg) cudaMalloc(&d_dbg, 64);
-    unsigned long long init[4] = {~0ull, 0ull, 0, 0};
-    cudaMemcpyAsync(d_dbg, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream2);
-    fu.dbg = d_dbg;
-    ctx->dbg_ptr = d_dbg;
-  }
-  if (const int wpc = qpw_warps_per_cta(p->dev, nB, true)) {
-    const size_t smem_w = (size_t)wpc * p->dev.ws_warp * sizeof(double);
-    if (smem_w > 48 * 1024) cudaFuncSetAttribute(qp_solve_warp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
-    qp_solve_warp_fused_kernel<<<(nB + wpc - 1) / wpc, 32 * wpc, smem_w, ctx->stream2>>>(p->dev, io, *st, wpc, fu);
-    UAVMP_CUDA(ctx, cudaGetLastError());
-    ctx->tm.qp_launches = 1;
-    return UAVMP_OK;
-  }
-  const int threads = QP_TPB;
-  size_t smem = (size_t)2 * p->dev.N * sizeof(double) * threads;
-  const int use_smem = smem <= 200 * 1024 ? 1 : 0;
-  if (!use_smem) smem = 0;
-  if (smem > 48 * 1024) cudaFuncSetAttribute(qp_solve_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  qp_solve_fused_kernel<<<(nB + threads - 1) / threads, threads, smem, ctx->stream2>>>(p->dev, io, *st, (double*)ctx->d_qp_ws, use_smem, fu);
-  UAVMP_CUDA(ctx, cudaGetLastError());
-  ctx->tm.qp_launches = 1;
-  return UAVMP_OK;
-}
-
-int qp_waypoints_from_paths(uavmp_ctx* ctx, int B, int S, double seg_time, const double* d_sv, const double* d_ev,
-                            int order, double** d_pos, double** d_bv, double** d_ba, double** d_bj, double** d_T) {
-  (void)order;
+int qp_waypoints_from_paths(uavmp_ctx* ctx, PlanSlot& sl, int B, int S, double seg_time, const double* d_sv, const double* d_ev,
+                            double** d_pos, double** d_bv, double** d_ba, double** d_bj, double** d_T) {
   const size_t nB = (size_t)3 * B;
-  const size_t need = nB * ((S + 1) + 6 + S) * sizeof(double);
-  int r = ensure_bytes(ctx, (void**)&ctx->d_wp, &ctx->wp_bytes, need);
-  if (r) return r;
-  double* pos = ctx->d_wp; double* bv = pos + nB * (S + 1); double* ba = bv + nB * 2; double* bj = ba + nB * 2;
+  double* pos = sl.d_wp; double* bv = pos + nB * (S + 1); double* ba = bv + nB * 2; double* bj = ba + nB * 2;
   double* T = bj + nB * 2;
-  k_waypoints<<<(B + 127) / 128, 128, 0, ctx->stream>>>(B, S, seg_time, ctx->d_npath, ctx->d_path_stage, ctx->path_cap,
-                                                        ctx->d_status, d_sv, d_ev, pos, bv, ba, bj, T);
+  k_waypoints<<<(B + 127) / 128, 128, 0, sl.stream>>>(B, S, seg_time, sl.d_npath, sl.d_path_stage, sl.path_cap, sl.d_status, d_sv,
+                                                      d_ev, pos, bv, ba, bj, T);
   UAVMP_CUDA(ctx, cudaGetLastError());
   *d_pos = pos; *d_bv = bv; *d_ba = ba; *d_bj = bj; *d_T = T;
   return UAVMP_OK;
 }
 
-int qp_scatter_plan_outputs(uavmp_ctx* ctx, int B, int order, int S, const int* d_solved3, const double* d_coef3,
+int qp_scatter_plan_outputs(uavmp_ctx* ctx, PlanSlot& sl, int B, int order, int S, const int* d_solved3, const double* d_coef3,
                             int* d_qp_solved, double* d_coef) {
   const int n = (order + 1) * S;
-  k_scatter_plan<<<B, 128, 0, ctx->stream>>>(B, n, ctx->d_status, d_solved3, d_coef3, d_qp_solved, d_coef);
+  k_scatter_plan<<<B, 128, 0, sl.stream>>>(B, n, sl.d_status, d_solved3, d_coef3, d_qp_solved, d_coef);
   UAVMP_CUDA(ctx, cudaGetLastError());
   return UAVMP_OK;
 }

@@ -102,13 +102,61 @@ struct KinoBatchDev {
   unsigned long long* phase_cycles;  // optional profiling: 8 words, SM cycles per phase summed over CTAs
   long long* query_cycles;           // optional profiling: B words, SM cycles each query occupied its CTA
   unsigned long long* query_phase;   // optional profiling: B x 16 words, the phase cycles of every query
-  int* done_flag;                    // optional: done_flag[q] = 1 once query q's outputs are visible (overlapped QP)
-  unsigned long long* dbg;           // optional diagnostics (globaltimer stamps)
-  int* qp_solved;                    // optional: initialised to "search reached the goal" for the overlapped QP to AND into
+};
+
+// In-kernel QP of the plan pipeline: the CTA that finished a query also solves its three 1-D problems (one warp per problem,
+// workspace in the shared memory the search no longer needs), so a batch is ONE kernel with no second stream and no
+// cross-kernel flag polling.  Problem id = 3 * query + axis.
+struct KinoQpDev {
+  int enabled;               // 0: search only
+  int warps;                 // problems solved concurrently per round (how many workspaces fit in the overlay)
+  int Sg, n;                 // segments, coefficients per axis ((order + 1) * S)
+  double seg_time;
+  double* pos; double* bv; double* ba; double* bj; double* T;  // per-problem inputs of qp_warp_solve_one (3 B problems)
+  double* coef;              // B x 3 x n, the caller-visible layout (problem id * n)
+  int* solved3; int* status3; int* iters3;                     // per problem
+  int* qp_solved;            // per query: search reached the goal AND all three axes solved
 };
 
 // ---- host-side context -----------------------------------------------------------------------------
-struct QpPlan;  // qp_symbolic.cpp
+struct QpPlan;  // qp_kernel.cu
+
+#define UAVMP_NSLOT 7  // slot 0: the synchronous entry points; 1..6: batches in flight (uavmp_plan_submit) — the tail of a batch
+                       // spans ~3 batch times
+
+// device scratch of the stand-alone QP kernels (one per user of qp_solve_batch_dev: the context and every slot)
+struct QpScratch {
+  void* ws = nullptr; size_t ws_bytes = 0;       // batch-interleaved workspace of the thread-per-problem kernel
+};
+
+// Everything ONE batch in flight owns.  Slot 0 runs on the context's stream and serves the synchronous entry points.
+struct PlanSlot {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[5];               // 0 start, 1 inputs on the device, 2 after the kernels, 3 outputs copied, 4 done (info copied)
+  bool in_flight = false;
+  long long ticket = -1;
+  int B = 0;
+  bool host_io = false;
+  // search batch buffers
+  int cap = 0, path_cap = 0, pop_cap = 0;
+  double* d_q = nullptr;           // 4 x B x 3 (host-input calls)
+  int* d_order = nullptr;          // idx | idx_sorted | key | key_sorted
+  int* d_status = nullptr; int* d_use = nullptr; int* d_npop = nullptr; unsigned long long* d_hash = nullptr;
+  int* d_npath = nullptr; double* d_path_stage = nullptr; int* d_trace = nullptr; long long* d_offsets = nullptr;
+  int* d_misc = nullptr;           // [0] error flag, [1] work counter
+  unsigned long long* d_counters = nullptr;
+  void* d_cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
+  // plan pipeline
+  double* d_wp = nullptr; size_t wp_bytes = 0;         // per-problem QP inputs (3 B problems)
+  int* d_qp_int = nullptr; size_t qp_int_bytes = 0;    // solved | status | iters per problem
+  double* d_qp_out = nullptr; size_t qp_out_bytes = 0; // sequential fallback only: axis-major coefficients
+  double* d_plan_out = nullptr; size_t plan_out_bytes = 0;  // host-output calls: B x 3 x n staging
+  int* d_plan_io = nullptr; size_t plan_io_bytes = 0;       // host-output calls: status | qp_solved
+  QpScratch qp_scr;
+  // pinned host mirror of the error flag and the counters, written by the stream at the end of the batch
+  struct HostInfo { int flag; int pad; unsigned long long counters[8]; }* h_info = nullptr;
+  int launches_search = 0, launches_qp = 0, launches_aux = 0;
+};
 
 struct uavmp_ctx {
   int device = 0;
@@ -123,6 +171,7 @@ struct uavmp_ctx {
   double* d_lattice = nullptr;  // ux|uy|uz|ginc|Einv|b3
   float4* d_b3f = nullptr;
   int nprim = 0;
+  int path_cap = 1024, pop_cap = 0;
 
   // map
   bool have_map = false;
@@ -142,46 +191,34 @@ struct uavmp_ctx {
   bool have_tmap = false;
   bool flags_dirty = true;
 
-  // search arenas
+  // search arenas: a pool shared by every search kernel in flight; a CTA takes a free one when it starts (arena_busy)
   int n_arenas = 0, arena_nodes = 0, table_size = 0;
   void* d_arena_mem = nullptr;
   KinoArena* d_arenas = nullptr;
+  int* d_arena_busy = nullptr;
 
-  // batch buffers
-  int batch_cap = 0, path_cap = 1024, pop_cap = 0;
-  double* d_q = nullptr;  // 4 x B x 3
-  int* d_order = nullptr;
-  int* d_status = nullptr; int* d_use = nullptr; int* d_npop = nullptr; unsigned long long* d_hash = nullptr;
-  int* d_npath = nullptr; double* d_path_stage = nullptr; int* d_trace = nullptr;
-  long long* d_offsets = nullptr; double* d_path_packed = nullptr; long long path_packed_cap = 0;
-  int* d_misc = nullptr;  // [0] error flag, [1] work counter
-  unsigned long long* d_counters = nullptr;
+  // batches
+  PlanSlot slots[UAVMP_NSLOT];
+  long long next_ticket = 0;
+  int last_slot = 0;               // slot of the most recently completed batch (what the legacy getters read)
   long long last_total_path = 0;
-  int last_B = 0;
-  void* d_cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
+  double* d_path_packed = nullptr; long long path_packed_cap = 0;
   bool profile_phases = false;
-  // overlapped pipeline: second (low-priority) stream for the QP kernel, per-query completion flags
-  cudaStream_t stream2 = nullptr; cudaEvent_t ev_fuse[2]; bool fuse_ready = false;
-  int* d_done_flags = nullptr; int done_flags_cap = 0;
-  unsigned long long* dbg_ptr = nullptr;
-  int* fuse_flags = nullptr; int* fuse_qp_solved = nullptr;  // set only while a fused launch is being issued
   unsigned long long* d_phase = nullptr; long long* d_query_cycles = nullptr; int query_cycles_cap = 0;
   int last_grid = 0;
+  uavmp_kino_counters last_counters;
+  int last_error_flag = 0;
 
-  // qp
+  // qp (stand-alone uavmp_minctrl_solve_batch, on the context's stream)
   std::vector<QpPlan*> qp_plans;
-  void* d_qp_ws = nullptr; size_t qp_ws_bytes = 0;
+  QpScratch qp_scr;
   double* d_qp_in = nullptr; size_t qp_in_bytes = 0;
   double* d_qp_out = nullptr; size_t qp_out_bytes = 0;
   int* d_qp_int = nullptr; size_t qp_int_bytes = 0;
-  double* d_plan_out = nullptr; size_t plan_out_bytes = 0;
-  int* d_plan_io = nullptr; size_t plan_io_bytes = 0;
-  double* d_wp = nullptr; size_t wp_bytes = 0;
 
-  // timings
+  // timings of the last completed call
   cudaEvent_t ev[8];
   uavmp_timings tm;
-  bool tm_pending_dev = false;
 };
 
 int uavmp_fail(uavmp_ctx* ctx, int code, const char* fmt, ...);
@@ -191,11 +228,19 @@ int uavmp_fail(uavmp_ctx* ctx, int code, const char* fmt, ...);
     if (e_ != cudaSuccess) return uavmp_fail(ctx, UAVMP_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
   } while (0)
 
+int ensure_bytes(uavmp_ctx* ctx, void** p, size_t* have, size_t want);
+int drain_all(uavmp_ctx* ctx);  // capi.cu: wait for every batch in flight
+int uavmp_map_check_geometry(uavmp_ctx* ctx, int nx, int ny, int nz, const double origin[3], const double map_size[3], double resolution);
+
 // kino_kernel.cu
 int kino_upload_params(uavmp_ctx* ctx);
 int kino_build_map(uavmp_ctx* ctx);
 int kino_ensure_arenas(uavmp_ctx* ctx);
-int kino_ensure_batch(uavmp_ctx* ctx, int B);
-int kino_launch_search(uavmp_ctx* ctx, int B, const double* d_start_pt, const double* d_start_vel,
-                       const double* d_end_pt, const double* d_end_vel, bool sort_order);
-int kino_pack_paths(uavmp_ctx* ctx, int B);
+int kino_ensure_slot(uavmp_ctx* ctx, PlanSlot& sl, int B);
+void kino_free_slot(PlanSlot& sl);
+int kino_qp_overlay_bytes();  // shared memory of the search CTA the in-kernel QP may overlay
+struct QpPlanDev;
+int kino_launch_search(uavmp_ctx* ctx, PlanSlot& sl, int B, const double* d_start_pt, const double* d_start_vel,
+                       const double* d_end_pt, const double* d_end_vel, bool sort_order, bool profile,
+                       const KinoQpDev* qp, const QpPlanDev* plan, const uavmp_osqp_settings* settings);
+int kino_pack_paths(uavmp_ctx* ctx, PlanSlot& sl, int B);

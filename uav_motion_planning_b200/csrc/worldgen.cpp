@@ -1,4 +1,4 @@
-// mapgen.cpp — synthetic world generator used by tests and bench.py (host utility, not the hot path).
+// worldgen.cpp — synthetic world generator used by tests and bench.py (host utility, not the hot path).
 //
 // It DEFINES the inputs both the oracle and the CUDA path consume:
 //   1. global cloud  : the obstacle generators of the reference simulator
@@ -20,7 +20,7 @@
 #include <map>
 #include <vector>
 
-#include "uavmp.h"
+#include "uavmp_worldgen.h"
 
 namespace {
 

@@ -1,4 +1,5 @@
-"""Synthetic worlds (host utility): the reference simulator's obstacle generators restated in csrc/mapgen.cpp.
+"""Synthetic worlds (host utility, libuavmp_worldgen.so): the reference simulator's obstacle generators restated in
+csrc/worldgen.cpp.  Nothing here touches the CUDA library.
 
 random_forest.cpp:55-155 / :286-306 -> cloud; pointcloud_render_node.cpp:84-86 -> 0.1 m voxel centroids;
 grid_map.cpp:733-785 -> inflated int8 grid (x-major, z-fastest, grid_map.h:257-260).
@@ -27,7 +28,7 @@ class World:
 
 def make_world(x_size, y_size, z_size, seed=1, map_type=0, resolution=0.1, ground_height=0.0,
                obstacles_inflation=0.099, **overrides):
-    lib = _lib.load()
+    lib = _lib.load_worldgen()
     mp = _lib.MapgenParams()
     lib.uavmp_mapgen_params_default(C.byref(mp), float(x_size), float(y_size), int(seed))
     mp.map_type = map_type

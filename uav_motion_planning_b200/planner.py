@@ -27,6 +27,69 @@ def plan_batch(ctx, start_pt, start_vel, end_pt, end_vel, order=7, S=8, seg_time
     return dict(search_status=status, qp_solved=solved, coef=coef)
 
 
+PLAN_DEVICE_IO = 1
+
+
+def _info_dict(info):
+    return dict(error_flags=info.error_flags,
+                counters={k: getattr(info.counters, k) for k, _ in _lib.KinoCounters._fields_},
+                timings={k: getattr(info.timings, k) for k, _ in _lib.Timings._fields_})
+
+
+def plan_submit(ctx, B, sp, sv, ep, ev, status, solved, coef, order=7, S=8, seg_time=1.0, settings=None, device_io=False):
+    """uavmp_plan_submit: asynchronous, returns a ticket.  Every argument is a raw pointer (int): page-locked host memory, or
+    device memory with device_io=True.  The buffers must stay alive until plan_wait(ticket) has returned."""
+    vp = C.c_void_p
+    t = C.c_longlong(-1)
+    ctx.check(ctx.lib.uavmp_plan_submit(ctx.h, B, vp(sp), vp(sv), vp(ep), vp(ev), order, S, float(seg_time),
+                                        C.byref(settings) if settings is not None else None,
+                                        PLAN_DEVICE_IO if device_io else 0, vp(status), vp(solved), vp(coef), C.byref(t)))
+    return t.value
+
+
+def plan_wait(ctx, ticket):
+    """uavmp_plan_wait: blocks until the batch is complete; returns its error flags / counters / timings."""
+    info = _lib.PlanInfo()
+    ctx.check(ctx.lib.uavmp_plan_wait(ctx.h, ticket, C.byref(info)))
+    return _info_dict(info)
+
+
+def plan_stream_wait(ctx, ticket, cuda_stream):
+    """Make a CUDA stream of the caller (raw handle) wait for the batch; the host does not block."""
+    ctx.check(ctx.lib.uavmp_plan_stream_wait(ctx.h, ticket, C.c_void_p(cuda_stream)))
+
+
+def max_in_flight(ctx):
+    return ctx.lib.uavmp_plan_max_in_flight()
+
+
+def plan_batches_pipelined(ctx, batches, order=7, S=8, seg_time=1.0, settings=None):
+    """Host arrays in, host arrays out, every batch through uavmp_plan_submit / uavmp_plan_wait with as many batches in flight
+    as the library allows (cross-batch pipelining).  `batches`: iterable of (start_pt, start_vel, end_pt, end_vel)."""
+    n = (order + 1) * S
+    depth = max_in_flight(ctx)
+    live, out = [], []
+
+    def collect():
+        t, bufs, res = live.pop(0)
+        res["info"] = plan_wait(ctx, t)
+        out.append(res)
+
+    for bt in batches:
+        sp, sv, ep, ev = (_lib.as_f64(a).reshape(-1, 3) for a in bt)
+        B = sp.shape[0]
+        res = dict(search_status=np.zeros(B, np.int32), qp_solved=np.zeros(B, np.int32), coef=np.zeros((B, 3, n)))
+        if len(live) == depth:
+            collect()
+        t = plan_submit(ctx, B, sp.ctypes.data, sv.ctypes.data, ep.ctypes.data, ev.ctypes.data,
+                        res["search_status"].ctypes.data, res["qp_solved"].ctypes.data, res["coef"].ctypes.data,
+                        order=order, S=S, seg_time=seg_time, settings=settings)
+        live.append((t, (sp, sv, ep, ev), res))
+    while live:
+        collect()
+    return out
+
+
 def plan_batch_dev(ctx, B, d_sp, d_sv, d_ep, d_ev, d_status, d_solved, d_coef, order=7, S=8, seg_time=1.0,
                    settings=None):
     """Every argument is a raw device pointer (int); asynchronous on the context's stream."""
