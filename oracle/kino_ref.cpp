@@ -13,9 +13,11 @@
 //     accept/reject result of isCollisionFree does not depend on which superset is returned;
 //   * cbrt/acos/cos/pow come from csrc/fpmath.h (shared with the device) unless libm_mode == 1, in which case
 //     glibc is called like the reference does; tests compare both modes.
-// PARITY STATUS: unpinned by the reference's own tests (it has none for this path); pinned
-// only by the golden vectors this oracle generated itself (tests/golden) and, when oracle/_ref/libkino_ref.so
-// was built, by the reference's unmodified kino_astar.cpp compiled against header shims (oracle/shim).
+// PARITY STATUS: the reference has no expected outputs for this path.  This restatement is pinned to the
+// reference ITSELF: /root/reference's kino_astar.cpp compiles unmodified against the header shims in oracle/shim into
+// oracle/_ref/libkino_ref.so (oracle/Makefile), and tests/test_kino_reference_build.py requires bit-identical return
+// codes, use_node_num_, path points and map-lookup sequences from the two on the golden queries and on > 150 random ones.
+// What remains "believed" is Eigen's floating-point association (restated in oracle/shim/Eigen/Eigen, same contract).
 #include <algorithm>
 #include <cmath>
 #include <cstdint>

@@ -63,6 +63,9 @@ void refkino_destroy(refkino* k) { delete k; }
 
 int refkino_search(refkino* k, const double sp[3], const double sv[3], const double ep[3], const double ev[3], refkino_result* res,
                    double* path_xyz, int path_cap) {
+  // This library carries its own (statically linked) libstdc++ when built by the image's g++ wrapper; loaded with RTLD_LOCAL
+  // from Python nobody has constructed that copy's std::cout yet, and the reference prints to it.
+  static std::ios_base::Init iostreams_ready;
   std::ostringstream sink;                       // the reference prints to std::cout; keep the test output clean
   std::streambuf* old = std::cout.rdbuf(sink.rdbuf());
   std::streambuf* olde = std::cerr.rdbuf(sink.rdbuf());

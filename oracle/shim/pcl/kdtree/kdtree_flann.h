@@ -7,7 +7,7 @@
 #include <boost/make_shared.hpp>
 #include <cmath>
 #include <cstdint>
-#include <unordered_map>
+#include <algorithm>
 #include <vector>
 
 namespace pcl {
@@ -22,29 +22,48 @@ struct PointCloud {
 template <typename P>
 class KdTreeFLANN {
   typename PointCloud<P>::ConstPtr cloud_;
-  std::unordered_map<long long, std::vector<int>> cells_;
-  float cell_ = 0.5f;
-  static long long key(int x, int y, int z) { return ((long long)(x + (1 << 20)) << 42) | ((long long)(y + (1 << 20)) << 21) | (long long)(z + (1 << 20)); }
+  std::vector<int> start_, idx_;     // dense cell grid (CSR): points of cell c are idx_[start_[c] .. start_[c + 1])
+  float cell_ = 0.5f, lo_[3] = {0, 0, 0};
+  int n_[3] = {0, 0, 0};
+  int cell_of(float v, int a) const { return (int)std::floor((v - lo_[a]) / cell_); }
  public:
   void setInputCloud(const typename PointCloud<P>::ConstPtr& c) {
     cloud_ = c;
-    cells_.clear();
-    for (size_t i = 0; i < c->points.size(); i++) {
-      const P& p = c->points[i];
-      cells_[key((int)std::floor(p.x / cell_), (int)std::floor(p.y / cell_), (int)std::floor(p.z / cell_))].push_back((int)i);
+    start_.clear(); idx_.clear();
+    n_[0] = n_[1] = n_[2] = 0;
+    const size_t np = c->points.size();
+    if (!np) return;
+    float hi[3] = {c->points[0].x, c->points[0].y, c->points[0].z};
+    lo_[0] = hi[0]; lo_[1] = hi[1]; lo_[2] = hi[2];
+    for (const P& p : c->points) {
+      const float v[3] = {p.x, p.y, p.z};
+      for (int a = 0; a < 3; a++) { if (v[a] < lo_[a]) lo_[a] = v[a]; if (v[a] > hi[a]) hi[a] = v[a]; }
     }
+    for (int a = 0; a < 3; a++) n_[a] = cell_of(hi[a], a) + 1;
+    const size_t nc = (size_t)n_[0] * n_[1] * n_[2];
+    start_.assign(nc + 1, 0);
+    auto id = [&](const P& p) { return ((size_t)cell_of(p.x, 0) * n_[1] + cell_of(p.y, 1)) * n_[2] + cell_of(p.z, 2); };
+    for (const P& p : c->points) start_[id(p) + 1]++;
+    for (size_t i = 0; i < nc; i++) start_[i + 1] += start_[i];
+    idx_.resize(np);
+    std::vector<int> at(start_.begin(), start_.end() - 1);
+    for (size_t i = 0; i < np; i++) idx_[at[id(c->points[i])]++] = (int)i;
   }
   int radiusSearch(const P& q, double radius, std::vector<int>& idx, std::vector<float>& d2, unsigned = 0) const {
     idx.clear(); d2.clear();
-    if (!cloud_) return 0;
+    if (!cloud_ || !n_[0]) return 0;
     const float r = (float)radius, r2 = r * r;
-    const int x0 = (int)std::floor((q.x - r) / cell_), x1 = (int)std::floor((q.x + r) / cell_);
-    const int y0 = (int)std::floor((q.y - r) / cell_), y1 = (int)std::floor((q.y + r) / cell_);
-    const int z0 = (int)std::floor((q.z - r) / cell_), z1 = (int)std::floor((q.z + r) / cell_);
-    for (int x = x0; x <= x1; x++) for (int y = y0; y <= y1; y++) for (int z = z0; z <= z1; z++) {
-      auto it = cells_.find(key(x, y, z));
-      if (it == cells_.end()) continue;
-      for (int i : it->second) {
+    const float qv[3] = {q.x, q.y, q.z};
+    int c0[3], c1[3];
+    for (int a = 0; a < 3; a++) {
+      c0[a] = std::max(cell_of(qv[a] - r, a), 0);
+      c1[a] = std::min(cell_of(qv[a] + r, a), n_[a] - 1);
+      if (c0[a] > c1[a]) return 0;
+    }
+    for (int x = c0[0]; x <= c1[0]; x++) for (int y = c0[1]; y <= c1[1]; y++) {
+      const size_t row = ((size_t)x * n_[1] + y) * n_[2];
+      for (int k = start_[row + c0[2]]; k < start_[row + c1[2] + 1]; k++) {
+        const int i = idx_[k];
         const P& p = cloud_->points[i];
         const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
         const float d = dx * dx + dy * dy + dz * dz;

@@ -1,6 +1,7 @@
 """CPU tests of the search oracle (oracle/kino_ref.cpp) and of the input generators, against the committed golden vectors
 (tests/golden/kino_golden.json, produced by tests/golden/make_golden.py).  The reference has no expected outputs for this
-path: these goldens freeze the oracle itself, they do not pin it to the reference ("parity unpinned")."""
+path: these goldens freeze the oracle; tests/test_kino_reference_build.py pins it to the reference's own
+kino_astar.cpp compiled unmodified (oracle/_ref/libkino_ref.so)."""
 import ctypes as C
 import hashlib
 import json
