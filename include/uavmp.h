@@ -147,6 +147,17 @@ int uavmp_minctrl_solve_batch(uavmp_ctx* ctx, int order, int S, int B, const dou
                               const double* time_vec, const uavmp_osqp_settings* settings, double* coef,
                               int* solved, int* osqp_status, int* iters);
 
+/* The same with corridor (inequality) rows — an EXTENSION (the reference's rows are all equalities,
+ * minimum_control.cpp:98-125): for every segment s and every j < n_corridor, the position at the interior time
+ * (j + 1) / (n_corridor + 1) * T_s must lie in [corridor_lo[b][s], corridor_hi[b][s]] (B x S each).  These are true
+ * inequality rows of the OSQP problem: rho = settings->rho on them (1e3 rho on the equality rows, auxil.c:75-104) and the
+ * z-projection clip(., l, u) of update_z (auxil.c:188-203) is active.  n_corridor = 0 is uavmp_minctrl_solve_batch. */
+int uavmp_minctrl_solve_corridor_batch(uavmp_ctx* ctx, int order, int S, int n_corridor, int B, const double* pos_1d,
+                                       const double* bound_vel, const double* bound_acc, const double* bound_jerk,
+                                       const double* time_vec, const double* corridor_lo, const double* corridor_hi,
+                                       const uavmp_osqp_settings* settings, double* coef, int* solved, int* osqp_status,
+                                       int* iters);
+
 /* ---- pipeline: search -> waypoints -> QP (extension) ------------------------------------------------ */
 /* For every query whose search reaches the goal, S+1 waypoints are taken from the sampled path at indices
  * floor(k*(n-1)/S), T_i = seg_time (the reference's convention is 1.0, test_minimum_jerk.cpp:66-71), boundary
@@ -161,6 +172,23 @@ int uavmp_plan_batch_dev(uavmp_ctx* ctx, int B, const double* d_start_pt, const 
                          const double* d_end_pt, const double* d_end_vel, int order, int S, double seg_time,
                          const uavmp_osqp_settings* settings, int* d_search_status, int* d_qp_solved, double* d_coef);
 
+/* What the pipeline builds between the search and the QP (all of it an extension: the reference never chains the two).
+ * With n sampled path points (one every time_step_size along the searched trajectory) and idx_k = floor(k (n - 1) / S):
+ *   waypoint k = path[idx_k];
+ *   time_alloc 0: T_s = seg_time (the reference's convention, test_minimum_jerk.cpp:66-71);
+ *   time_alloc 1: T_s = max(idx_{s+1} - idx_s, 1) * time_step_size — the searched trajectory's own timing;
+ *   corridor_samples > 0: per segment and axis the box [min - margin, max + margin] over path[idx_s .. idx_{s+1}], imposed
+ *   at corridor_samples interior times (uavmp_minctrl_solve_corridor_batch). */
+typedef struct {
+  int order; /* 5 or 7 */
+  int S;
+  double seg_time;
+  int time_alloc;
+  int corridor_samples;
+  double corridor_margin;
+} uavmp_plan_options;
+void uavmp_plan_options_default(uavmp_plan_options* o); /* order 7, S 8, seg_time 1.0, no time allocation, no corridor */
+
 /* Asynchronous form with several batches in flight.  A batch is ONE kernel (the CTA that finishes a query also solves its three
  * QPs), each batch runs on its own stream and its CTAs take search arenas from a shared pool, so the CTAs of batch k + 1 fill the
  * SMs the long tail of batch k leaves idle.  uavmp_plan_submit returns at once with a ticket; the outputs (and, for host
@@ -172,6 +200,10 @@ int uavmp_plan_batch_dev(uavmp_ctx* ctx, int B, const double* d_start_pt, const 
 int uavmp_plan_submit(uavmp_ctx* ctx, int B, const double* start_pt, const double* start_vel, const double* end_pt,
                       const double* end_vel, int order, int S, double seg_time, const uavmp_osqp_settings* settings,
                       unsigned flags, int* search_status, int* qp_solved, double* coef, long long* ticket);
+/* uavmp_plan_submit with the full option block (time allocation, corridor rows) */
+int uavmp_plan_submit_opt(uavmp_ctx* ctx, int B, const double* start_pt, const double* start_vel, const double* end_pt,
+                          const double* end_vel, const uavmp_plan_options* opt, const uavmp_osqp_settings* settings,
+                          unsigned flags, int* search_status, int* qp_solved, double* coef, long long* ticket);
 int uavmp_plan_wait(uavmp_ctx* ctx, long long ticket, uavmp_plan_info* info /* nullable */);
 int uavmp_plan_stream_wait(uavmp_ctx* ctx, long long ticket, void* cuda_stream);
 int uavmp_plan_max_in_flight(void);

@@ -79,22 +79,26 @@ extern "C" {
 
 // Assemble P (upper CSC), q, A (CSC with the reference's explicit zeros), l, u.  d = order, k = (d+1)/2.
 // Returns n (variables); *m_out constraints.  Buffers sized by the caller (see oracle_minctrl_dims).
-void oracle_minctrl_dims(int order, int S, int* n, int* m, int* nnzP, int* nnzA) {
+// Kc > 0 (extension, SURVEY.md §9.3 "Corridor"): Kc inequality rows per segment, lo <= p_s(phi_j T_s) <= hi at
+// phi_j = (j + 1) / (Kc + 1); row index m_eq + s Kc + j; the entry for coefficient i is phi_j^i * T_s^i.
+void oracle_minctrl_dims_c(int order, int S, int Kc, int* n, int* m, int* nnzP, int* nnzA) {
   int k = (order + 1) / 2, nc = order + 1;
   *n = nc * S;
-  *m = 2 * k + (k + 1) * (S - 1);
+  *m = 2 * k + (k + 1) * (S - 1) + Kc * S;
   *nnzP = S * (k * (k + 1)) / 2;
   // start k ; interior: waypoint nc + sum_r (nc + r + 1) ; end k*nc
   int per = nc;
   for (int r = 0; r < k; r++) per += nc + r + 1;
-  *nnzA = k + (S - 1) * per + k * nc;
+  *nnzA = k + (S - 1) * per + k * nc + Kc * S * nc;
 }
+void oracle_minctrl_dims(int order, int S, int* n, int* m, int* nnzP, int* nnzA) { oracle_minctrl_dims_c(order, S, 0, n, m, nnzP, nnzA); }
 
-int oracle_minctrl_assemble(int order, int S, const double* pos_1d, const double* bound_vel, const double* bound_acc,
-                            const double* bound_jerk, const double* T, int libm_mode, long long* Pp, long long* Pi,
-                            double* Px, double* q, long long* Ap, long long* Ai, double* Ax, double* l, double* u) {
+int oracle_minctrl_assemble_c(int order, int S, int Kc, const double* pos_1d, const double* bound_vel, const double* bound_acc,
+                              const double* bound_jerk, const double* T, const double* corridor_lo, const double* corridor_hi,
+                              int libm_mode, long long* Pp, long long* Pi, double* Px, double* q, long long* Ap, long long* Ai,
+                              double* Ax, double* l, double* u) {
   const int k = (order + 1) / 2, nc = order + 1;
-  const int n = nc * S, m = 2 * k + (k + 1) * (S - 1);
+  const int n = nc * S, m_eq = 2 * k + (k + 1) * (S - 1), m = m_eq + Kc * S;
   Triplets P, A;
   // getHessian (minimum_control.cpp:5-19): full symmetric block inserted; OsqpEigen keeps the upper triangle
   for (int s = 0; s < S; s++)
@@ -140,6 +144,15 @@ int oracle_minctrl_assemble(int order, int S, const double* pos_1d, const double
     long long row = k + (long long)(k + 1) * s;
     l[row] = u[row] = pos_1d[s + 1];
   }
+  // corridor rows (extension): lo <= sum_i c_i (phi_j^i) (T_s^i) <= hi
+  for (int s = 0; s < S; s++)
+    for (int j = 0; j < Kc; j++) {
+      const double phi = (double)(j + 1) / (double)(Kc + 1);
+      const long long row = m_eq + (long long)s * Kc + j;
+      for (int i = 0; i < nc; i++) A.insert(row, nc * s + i, fpm::powi(phi, i) * mpow(libm_mode, T[s], i));
+      l[row] = corridor_lo[s];
+      u[row] = corridor_hi[s];
+    }
   std::vector<long long> p, i;
   std::vector<double> x;
   P.toCSC(n, p, i, x, true);
@@ -149,22 +162,35 @@ int oracle_minctrl_assemble(int order, int S, const double* pos_1d, const double
   return 0;
 }
 
+int oracle_minctrl_assemble(int order, int S, const double* pos_1d, const double* bound_vel, const double* bound_acc,
+                            const double* bound_jerk, const double* T, int libm_mode, long long* Pp, long long* Pi,
+                            double* Px, double* q, long long* Ap, long long* Ai, double* Ax, double* l, double* u) {
+  return oracle_minctrl_assemble_c(order, S, 0, pos_1d, bound_vel, bound_acc, bound_jerk, T, nullptr, nullptr, libm_mode, Pp, Pi, Px, q,
+                                   Ap, Ai, Ax, l, u);
+}
+
 // MinimumControl::solve (+ getCoef1d): returns 1 iff OSQP status == SOLVED (Solver.cpp:181-187), else 0; -1 if the
 // reference library is unavailable.
-int oracle_minctrl_solve(int order, int S, const double* pos_1d, const double* bound_vel, const double* bound_acc,
-                         const double* bound_jerk, const double* T, const oracle_osqp_settings* st, int libm_mode,
-                         double* coef, oracle_osqp_info* info) {
+int oracle_minctrl_solve_c(int order, int S, int Kc, const double* pos_1d, const double* bound_vel, const double* bound_acc,
+                           const double* bound_jerk, const double* T, const double* corridor_lo, const double* corridor_hi,
+                           const oracle_osqp_settings* st, int libm_mode, double* coef, oracle_osqp_info* info) {
   if (!load_ref()) return -1;
   int n, m, nnzP, nnzA;
-  oracle_minctrl_dims(order, S, &n, &m, &nnzP, &nnzA);
+  oracle_minctrl_dims_c(order, S, Kc, &n, &m, &nnzP, &nnzA);
   std::vector<long long> Pp(n + 1), Pi(nnzP), Ap(n + 1), Ai(nnzA);
   std::vector<double> Px(nnzP), q(n), Ax(nnzA), l(m), u(m), y(m);
-  oracle_minctrl_assemble(order, S, pos_1d, bound_vel, bound_acc, bound_jerk, T, libm_mode, Pp.data(), Pi.data(),
-                          Px.data(), q.data(), Ap.data(), Ai.data(), Ax.data(), l.data(), u.data());
+  oracle_minctrl_assemble_c(order, S, Kc, pos_1d, bound_vel, bound_acc, bound_jerk, T, corridor_lo, corridor_hi, libm_mode, Pp.data(),
+                            Pi.data(), Px.data(), q.data(), Ap.data(), Ai.data(), Ax.data(), l.data(), u.data());
   int rc = g_solve(n, m, Pp.data(), Pi.data(), Px.data(), q.data(), Ap.data(), Ai.data(), Ax.data(), l.data(),
                    u.data(), st, coef, y.data(), info);
   if (rc) return 0;  // "solver init failed!" (:173-177)
   return info->status_val == 1 ? 1 : 0;
+}
+
+int oracle_minctrl_solve(int order, int S, const double* pos_1d, const double* bound_vel, const double* bound_acc,
+                         const double* bound_jerk, const double* T, const oracle_osqp_settings* st, int libm_mode,
+                         double* coef, oracle_osqp_info* info) {
+  return oracle_minctrl_solve_c(order, S, 0, pos_1d, bound_vel, bound_acc, bound_jerk, T, nullptr, nullptr, st, libm_mode, coef, info);
 }
 
 // generic QP through the reference OSQP (known-answer tests)

@@ -24,37 +24,39 @@ def load():
     return _lib
 
 
-def solve_batch(order, pos, bv, ba, T, bj=None, settings=None):
+def solve_batch(order, pos, bv, ba, T, bj=None, settings=None, lo=None, hi=None, n_corridor=0):
     from uav_motion_planning_b200.minimum_control import default_settings
     lib = load()
     f = lambda a: np.ascontiguousarray(a, np.float64)
     pos, bv, ba, T = f(pos), f(bv), f(ba), f(T)
     B, S = pos.shape[0], pos.shape[1] - 1
+    lo, hi = (f(lo), f(hi)) if n_corridor else (None, None)
     bj = f(np.zeros((B, 2)) if bj is None else bj)
     n = (order + 1) * S
     coef = np.zeros((B, n))
     solved, status, iters = (np.zeros(B, np.int32) for _ in range(3))
     stats = np.zeros(6, np.int32)
     st = settings or default_settings()
-    p = lambda a: a.ctypes.data_as(C.c_void_p)
-    lib.host_qp_solve(order, S, B, p(pos), p(bv), p(ba), p(bj), p(T), C.byref(st), p(coef), p(solved), p(status),
-                      p(iters), p(stats))
+    p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    lib.host_qp_solve_c(order, S, n_corridor, B, p(pos), p(bv), p(ba), p(bj), p(T), p(lo), p(hi), C.byref(st), p(coef), p(solved),
+                        p(status), p(iters), p(stats))
     return dict(coef=coef, solved=solved, status=status, iters=iters, stats=stats)
 
 
-def solve_batch_warp(order, pos, bv, ba, T, bj=None, settings=None, reversed_loops=False):
+def solve_batch_warp(order, pos, bv, ba, T, bj=None, settings=None, reversed_loops=False, lo=None, hi=None, n_corridor=0):
     """The warp-per-problem body (qp_body_warp.h) run as one lane on the host; reversed_loops flips every parallel loop."""
     from uav_motion_planning_b200.minimum_control import default_settings
     lib = load()
     f = lambda a: np.ascontiguousarray(a, np.float64)
     pos, bv, ba, T = f(pos), f(bv), f(ba), f(T)
     B, S = pos.shape[0], pos.shape[1] - 1
+    lo, hi = (f(lo), f(hi)) if n_corridor else (None, None)
     bj = f(np.zeros((B, 2)) if bj is None else bj)
     n = (order + 1) * S
     coef = np.zeros((B, n))
     solved, status, iters = (np.zeros(B, np.int32) for _ in range(3))
     st = settings or default_settings()
-    p = lambda a: a.ctypes.data_as(C.c_void_p)
-    lib.host_qp_solve_warp(int(reversed_loops), order, S, B, p(pos), p(bv), p(ba), p(bj), p(T), C.byref(st), p(coef), p(solved),
-                           p(status), p(iters))
+    p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    lib.host_qp_solve_warp_c(int(reversed_loops), order, S, n_corridor, B, p(pos), p(bv), p(ba), p(bj), p(T), p(lo), p(hi),
+                             C.byref(st), p(coef), p(solved), p(status), p(iters))
     return dict(coef=coef, solved=solved, status=status, iters=iters)

@@ -145,16 +145,19 @@ def _p(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
 
 
-def minctrl_solve(order, S, pos_1d, bound_vel, bound_acc, T, bound_jerk=None, settings=None, libm_mode=0):
+def minctrl_solve(order, S, pos_1d, bound_vel, bound_acc, T, bound_jerk=None, settings=None, libm_mode=0,
+                  corridor_lo=None, corridor_hi=None, n_corridor=0):
+    """n_corridor > 0: the corridor extension — corridor_lo / corridor_hi hold one box per segment."""
     lib = load()
     st = settings or osqp_settings()
     pos_1d, bound_vel, bound_acc, bound_jerk, T = _f(pos_1d), _f(bound_vel), _f(bound_acc), _f(bound_jerk), _f(T)
+    lo, hi = _f(corridor_lo), _f(corridor_hi)
     coef = np.zeros((order + 1) * S)
     info = OsqpInfo()
-    lib.oracle_minctrl_solve.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.POINTER(OsqpSettings), C.c_int,
-                                                                               C.c_void_p, C.POINTER(OsqpInfo)]
-    ok = lib.oracle_minctrl_solve(order, S, _p(pos_1d), _p(bound_vel), _p(bound_acc), _p(bound_jerk), _p(T),
-                                  C.byref(st), libm_mode, _p(coef), C.byref(info))
+    lib.oracle_minctrl_solve_c.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7 + [C.POINTER(OsqpSettings), C.c_int,
+                                                                                          C.c_void_p, C.POINTER(OsqpInfo)]
+    ok = lib.oracle_minctrl_solve_c(order, S, n_corridor, _p(pos_1d), _p(bound_vel), _p(bound_acc), _p(bound_jerk), _p(T),
+                                    _p(lo), _p(hi), C.byref(st), libm_mode, _p(coef), C.byref(info))
     if ok < 0:
         raise RuntimeError("oracle/_ref/libosqp_ref.so is not available")
     return ok, coef, info_dict(info)

@@ -46,8 +46,10 @@ def test_config2_ellipsoid_only_32768(gpu_ctx):
     check_subset(ka, world, qs, a, list(range(0, B, B // 24)))
 
 
-def test_config3_wall_map_12_segments(gpu_ctx):
-    """configs[3] without its corridor rows (not built): two-slab wall map, search + 12-segment minimum snap."""
+def test_config3_wall_map_12_segments_with_corridor(gpu_ctx):
+    """configs[3]: two-slab wall map, search + 12-segment minimum snap WITH corridor box constraints (2 samples per segment, boxes
+    = the segment's path extent +- 0.2 m; uavmp_plan_options), through uavmp_plan_submit_opt; oracle chain on a subset."""
+    from uav_motion_planning_b200.planner import plan_batches_pipelined, plan_options
     world = u.make_world(50, 50, 10, seed=1, map_type=2)
     ka = u.KinoAstar(gpu_ctx)
     ka.setLaunchParams()
@@ -57,14 +59,19 @@ def test_config3_wall_map_12_segments(gpu_ctx):
     # half of the queries must cross the wall plane x = 0 (through the 0.5 m gap or around)
     sp[: B // 2, 0] = -np.abs(sp[: B // 2, 0]) - 1.0
     ep[: B // 2, 0] = np.abs(ep[: B // 2, 0]) + 1.0
-    got = plan_batch(gpu_ctx, sp, sv, ep, ev, order=7, S=12)
+    opt = plan_options(order=7, S=12, seg_time=1.0, corridor_samples=2, corridor_margin=0.2)
+    got = plan_batches_pipelined(gpu_ctx, [(sp, sv, ep, ev)], options=opt)[0]
+    assert got["info"]["error_flags"] == 0
     assert set(np.unique(got["search_status"])) <= {1, 2}
+    plain = plan_batch(gpu_ctx, sp, sv, ep, ev, order=7, S=12)
+    assert np.array_equal(plain["search_status"], got["search_status"])
     orc = oracle_lib.KinoOracle(world, ka.params)
-    n_ok = 0
+    n_ok = n_active = 0
     for q in list(range(0, 8)) + list(range(B // 2, B // 2 + 8)):
-        st, solved, coef, _ = plan_one(orc, sp[q], sv[q], ep[q], ev[q], 7, 12, 1.0)
+        st, solved, coef, _ = plan_one(orc, sp[q], sv[q], ep[q], ev[q], 7, 12, 1.0, n_corridor=2, margin=0.2)
         assert (st, solved) == (got["search_status"][q], got["qp_solved"][q])
         if solved:
             assert np.array_equal(coef, got["coef"][q])   # tabulated AMD order: bit-identical to the reference's OSQP
             n_ok += 1
-    assert n_ok >= 4
+            n_active += np.abs(coef - plain["coef"][q]).max() > 1e-6
+    assert n_ok >= 4 and n_active >= 2

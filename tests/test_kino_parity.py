@@ -110,3 +110,48 @@ def test_map_far_from_the_origin(gpu_ctx, world_small):
     bad, got, *_ = run_case(gpu_ctx, far, 24, seed=5, ctype=1, min_dist=8.0)
     assert not bad, bad
     assert (got["status"] == 1).mean() > 0.3
+
+
+def test_bench_batch_tail_and_counters(gpu_ctx, world_big):
+    """The queries that set the benchmark step: bench.py's first timed batch (seed 11 + warm-up 3, 4 096 queries, 50 x 50 x 10 m).
+    The 8 queries with the most expansions (pool-exhausting: 100 000 nodes, >= 10 k expansions, kino_astar.cpp:243-247) plus 8
+    random ones are compared with the oracle bit for bit, and the counters that feed bench.py's roofline (uavmp_kino_get_counters,
+    SURVEY.md §8(d)) with the oracle's: n_pop / n_insert / n_update / n_hash_probe / n_heuristic / n_shot identical;
+    n_occ_lookup and n_cloud_pts_tested are defined on a subset of what the reference touches, so they
+    must not exceed the oracle's (the reported GB/s is never inflated)."""
+    from concurrent.futures import ThreadPoolExecutor
+    import os
+    B = 4096
+    ka = u.KinoAstar(gpu_ctx)
+    ka.setLaunchParams()
+    ka.setParam(collision_check_type=1)
+    ka.setGridMap(world_big)
+    sp, sv, ep, ev = u.sample_queries(world_big, B, seed=14)
+    full = ka.search_batch(sp, sv, ep, ev, want_paths=False)
+    top = np.argsort(-full["n_pop"], kind="stable")[:8]
+    rnd = np.random.default_rng(0).choice(np.setdiff1d(np.arange(B), top), 8, replace=False)
+    sel = np.concatenate([top, rnd])
+    assert (full["status"][top] == 2).all() and (full["use_node_num"][top] == ka.params.allocated_node_num).all()
+    assert full["n_pop"][top].min() >= 3000
+    got = ka.search_batch(sp[sel], sv[sel], ep[sel], ev[sel])
+    cg = ka.counters()
+    for k in ("status", "use_node_num", "n_pop", "pop_hash"):  # a query's result does not depend on its batch
+        assert np.array_equal(got[k], full[k][sel]), k
+
+    def one(j):
+        orc = oracle_lib.KinoOracle(world_big, ka.params)
+        r = orc.search(sp[sel[j]], sv[sel[j]], ep[sel[j]], ev[sel[j]])
+        orc.close()
+        return r
+    with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
+        refs = list(ex.map(one, range(len(sel))))
+    for j, ref in enumerate(refs):
+        o0, o1 = got["path_offsets"][j], got["path_offsets"][j + 1]
+        assert ref["status"] == got["status"][j] and ref["use_node_num"] == got["use_node_num"][j], (j, sel[j])
+        assert ref["n_pop"] == got["n_pop"][j] and ref["pop_hash"] == int(got["pop_hash"][j]), (j, sel[j])
+        assert np.array_equal(ref["path"].view(np.uint64), got["paths"][o0:o1].view(np.uint64)), (j, sel[j])
+    tot = {k: sum(r["counters"][k] for r in refs) for k in refs[0]["counters"]}
+    for k in ("n_pop", "n_insert", "n_update", "n_hash_probe", "n_heuristic", "n_shot"):
+        assert cg[k] == tot[k], (k, cg[k], tot[k])
+    for k in ("n_occ_lookup", "n_cloud_pts_tested"):
+        assert 0 < cg[k] <= tot[k], (k, cg[k], tot[k])

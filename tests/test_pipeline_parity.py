@@ -149,3 +149,38 @@ def test_device_io_tickets_and_stream_wait(gpu_ctx):
         assert np.array_equal(r["coef"].reshape(B, -1).view(np.uint64), cp.cpu().numpy().view(np.uint64))
     with pytest.raises(u.UavmpError, match="ticket"):
         plan_wait(gpu_ctx, tickets[0])
+
+
+@pytest.mark.parametrize("order,S,Kc,time_alloc", [(7, 12, 2, 0), (7, 8, 2, 1), (5, 4, 0, 1)])
+def test_plan_options_time_allocation_and_corridor(gpu_ctx, monkeypatch, order, S, Kc, time_alloc):
+    """uavmp_plan_submit_opt: segment times from the searched trajectory's own timing (time_alloc 1) and corridor boxes around
+    each segment's path points (corridor rows active in the QP), against the same chain on the oracle (tests/pipeline_ref.py):
+    identical search status / qp_solved, coefficients bit-identical; the in-kernel QP (default) and the sequential pipeline
+    (UAVMP_NO_FUSE) give the same bits."""
+    from uav_motion_planning_b200.planner import plan_batches_pipelined, plan_options
+    world = u.make_world(20, 20, 5, seed=1)
+    ka = u.KinoAstar(gpu_ctx)
+    ka.setLaunchParams()
+    ka.setGridMap(world)
+    margin = 0.15
+    sp, sv, ep, ev = u.sample_queries(world, 40, seed=61, min_dist=8.0)
+    opt = plan_options(order=order, S=S, seg_time=1.0, time_alloc=time_alloc, corridor_samples=Kc, corridor_margin=margin)
+    a = plan_batches_pipelined(gpu_ctx, [(sp, sv, ep, ev)], options=opt)[0]
+    monkeypatch.setenv("UAVMP_NO_FUSE", "1")
+    b = plan_batches_pipelined(gpu_ctx, [(sp, sv, ep, ev)], options=opt)[0]
+    monkeypatch.delenv("UAVMP_NO_FUSE")
+    assert a["info"]["error_flags"] == 0
+    assert np.array_equal(a["search_status"], b["search_status"]) and np.array_equal(a["qp_solved"], b["qp_solved"])
+    assert np.array_equal(a["coef"].view(np.uint64), b["coef"].view(np.uint64))
+    plain = plan_batch(gpu_ctx, sp, sv, ep, ev, order=order, S=S)
+    orc = oracle_lib.KinoOracle(world, ka.params)
+    n_ok = n_diff = 0
+    for q in range(40):
+        st, solved, coef, _ = plan_one(orc, sp[q], sv[q], ep[q], ev[q], order, S, 1.0, time_alloc=time_alloc,
+                                       step=ka.params.time_step_size, n_corridor=Kc, margin=margin)
+        assert (st, solved) == (a["search_status"][q], a["qp_solved"][q]), q
+        if solved:
+            assert np.array_equal(coef, a["coef"][q]), q
+            n_ok += 1
+            n_diff += np.abs(coef - plain["coef"][q]).max() > 1e-6
+    assert n_ok >= 10 and n_diff >= 5   # the options change the trajectories (they are not silently ignored)

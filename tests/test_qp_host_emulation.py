@@ -107,3 +107,62 @@ def test_warp_body_equals_thread_body_on_random_problems():
     a = host_qp.solve_batch(5, pos, z, z, np.ones((2, 41)), settings=default_settings(max_iter=10))
     w = host_qp.solve_batch_warp(5, pos, z, z, np.ones((2, 41)), settings=default_settings(max_iter=10), reversed_loops=True)
     assert np.array_equal(a["coef"], w["coef"]) and np.array_equal(a["status"], w["status"])
+
+
+def corridor_problems(order, S, B, seed, margin=0.05):
+    rng = np.random.default_rng(seed)
+    pos = np.cumsum(rng.normal(size=(B, S + 1)), axis=1)
+    bv, ba, bj = rng.normal(size=(B, 2)) * 0.2, np.zeros((B, 2)), np.zeros((B, 2))
+    T = rng.uniform(0.5, 2.0, size=(B, S))
+    lo = np.minimum(pos[:, :-1], pos[:, 1:]) - margin
+    hi = np.maximum(pos[:, :-1], pos[:, 1:]) + margin
+    return pos, bv, ba, bj, T, lo, hi
+
+
+@pytest.mark.skipif(not oracle_lib.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("order,S,Kc,eps", [(7, 12, 2, 1e-3), (7, 8, 3, 1e-5), (5, 4, 1, 1e-3), (5, 6, 2, 1e-4), (7, 16, 4, 1e-3)])
+def test_corridor_rows_against_reference_osqp(order, S, Kc, eps):
+    """Corridor (inequality) rows — the SURVEY.md §9.3 extension — through the reference's own OSQP: rho = 0.1 on those rows
+    (1e3 x on the equality rows, auxil.c:75-104), the z-projection of update_z (auxil.c:188-203) clips, adaptive rho refactors.
+    Same status, same iteration count, coefficients bit-identical (tabulated AMD order of the corridor pattern) for the
+    thread body and for the warp body in both loop orders."""
+    B = 6
+    pos, bv, ba, bj, T, lo, hi = corridor_problems(order, S, B, seed=order * 1000 + S * 10 + Kc)
+    kw = dict(eps_abs=eps, eps_rel=eps)
+    st = default_settings(**kw)
+    got = host_qp.solve_batch(order, pos, bv, ba, T, bj, settings=st, lo=lo, hi=hi, n_corridor=Kc)
+    gw = host_qp.solve_batch_warp(order, pos, bv, ba, T, bj, settings=st, lo=lo, hi=hi, n_corridor=Kc)
+    gr = host_qp.solve_batch_warp(order, pos, bv, ba, T, bj, settings=st, lo=lo, hi=hi, n_corridor=Kc, reversed_loops=True)
+    free = host_qp.solve_batch(order, pos, bv, ba, T, bj, settings=st)
+    n_rho, n_active = 0, 0
+    for b in range(B):
+        ok, coef, info = oracle_lib.minctrl_solve(order, S, pos[b], bv[b], ba[b], T[b], bound_jerk=bj[b],
+                                                  settings=oracle_lib.osqp_settings(**kw), corridor_lo=lo[b], corridor_hi=hi[b],
+                                                  n_corridor=Kc)
+        for g in (got, gw, gr):
+            assert (ok, info["status_val"], info["iter"]) == (g["solved"][b], g["status"][b], g["iters"][b])
+        n_rho += info["rho_updates"] > 0
+        if ok:
+            assert np.abs(coef - got["coef"][b]).max() / np.abs(coef).max() < RTOL
+            for g in (got, gw, gr):
+                assert np.array_equal(coef, g["coef"][b])
+            n_active += np.abs(coef - free["coef"][b]).max() > 1e-6   # the box changed the trajectory: rows are active
+    assert n_rho > 0 and n_active > 0
+
+
+def test_corridor_row_values_and_feasibility():
+    """The solved polynomial respects its boxes at the sample times (to the ADMM tolerance) and lo > hi is refused upstream."""
+    order, S, Kc = 7, 6, 3
+    pos, bv, ba, bj, T, lo, hi = corridor_problems(order, S, 4, seed=3, margin=0.1)
+    got = host_qp.solve_batch(order, pos, bv, ba, T, bj, settings=default_settings(eps_abs=1e-6, eps_rel=1e-6, max_iter=4000),
+                              lo=lo, hi=hi, n_corridor=Kc)
+    nc = order + 1
+    for b in range(4):
+        if not got["solved"][b]:
+            continue
+        for s in range(S):
+            c = got["coef"][b][nc * s: nc * (s + 1)]
+            for j in range(Kc):
+                t = (j + 1) / (Kc + 1) * T[b, s]
+                p = np.polyval(c[::-1], t)
+                assert lo[b, s] - 1e-3 <= p <= hi[b, s] + 1e-3

@@ -94,3 +94,48 @@ def test_both_kernels_agree_bitwise(gpu_ctx, monkeypatch):
         assert np.array_equal(a[k], b[k]), k
     ok, coef, info = oracle_lib.minctrl_solve(7, 8, pos[0], bv[0], ba[0], T[0], bound_jerk=bj[0])
     assert np.array_equal(coef, b["coef"][0]) and info["iter"] == b["iters"][0]
+
+
+@pytest.mark.parametrize("order,S,Kc,eps", [(7, 12, 2, 1e-3), (7, 8, 3, 1e-5), (5, 4, 1, 1e-3), (7, 16, 4, 1e-4)])
+def test_corridor_rows(gpu_ctx, monkeypatch, order, S, Kc, eps):
+    """Corridor (inequality) rows, the §9.3 extension of configs[3]: ACTIVE z-projection (auxil.c:188-203), rho classes
+    (auxil.c:75-104) and adaptive-rho refactorisations, on both CUDA kernels, against the reference's own OSQP: identical
+    status and iteration count, coefficients within 1e-5 relative (and bit-identical: the corridor patterns' AMD orders are
+    tabulated)."""
+    from test_qp_host_emulation import corridor_problems
+    B = 40
+    pos, bv, ba, bj, T, lo, hi = corridor_problems(order, S, B, seed=order * 1000 + S * 10 + Kc)
+    kw = dict(eps_abs=eps, eps_rel=eps)
+    mc = MinimumControl(gpu_ctx, order=order)
+    res = []
+    for env in ("UAVMP_QP_THREAD", "UAVMP_QP_WARP"):
+        monkeypatch.setenv(env, "1")
+        r = mc.solve_batch(pos, bv, ba, T, bound_jerk=bj, settings=default_settings(**kw), corridor_lo=lo, corridor_hi=hi,
+                           n_corridor=Kc)
+        res.append({k: v.copy() for k, v in r.items()})
+        monkeypatch.delenv(env)
+    free = mc.solve_batch(pos, bv, ba, T, bound_jerk=bj, settings=default_settings(**kw))
+    n_rho = n_active = n_ok = 0
+    for b in range(B):
+        ok, coef, info = oracle_lib.minctrl_solve(order, S, pos[b], bv[b], ba[b], T[b], bound_jerk=bj[b],
+                                                  settings=oracle_lib.osqp_settings(**kw), corridor_lo=lo[b], corridor_hi=hi[b],
+                                                  n_corridor=Kc)
+        for g in res:
+            assert (ok, info["status_val"], info["iter"]) == (g["solved"][b], g["status"][b], g["iters"][b]), (b, info)
+        n_rho += info["rho_updates"] > 0
+        if ok:
+            n_ok += 1
+            for g in res:
+                assert np.abs(coef - g["coef"][b]).max() / np.abs(coef).max() < RTOL
+                assert np.array_equal(coef, g["coef"][b]), b
+            n_active += np.abs(coef - free["coef"][b]).max() > 1e-6
+    assert n_ok > B // 2 and n_rho > 0 and n_active > B // 4
+
+
+def test_corridor_argument_checks(gpu_ctx):
+    mc = MinimumControl(gpu_ctx, order=7)
+    pos, z, T = np.zeros((2, 5)), np.zeros((2, 2)), np.ones((2, 4))
+    with pytest.raises(u.UavmpError):  # lo > hi: osqp_setup would refuse the problem (auxil.c:856-921)
+        mc.solve_batch(pos, z, z, T, bound_jerk=z, corridor_lo=np.ones((2, 4)), corridor_hi=np.zeros((2, 4)), n_corridor=2)
+    with pytest.raises(u.UavmpError):
+        mc.solve_batch(pos, z, z, T, bound_jerk=z, corridor_lo=np.zeros((2, 4)), corridor_hi=np.ones((2, 4)), n_corridor=9)

@@ -48,6 +48,12 @@ class KinoCounters(C.Structure):
                                             "n_insert", "n_update", "n_heuristic", "n_shot")]
 
 
+class PlanOptions(C.Structure):
+    """uavmp_plan_options: what the pipeline builds between the search and the QP (time allocation, corridor rows)."""
+    _fields_ = [("order", C.c_int), ("S", C.c_int), ("seg_time", C.c_double), ("time_alloc", C.c_int),
+                ("corridor_samples", C.c_int), ("corridor_margin", C.c_double)]
+
+
 class PlanInfo(C.Structure):
     """uavmp_plan_info: what uavmp_plan_wait reports about one batch."""
     _fields_ = [("error_flags", C.c_int), ("counters", KinoCounters), ("timings", Timings)]
@@ -62,7 +68,7 @@ SYMBOLS = [
     "uavmp_plan_batch", "uavmp_plan_batch_dev", "uavmp_get_timings", "uavmp_fpmath_eval", "uavmp_kino_set_profile",
     "uavmp_kino_get_profile", "uavmp_map_set_from_cloud", "uavmp_map_get_occupancy", "uavmp_polytraj_eval_batch",
     "uavmp_plan_submit", "uavmp_plan_wait", "uavmp_plan_stream_wait", "uavmp_plan_max_in_flight",
-    "uavmp_kino_set_path_cap",
+    "uavmp_kino_set_path_cap", "uavmp_minctrl_solve_corridor_batch", "uavmp_plan_options_default", "uavmp_plan_submit_opt",
 ]
 
 WORLDGEN_SYMBOLS = ["uavmp_mapgen_params_default", "uavmp_mapgen_cloud", "uavmp_grid_inflate_host"]
@@ -145,6 +151,12 @@ def load():
                                          C.POINTER(OsqpSettings), vp, vp, vp]
     lib.uavmp_plan_submit.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_double,
                                       C.POINTER(OsqpSettings), C.c_uint, vp, vp, vp, C.POINTER(C.c_longlong)]
+    lib.uavmp_plan_submit_opt.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.POINTER(PlanOptions), C.POINTER(OsqpSettings), C.c_uint,
+                                          vp, vp, vp, C.POINTER(C.c_longlong)]
+    lib.uavmp_plan_options_default.argtypes = [C.POINTER(PlanOptions)]
+    lib.uavmp_plan_options_default.restype = None
+    lib.uavmp_minctrl_solve_corridor_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp,
+                                                       C.POINTER(OsqpSettings), vp, vp, vp, vp]
     lib.uavmp_plan_wait.argtypes = [vp, C.c_longlong, C.POINTER(PlanInfo)]
     lib.uavmp_plan_stream_wait.argtypes = [vp, C.c_longlong, vp]
     lib.uavmp_kino_set_path_cap.argtypes = [vp, C.c_int]

@@ -12,14 +12,15 @@
 
 int kino_fpmath_eval(uavmp_ctx* ctx, int op, int npow, const double* x, double* y, long long n);
 // qp_kernel.cu
-int qp_solve_batch_dev(uavmp_ctx* ctx, cudaStream_t stream, QpScratch& scr, int* launches, int order, int S, int B,
+int qp_solve_batch_dev(uavmp_ctx* ctx, cudaStream_t stream, QpScratch& scr, int* launches, int order, int S, int Kc, int B,
                        const double* d_pos, const double* d_bv, const double* d_ba, const double* d_bj, const double* d_T,
-                       const uavmp_osqp_settings* st, double* d_coef, int* d_solved, int* d_status, int* d_iters);
-int qp_waypoints_from_paths(uavmp_ctx* ctx, PlanSlot& sl, int B, int S, double seg_time, const double* d_sv, const double* d_ev,
-                            double** d_pos, double** d_bv, double** d_ba, double** d_bj, double** d_T);
+                       const double* d_lo, const double* d_hi, const uavmp_osqp_settings* st, double* d_coef, int* d_solved,
+                       int* d_status, int* d_iters);
+int qp_waypoints_from_paths(uavmp_ctx* ctx, PlanSlot& sl, int B, const uavmp_plan_options& o, const double* d_sv, const double* d_ev,
+                            double** d_pos, double** d_bv, double** d_ba, double** d_bj, double** d_T, double** d_lo, double** d_hi);
 int qp_scatter_plan_outputs(uavmp_ctx* ctx, PlanSlot& sl, int B, int order, int S, const int* d_solved3, const double* d_coef3,
                             int* d_qp_solved, double* d_coef);
-int qp_get_plan_dev(uavmp_ctx* ctx, int order, int S, const QpPlanDev** out);
+int qp_get_plan_dev(uavmp_ctx* ctx, int order, int S, int Kc, const QpPlanDev** out);
 void qp_free_plans(uavmp_ctx* ctx);
 
 int ensure_bytes(uavmp_ctx* ctx, void** p, size_t* have, size_t want) {
@@ -362,7 +363,21 @@ int uavmp_minctrl_solve_batch(uavmp_ctx* ctx, int order, int S, int B, const dou
                               const double* bound_acc, const double* bound_jerk, const double* time_vec,
                               const uavmp_osqp_settings* settings, double* coef, int* solved, int* osqp_status,
                               int* iters) {
+  return uavmp_minctrl_solve_corridor_batch(ctx, order, S, 0, B, pos_1d, bound_vel, bound_acc, bound_jerk, time_vec, nullptr, nullptr,
+                                            settings, coef, solved, osqp_status, iters);
+}
+
+int uavmp_minctrl_solve_corridor_batch(uavmp_ctx* ctx, int order, int S, int Kc, int B, const double* pos_1d,
+                                       const double* bound_vel, const double* bound_acc, const double* bound_jerk,
+                                       const double* time_vec, const double* corridor_lo, const double* corridor_hi,
+                                       const uavmp_osqp_settings* settings, double* coef, int* solved, int* osqp_status,
+                                       int* iters) {
   if (!ctx || B <= 0 || S <= 0 || !pos_1d || !bound_vel || !bound_acc || !time_vec || !coef) return UAVMP_EINVAL;
+  if (Kc < 0 || Kc > 8) return uavmp_fail(ctx, UAVMP_EINVAL, "n_corridor must be in [0, 8]");
+  if (Kc > 0 && (!corridor_lo || !corridor_hi)) return uavmp_fail(ctx, UAVMP_EINVAL, "n_corridor > 0 needs corridor_lo / corridor_hi");
+  if (Kc > 0)  // osqp_setup rejects l > u (auxil.c:856-921): "solver init failed" for the whole call, like validate_data
+    for (size_t i = 0; i < (size_t)B * S; i++)
+      if (!(corridor_lo[i] <= corridor_hi[i])) return uavmp_fail(ctx, UAVMP_EINVAL, "corridor_lo > corridor_hi at entry %zu", i);
   if (order != 5 && order != 7) return uavmp_fail(ctx, UAVMP_EINVAL, "order must be 5 (jerk) or 7 (snap)");
   if (order == 7 && !bound_jerk) return uavmp_fail(ctx, UAVMP_EINVAL, "order 7 needs bound_jerk");
   cudaSetDevice(ctx->device);
@@ -370,23 +385,28 @@ int uavmp_minctrl_solve_batch(uavmp_ctx* ctx, int order, int S, int B, const dou
   if (!settings) { uavmp_osqp_settings_default(&def); settings = &def; }
   cudaStream_t st = ctx->stream;
   const int n = (order + 1) * S;
-  const size_t in_d = (size_t)B * ((S + 1) + 6 + S);
+  const size_t in_d = (size_t)B * ((S + 1) + 6 + S + 2 * S);
   int r = ensure_bytes(ctx, (void**)&ctx->d_qp_in, &ctx->qp_in_bytes, in_d * sizeof(double)); if (r) return r;
   r = ensure_bytes(ctx, (void**)&ctx->d_qp_out, &ctx->qp_out_bytes, (size_t)B * n * sizeof(double)); if (r) return r;
   r = ensure_bytes(ctx, (void**)&ctx->d_qp_int, &ctx->qp_int_bytes, (size_t)B * 3 * sizeof(int)); if (r) return r;
   double* d_pos = ctx->d_qp_in; double* d_bv = d_pos + (size_t)B * (S + 1); double* d_ba = d_bv + 2 * (size_t)B;
   double* d_bj = d_ba + 2 * (size_t)B; double* d_T = d_bj + 2 * (size_t)B;
+  double* d_lo = d_T + (size_t)B * S; double* d_hi = d_lo + (size_t)B * S;
   cudaEventRecord(ctx->ev[0], st);
   UAVMP_CUDA(ctx, cudaMemcpyAsync(d_pos, pos_1d, (size_t)B * (S + 1) * sizeof(double), cudaMemcpyHostToDevice, st));
   UAVMP_CUDA(ctx, cudaMemcpyAsync(d_bv, bound_vel, (size_t)B * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
   UAVMP_CUDA(ctx, cudaMemcpyAsync(d_ba, bound_acc, (size_t)B * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
   if (order == 7) UAVMP_CUDA(ctx, cudaMemcpyAsync(d_bj, bound_jerk, (size_t)B * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
   UAVMP_CUDA(ctx, cudaMemcpyAsync(d_T, time_vec, (size_t)B * S * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (Kc > 0) {
+    UAVMP_CUDA(ctx, cudaMemcpyAsync(d_lo, corridor_lo, (size_t)B * S * sizeof(double), cudaMemcpyHostToDevice, st));
+    UAVMP_CUDA(ctx, cudaMemcpyAsync(d_hi, corridor_hi, (size_t)B * S * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
   cudaEventRecord(ctx->ev[1], st);
   int* d_solved = ctx->d_qp_int; int* d_stat = d_solved + B; int* d_it = d_stat + B;
   int launches = 0;
-  r = qp_solve_batch_dev(ctx, st, ctx->qp_scr, &launches, order, S, B, d_pos, d_bv, d_ba, order == 7 ? d_bj : nullptr, d_T,
-                         settings, ctx->d_qp_out, d_solved, d_stat, d_it);
+  r = qp_solve_batch_dev(ctx, st, ctx->qp_scr, &launches, order, S, Kc, B, d_pos, d_bv, d_ba, order == 7 ? d_bj : nullptr, d_T,
+                         d_lo, d_hi, settings, ctx->d_qp_out, d_solved, d_stat, d_it);
   if (r) return r;
   cudaEventRecord(ctx->ev[2], st);
   UAVMP_CUDA(ctx, cudaMemcpyAsync(coef, ctx->d_qp_out, (size_t)B * n * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -409,10 +429,13 @@ int uavmp_minctrl_solve_batch(uavmp_ctx* ctx, int order, int S, int B, const dou
 // memory and the copies are part of the batch; otherwise they are device memory and the batch is ordered after everything
 // submitted to the context's stream so far.
 static int plan_issue(uavmp_ctx* ctx, PlanSlot& sl, int B, const double* sp, const double* sv, const double* ep, const double* ev,
-                      int order, int S, double seg_time, const uavmp_osqp_settings* settings, bool host_io, int* status,
+                      const uavmp_plan_options& opt, const uavmp_osqp_settings* settings, bool host_io, int* status,
                       int* qp_solved, double* coef) {
+  const int order = opt.order, S = opt.S, Kc = opt.corridor_samples;
   if (order != 5 && order != 7) return uavmp_fail(ctx, UAVMP_EINVAL, "order must be 5 or 7");
   if (S <= 0) return uavmp_fail(ctx, UAVMP_EINVAL, "S must be > 0");
+  if (Kc < 0 || Kc > 8 || !(opt.corridor_margin >= 0.0)) return uavmp_fail(ctx, UAVMP_EINVAL, "corridor_samples must be in [0, 8] and corridor_margin >= 0");
+  if (!opt.time_alloc && !(opt.seg_time > 0.0)) return uavmp_fail(ctx, UAVMP_EINVAL, "seg_time must be > 0");
   uavmp_osqp_settings def;
   if (!settings) { uavmp_osqp_settings_default(&def); settings = &def; }
   if (settings->max_iter <= 0 || settings->check_termination < 0 || settings->scaling < 0)
@@ -422,11 +445,11 @@ static int plan_issue(uavmp_ctx* ctx, PlanSlot& sl, int B, const double* sp, con
   r = kino_ensure_slot(ctx, sl, B);
   if (r) return r;
   const QpPlanDev* plan = nullptr;
-  r = qp_get_plan_dev(ctx, order, S, &plan);
+  r = qp_get_plan_dev(ctx, order, S, Kc, &plan);
   if (r) return r;
   const int n = (order + 1) * S;
   const size_t nB = (size_t)3 * B;
-  r = ensure_bytes(ctx, (void**)&sl.d_wp, &sl.wp_bytes, nB * ((S + 1) + 6 + S) * sizeof(double)); if (r) return r;
+  r = ensure_bytes(ctx, (void**)&sl.d_wp, &sl.wp_bytes, nB * ((S + 1) + 6 + S + 2 * S) * sizeof(double)); if (r) return r;
   r = ensure_bytes(ctx, (void**)&sl.d_qp_int, &sl.qp_int_bytes, nB * 3 * sizeof(int)); if (r) return r;
   if (host_io) {
     r = ensure_bytes(ctx, (void**)&sl.d_plan_out, &sl.plan_out_bytes, (size_t)B * 3 * n * sizeof(double)); if (r) return r;
@@ -458,10 +481,12 @@ static int plan_issue(uavmp_ctx* ctx, PlanSlot& sl, int B, const double* sp, con
   }
   cudaEventRecord(sl.ev[1], st);
   double* pos = sl.d_wp; double* bv = pos + nB * (S + 1); double* ba = bv + nB * 2; double* bj = ba + nB * 2; double* T = bj + nB * 2;
+  double* lo = T + nB * S; double* hi = lo + nB * S;
   int* d_solved3 = sl.d_qp_int; int* d_stat3 = d_solved3 + nB; int* d_it3 = d_stat3 + nB;
   if (warps > 0) {
     KinoQpDev qp;
-    qp.enabled = 1; qp.warps = warps; qp.Sg = S; qp.n = n; qp.seg_time = seg_time;
+    qp.enabled = 1; qp.warps = warps; qp.Sg = S; qp.n = n; qp.seg_time = opt.seg_time;
+    qp.time_alloc = opt.time_alloc; qp.step = ctx->kp.time_step_size; qp.Kc = Kc; qp.margin = opt.corridor_margin; qp.lo = lo; qp.hi = hi;
     qp.pos = pos; qp.bv = bv; qp.ba = ba; qp.bj = bj; qp.T = T;
     qp.coef = d_coef; qp.solved3 = d_solved3; qp.status3 = d_stat3; qp.iters3 = d_it3; qp.qp_solved = d_solved;
     r = kino_launch_search(ctx, sl, B, d_sp, d_sv, d_ep, d_ev, true, false, &qp, plan, settings);
@@ -471,12 +496,12 @@ static int plan_issue(uavmp_ctx* ctx, PlanSlot& sl, int B, const double* sp, con
     // sequential fallback (the QP workspace does not fit next to the search, or UAVMP_NO_FUSE): three more kernels on the stream
     r = kino_launch_search(ctx, sl, B, d_sp, d_sv, d_ep, d_ev, true, false, nullptr, nullptr, nullptr);
     if (r) return r;
-    double *w_pos, *w_bv, *w_ba, *w_bj, *w_T;
-    r = qp_waypoints_from_paths(ctx, sl, B, S, seg_time, d_sv, d_ev, &w_pos, &w_bv, &w_ba, &w_bj, &w_T);
+    double *w_pos, *w_bv, *w_ba, *w_bj, *w_T, *w_lo, *w_hi;
+    r = qp_waypoints_from_paths(ctx, sl, B, opt, d_sv, d_ev, &w_pos, &w_bv, &w_ba, &w_bj, &w_T, &w_lo, &w_hi);
     if (r) return r;
     int launches = 0;
-    r = qp_solve_batch_dev(ctx, st, sl.qp_scr, &launches, order, S, 3 * B, w_pos, w_bv, w_ba, order == 7 ? w_bj : nullptr, w_T,
-                           settings, sl.d_qp_out, d_solved3, d_stat3, d_it3);
+    r = qp_solve_batch_dev(ctx, st, sl.qp_scr, &launches, order, S, Kc, 3 * B, w_pos, w_bv, w_ba, order == 7 ? w_bj : nullptr, w_T,
+                           w_lo, w_hi, settings, sl.d_qp_out, d_solved3, d_stat3, d_it3);
     if (r) return r;
     r = qp_scatter_plan_outputs(ctx, sl, B, order, S, d_solved3, sl.d_qp_out, d_solved, d_coef);
     if (r) return r;
@@ -499,20 +524,37 @@ static int plan_issue(uavmp_ctx* ctx, PlanSlot& sl, int B, const double* sp, con
 
 int uavmp_plan_max_in_flight(void) { return UAVMP_NSLOT - 1; }
 
-int uavmp_plan_submit(uavmp_ctx* ctx, int B, const double* start_pt, const double* start_vel, const double* end_pt,
-                      const double* end_vel, int order, int S, double seg_time, const uavmp_osqp_settings* settings,
-                      unsigned flags, int* search_status, int* qp_solved, double* coef, long long* ticket) {
-  if (!ctx || B <= 0 || !start_pt || !start_vel || !end_pt || !end_vel || !search_status || !qp_solved || !coef || !ticket) return UAVMP_EINVAL;
+void uavmp_plan_options_default(uavmp_plan_options* o) {
+  o->order = 7; o->S = 8; o->seg_time = 1.0; o->time_alloc = 0; o->corridor_samples = 0; o->corridor_margin = 0.0;
+}
+static uavmp_plan_options plain_options(int order, int S, double seg_time) {
+  uavmp_plan_options o;
+  uavmp_plan_options_default(&o);
+  o.order = order; o.S = S; o.seg_time = seg_time;
+  return o;
+}
+
+int uavmp_plan_submit_opt(uavmp_ctx* ctx, int B, const double* start_pt, const double* start_vel, const double* end_pt,
+                          const double* end_vel, const uavmp_plan_options* opt, const uavmp_osqp_settings* settings,
+                          unsigned flags, int* search_status, int* qp_solved, double* coef, long long* ticket) {
+  if (!ctx || B <= 0 || !start_pt || !start_vel || !end_pt || !end_vel || !opt || !search_status || !qp_solved || !coef || !ticket) return UAVMP_EINVAL;
   cudaSetDevice(ctx->device);
   PlanSlot& sl = ctx->slots[1 + ctx->next_ticket % (UAVMP_NSLOT - 1)];  // slot 0 serves the synchronous entry points
   if (sl.in_flight)
     return uavmp_fail(ctx, UAVMP_ESTATE, "%d batches are in flight: collect the oldest ticket with uavmp_plan_wait first", UAVMP_NSLOT - 1);
-  int r = plan_issue(ctx, sl, B, start_pt, start_vel, end_pt, end_vel, order, S, seg_time, settings,
-                     !(flags & UAVMP_PLAN_DEVICE_IO), search_status, qp_solved, coef);
+  int r = plan_issue(ctx, sl, B, start_pt, start_vel, end_pt, end_vel, *opt, settings, !(flags & UAVMP_PLAN_DEVICE_IO), search_status,
+                     qp_solved, coef);
   if (r) return r;
   sl.ticket = ctx->next_ticket++;
   *ticket = sl.ticket;
   return UAVMP_OK;
+}
+
+int uavmp_plan_submit(uavmp_ctx* ctx, int B, const double* start_pt, const double* start_vel, const double* end_pt,
+                      const double* end_vel, int order, int S, double seg_time, const uavmp_osqp_settings* settings,
+                      unsigned flags, int* search_status, int* qp_solved, double* coef, long long* ticket) {
+  const uavmp_plan_options o = plain_options(order, S, seg_time);
+  return uavmp_plan_submit_opt(ctx, B, start_pt, start_vel, end_pt, end_vel, &o, settings, flags, search_status, qp_solved, coef, ticket);
 }
 
 static PlanSlot* find_ticket(uavmp_ctx* ctx, long long ticket) {
@@ -546,7 +588,7 @@ int uavmp_plan_batch_dev(uavmp_ctx* ctx, int B, const double* d_sp, const double
   PlanSlot& sl = ctx->slots[0];
   int r = slot_finish(ctx, sl, nullptr);  // surfaces the error flag of the previous asynchronous batch on this slot
   if (r) return r;
-  r = plan_issue(ctx, sl, B, d_sp, d_sv, d_ep, d_ev, order, S, seg_time, settings, false, d_search_status, d_qp_solved, d_coef);
+  r = plan_issue(ctx, sl, B, d_sp, d_sv, d_ep, d_ev, plain_options(order, S, seg_time), settings, false, d_search_status, d_qp_solved, d_coef);
   if (r) return r;
   sl.ticket = -1;
   // everything submitted to the context's stream after this call sees the results
@@ -561,7 +603,7 @@ int uavmp_plan_batch(uavmp_ctx* ctx, int B, const double* start_pt, const double
   cudaSetDevice(ctx->device);
   PlanSlot& sl = ctx->slots[0];
   slot_finish(ctx, sl, nullptr);
-  int r = plan_issue(ctx, sl, B, start_pt, start_vel, end_pt, end_vel, order, S, seg_time, settings, true, search_status, qp_solved, coef);
+  int r = plan_issue(ctx, sl, B, start_pt, start_vel, end_pt, end_vel, plain_options(order, S, seg_time), settings, true, search_status, qp_solved, coef);
   if (r) return r;
   sl.ticket = -1;
   return slot_finish(ctx, sl, nullptr);

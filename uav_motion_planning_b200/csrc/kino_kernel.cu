@@ -565,7 +565,17 @@ __device__ __forceinline__ void qp_round(SearchSmem& s, unsigned char* smem_raw,
     const int np = bt.n_path[q];
     const double* path = bt.path_stage + (size_t)q * bt.path_cap * 3;
     for (int k = lane; k <= Sg; k += 32) qp.pos[(size_t)b * (Sg + 1) + k] = path[3 * (((long long)k * (np - 1)) / Sg) + ax];
-    for (int sgm = lane; sgm < Sg; sgm += 32) qp.T[(size_t)b * Sg + sgm] = qp.seg_time;
+    for (int sgm = lane; sgm < Sg; sgm += 32) {
+      const long long i0 = ((long long)sgm * (np - 1)) / Sg, i1 = ((long long)(sgm + 1) * (np - 1)) / Sg;
+      // time allocation (uavmp_plan_options): the searched trajectory's own timing, one path sample every time_step_size
+      qp.T[(size_t)b * Sg + sgm] = qp.time_alloc ? (double)(i1 > i0 ? i1 - i0 : 1) * qp.step : qp.seg_time;
+      if (qp.Kc > 0) {  // corridor box of the segment on this axis: its path points' extent +- margin (min / max: order-free)
+        double mn = path[3 * i0 + ax], mx = mn;
+        for (long long i = i0 + 1; i <= i1; i++) { const double v = path[3 * i + ax]; mn = fmin(mn, v); mx = fmax(mx, v); }
+        qp.lo[(size_t)b * Sg + sgm] = mn - qp.margin;
+        qp.hi[(size_t)b * Sg + sgm] = mx + qp.margin;
+      }
+    }
     if (lane == 0) {
       qp.bv[(size_t)b * 2] = bt.start_vel[3 * q + ax]; qp.bv[(size_t)b * 2 + 1] = bt.end_vel[3 * q + ax];
       qp.ba[(size_t)b * 2] = 0.0; qp.ba[(size_t)b * 2 + 1] = 0.0;
@@ -573,7 +583,7 @@ __device__ __forceinline__ void qp_round(SearchSmem& s, unsigned char* smem_raw,
     }
     __syncwarp();
     QpIo io;
-    io.pos = qp.pos; io.bv = qp.bv; io.ba = qp.ba; io.bj = qp.bj; io.T = qp.T;
+    io.pos = qp.pos; io.bv = qp.bv; io.ba = qp.ba; io.bj = qp.bj; io.T = qp.T; io.lo = qp.lo; io.hi = qp.hi;
     io.coef = qp.coef; io.solved = qp.solved3; io.status = qp.status3; io.iters = qp.iters3; io.B = 3 * bt.B; io.stride = 0;
     qp_warp_solve_one(pl, io, S, reinterpret_cast<double*>(smem_raw) + (size_t)warp * pl.ws_warp, b);
     if (lane == 0 && !qp.solved3[b]) atomicAnd(qp.qp_solved + q, 0);
@@ -1261,7 +1271,28 @@ __global__ void __launch_bounds__(KT, (KT <= 256 ? 2 : 1)) kino_search_kernel(co
       if (s.use_num + n_new >= P.allocated) {
         // pool exhausted while committing this expansion (:243-247): the reference returns on the spot
         if (tid == 0) {
-          s.cnt[3] += n1;  // probes up to the abort are not separable; count the expansion's
+          // The reference stops at the primitive whose new node takes the last pool slot; its counters stop there too
+          // (probes, inserts, in-place updates and heuristic calls of the lattice prefix up to that primitive).  Once per
+          // query at most, so one thread replays the prefix.
+          const uint32_t stop_id = (uint32_t)(P.allocated - 1);
+          int pstar = nprim;
+          for (int e = 0; e < n2; e++) {
+            const int p = s.list2[e];
+            if (s.state[p] == ST_NEW && s.id[p] == stop_id) { pstar = p; break; }
+          }
+          int probes = 0, upd = 0;
+          for (int e = 0; e < n1; e++) probes += ((int)s.list1[e] <= pstar) ? 1 : 0;
+          for (int e = 0; e < n2; e++) {
+            const int p = s.list2[e];
+            if (p >= pstar) break;
+            const uint8_t st = s.state[p];
+            if (st != ST_OPEN_CAND && st != ST_FOLLOW_CAND) continue;
+            const int leader = (st == ST_FOLLOW_CAND) ? (int)s.id[p] : p;
+            const double g = s.cg + ginc_of(P, p);
+            if (g < s.b.gcur[leader]) { s.b.gcur[leader] = g; upd++; }  // tmp_g_cost < old_node->g_cost (:254)
+          }
+          const int ins = P.allocated - s.use_num;
+          s.cnt[3] += probes; s.cnt[4] += ins; s.cnt[5] += upd; s.cnt[6] += ins + upd;
           s.use_num = P.allocated;
           s.status = UAVMP_NO_PATH_FOUND;
         }

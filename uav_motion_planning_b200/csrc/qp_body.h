@@ -322,18 +322,9 @@ QP_HD void qp_solve_one(const QpPlanDev& pl, const QpIo& io, const uavmp_osqp_se
   for (int p = 0; p < pl.nnzP; p++) W(pl.o_Px, p) = QP_LDG(pl.P_coef + p) * fpm::powi(T[QP_LDG(pl.P_seg + p)], QP_LDG(pl.P_pow + p));
   for (int p = 0; p < pl.nnzA; p++) W(pl.o_Ax, p) = QP_LDG(pl.A_coef + p) * fpm::powi(T[QP_LDG(pl.A_seg + p)], QP_LDG(pl.A_pow + p));
   for (int i = 0; i < n; i++) W(pl.o_q, i) = 0.0;
-  for (int i = 0; i < m; i++) {
-    const int src = QP_LDG(pl.l_src + i);
-    double v = 0.0;
-    if (src >= 0) {
-      if (src <= Sg) v = io.pos[(size_t)b * (Sg + 1) + src];
-      else {
-        const int r = (src - (Sg + 1)) >> 1, e = (src - (Sg + 1)) & 1;
-        v = (r == 0 ? io.bv : (r == 1 ? io.ba : io.bj))[(size_t)b * 2 + e];
-      }
-    }
-    W(pl.o_l, i) = v;
-    W(pl.o_u, i) = v;
+  for (int i = 0; i < m; i++) {  // equality rows: l == u (minimum_control.cpp:98-125); corridor rows (extension): lo <= . <= hi
+    W(pl.o_l, i) = qp_bound_value(io, b, Sg, QP_LDG(pl.l_src + i));
+    W(pl.o_u, i) = qp_bound_value(io, b, Sg, QP_LDG(pl.u_src + i));
   }
 
   // ---- scale_data (scaling.c:49-165) ----------------------------------------------------------------------------
@@ -474,7 +465,9 @@ QP_HD void qp_solve_one(const QpPlanDev& pl, const QpIo& io, const uavmp_osqp_se
         for (int u = 0; u < 2; u++) if (i0 + u < m) {
           const double zt = tmv[u] + rv[u] * WXZ(n + i0 + u);
           double zn = rv[u] * yv[u];
-          zn = (1.0 * zn + alpha * zt) + one_m_alpha * zp[u];
+          // OSQPVectorf_add_scaled3 with x == a and sca == 1 takes its incrementing form: z += (alpha ztilde + (1 - alpha) z_prev)
+          // (algebra/builtin/vector.c:441-444); the association only shows on inequality rows (equality rows are clipped to l == u)
+          zn = zn + (alpha * zt + one_m_alpha * zp[u]);
           zn = fmin(fmax(zn, lv[u]), uv[u]);
           W(pl.o_z, i0 + u) = zn;
           double dy = (alpha * zt + one_m_alpha * zp[u]) + (-1.0) * zn;

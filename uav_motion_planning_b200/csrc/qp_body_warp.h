@@ -290,16 +290,9 @@ QPW_HD void qp_warp_solve_one(const QpPlanDev& pl, const QpIo& io, const uavmp_o
   QPW_PFOR(p, 0, pl.nnzA) WW(pl.o_Ax, p) = QPW_LDG(pl.A_coef + p) * fpm::powi(T[QPW_LDG(pl.A_seg + p)], QPW_LDG(pl.A_pow + p));
   QPW_PFOR(i, 0, n) { WW(pl.o_q, i) = 0.0; WW(pl.o_D, i) = 1.0; }
   QPW_PFOR(i, 0, m) {
-    const int src = QPW_LDG(pl.l_src + i);
-    double v = 0.0;
-    if (src >= 0) {
-      if (src <= Sg) v = io.pos[(size_t)b * (Sg + 1) + src];
-      else {
-        const int r = (src - (Sg + 1)) >> 1, e = (src - (Sg + 1)) & 1;
-        v = (r == 0 ? io.bv : (r == 1 ? io.ba : io.bj))[(size_t)b * 2 + e];
-      }
-    }
-    WW(pl.o_l, i) = v; WW(pl.o_u, i) = v; WW(pl.o_E, i) = 1.0;
+    WW(pl.o_l, i) = qp_bound_value(io, b, Sg, QPW_LDG(pl.l_src + i));
+    WW(pl.o_u, i) = qp_bound_value(io, b, Sg, QPW_LDG(pl.u_src + i));
+    WW(pl.o_E, i) = 1.0;
   }
   QPW_SYNC();
   // ---- scale_data (scaling.c:49-165) ---------------------------------------------------------------------------------
@@ -402,7 +395,7 @@ QPW_HD void qp_warp_solve_one(const QpPlanDev& pl, const QpIo& io, const uavmp_o
         const double rv = WW(pl.o_rhoinv, i), zp = WW(pl.o_zprev, i), yv = WW(pl.o_y, i);
         const double zt = WW(pl.o_tm, i) + rv * WW(pl.o_xz, n + i);
         double zn = rv * yv;
-        zn = (1.0 * zn + alpha * zt) + one_m_alpha * zp;
+        zn = zn + (alpha * zt + one_m_alpha * zp);  // add_scaled3's incrementing form (vector.c:441-444), see qp_body.h
         zn = fmin(fmax(zn, WW(pl.o_l, i)), WW(pl.o_u, i));
         WW(pl.o_z, i) = zn;
         double dy = (alpha * zt + one_m_alpha * zp) + (-1.0) * zn;

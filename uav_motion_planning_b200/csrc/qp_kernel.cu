@@ -76,10 +76,10 @@ static int qpw_warps_per_cta(const QpPlanDev& pl, int B) {
 }
 
 // ---- pipeline glue: waypoints from the searched paths, outputs back to per-plan layout --------------------------------------
-__global__ void k_waypoints(int B, int S, double seg_time, const int* n_path, const double* path_stage, int path_cap,
-                            const int* search_status, const double* sv, const double* ev, double* pos, double* bv,
-                            double* ba, double* bj, double* T) {
-  // axis-major batch of 3B one-dimensional problems: problem id = axis * B + q
+__global__ void k_waypoints(int B, int S, double seg_time, int time_alloc, double step, int Kc, double margin, const int* n_path,
+                            const double* path_stage, int path_cap, const int* search_status, const double* sv, const double* ev,
+                            double* pos, double* bv, double* ba, double* bj, double* T, double* lo, double* hi) {
+  // axis-major batch of 3B one-dimensional problems: problem id = axis * B + q (the rule of uavmp_plan_options, see uavmp.h)
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= B) return;
   const int np = n_path[q];
@@ -99,7 +99,19 @@ __global__ void k_waypoints(int B, int S, double seg_time, const int* n_path, co
     bv[id * 2 + 1] = ok ? ev[3 * q + ax] : 0.0;
     ba[id * 2] = 0.0; ba[id * 2 + 1] = 0.0;
     bj[id * 2] = 0.0; bj[id * 2 + 1] = 0.0;
-    for (int s = 0; s < S; s++) T[id * S + s] = seg_time;
+    for (int s = 0; s < S; s++) {
+      const long long i0 = ok ? ((long long)s * (np - 1)) / S : 0, i1 = ok ? ((long long)(s + 1) * (np - 1)) / S : 0;
+      T[id * S + s] = (time_alloc && ok) ? (double)(i1 > i0 ? i1 - i0 : 1) * step : seg_time;
+      if (Kc > 0) {
+        double mn = 0.0, mx = 0.0;
+        if (ok) {
+          mn = mx = path[3 * i0 + ax];
+          for (long long i = i0 + 1; i <= i1; i++) { const double v = path[3 * i + ax]; mn = fmin(mn, v); mx = fmax(mx, v); }
+        }
+        lo[id * S + s] = mn - margin;
+        hi[id * S + s] = mx + margin;
+      }
+    }
   }
 }
 
@@ -117,11 +129,11 @@ __global__ void k_scatter_plan(int B, int n, const int* search_status, const int
 }  // namespace
 
 // =============================================================================================================
-static QpPlan* get_plan(uavmp_ctx* ctx, int order, int S) {
+static QpPlan* get_plan(uavmp_ctx* ctx, int order, int S, int Kc) {
   for (QpPlan* p : ctx->qp_plans)
-    if (p->host->order == order && p->host->S == S) return p;
+    if (p->host->order == order && p->host->S == S && p->host->Kc == Kc) return p;
   QpPlan* p = new QpPlan();
-  p->host = qp_plan_build(order, S);
+  p->host = qp_plan_build(order, S, Kc);
   const QpPlanHost& H = *p->host;
   std::vector<int> ints;
   std::vector<double> dbl;
@@ -148,31 +160,32 @@ void qp_free_plans(uavmp_ctx* ctx) {
 }
 
 // device view of the (order, S) plan, for the in-kernel QP of the search kernel
-int qp_get_plan_dev(uavmp_ctx* ctx, int order, int S, const QpPlanDev** out) {
-  QpPlan* p = get_plan(ctx, order, S);
+int qp_get_plan_dev(uavmp_ctx* ctx, int order, int S, int Kc, const QpPlanDev** out) {
+  QpPlan* p = get_plan(ctx, order, S, Kc);
   if (!p) return uavmp_fail(ctx, UAVMP_ECUDA, "cannot build the QP plan");
   *out = &p->dev;
   return UAVMP_OK;
 }
 
 int qp_plan_stats(uavmp_ctx* ctx, int order, int S, int* out6) {
-  QpPlan* p = get_plan(ctx, order, S);
+  QpPlan* p = get_plan(ctx, order, S, 0);
   if (!p) return UAVMP_ECUDA;
   out6[0] = p->host->n; out6[1] = p->host->m; out6[2] = p->host->nnzP; out6[3] = p->host->nnzA; out6[4] = p->host->nnzK;
   out6[5] = p->host->nnzL;
   return UAVMP_OK;
 }
 
-int qp_solve_batch_dev(uavmp_ctx* ctx, cudaStream_t stream, QpScratch& scr, int* launches, int order, int S, int B,
+int qp_solve_batch_dev(uavmp_ctx* ctx, cudaStream_t stream, QpScratch& scr, int* launches, int order, int S, int Kc, int B,
                        const double* d_pos, const double* d_bv, const double* d_ba, const double* d_bj, const double* d_T,
-                       const uavmp_osqp_settings* st, double* d_coef, int* d_solved, int* d_status, int* d_iters) {
-  QpPlan* p = get_plan(ctx, order, S);
+                       const double* d_lo, const double* d_hi, const uavmp_osqp_settings* st, double* d_coef, int* d_solved,
+                       int* d_status, int* d_iters) {
+  QpPlan* p = get_plan(ctx, order, S, Kc);
   if (!p) return uavmp_fail(ctx, UAVMP_ECUDA, "cannot build the QP plan");
   if (st->max_iter <= 0 || st->check_termination < 0 || st->scaling < 0)
     return uavmp_fail(ctx, UAVMP_EINVAL, "bad OSQP settings");
   const int stride = (B + 31) & ~31;
   QpIo io;
-  io.pos = d_pos; io.bv = d_bv; io.ba = d_ba; io.bj = d_bj ? d_bj : d_ba; io.T = d_T;
+  io.pos = d_pos; io.bv = d_bv; io.ba = d_ba; io.bj = d_bj ? d_bj : d_ba; io.T = d_T; io.lo = d_lo; io.hi = d_hi;
   io.coef = d_coef; io.solved = d_solved; io.status = d_status; io.iters = d_iters; io.B = B; io.stride = stride;
   if (launches) *launches = 1;
   if (const int wpc = qpw_warps_per_cta(p->dev, B)) {
@@ -199,15 +212,17 @@ int qp_solve_batch_dev(uavmp_ctx* ctx, cudaStream_t stream, QpScratch& scr, int*
   return UAVMP_OK;
 }
 
-int qp_waypoints_from_paths(uavmp_ctx* ctx, PlanSlot& sl, int B, int S, double seg_time, const double* d_sv, const double* d_ev,
-                            double** d_pos, double** d_bv, double** d_ba, double** d_bj, double** d_T) {
+int qp_waypoints_from_paths(uavmp_ctx* ctx, PlanSlot& sl, int B, const uavmp_plan_options& o, const double* d_sv, const double* d_ev,
+                            double** d_pos, double** d_bv, double** d_ba, double** d_bj, double** d_T, double** d_lo, double** d_hi) {
   const size_t nB = (size_t)3 * B;
+  const int S = o.S;
   double* pos = sl.d_wp; double* bv = pos + nB * (S + 1); double* ba = bv + nB * 2; double* bj = ba + nB * 2;
-  double* T = bj + nB * 2;
-  k_waypoints<<<(B + 127) / 128, 128, 0, sl.stream>>>(B, S, seg_time, sl.d_npath, sl.d_path_stage, sl.path_cap, sl.d_status, d_sv,
-                                                      d_ev, pos, bv, ba, bj, T);
+  double* T = bj + nB * 2; double* lo = T + nB * S; double* hi = lo + nB * S;
+  k_waypoints<<<(B + 127) / 128, 128, 0, sl.stream>>>(B, S, o.seg_time, o.time_alloc, ctx->kp.time_step_size, o.corridor_samples,
+                                                      o.corridor_margin, sl.d_npath, sl.d_path_stage, sl.path_cap, sl.d_status,
+                                                      d_sv, d_ev, pos, bv, ba, bj, T, lo, hi);
   UAVMP_CUDA(ctx, cudaGetLastError());
-  *d_pos = pos; *d_bv = bv; *d_ba = ba; *d_bj = bj; *d_T = T;
+  *d_pos = pos; *d_bv = bv; *d_ba = ba; *d_bj = bj; *d_T = T; *d_lo = lo; *d_hi = hi;
   return UAVMP_OK;
 }
 

@@ -6,9 +6,10 @@
 
 struct QpPlanHost {
   int order, S, k, nc, n, m, N, nnzP, nnzA, nnzK, nnzL;
+  int Kc = 0, m_eq = 0;                                                 // corridor samples per segment; rows [m_eq, m) are the corridor (inequality) rows
   std::vector<int> Pp, Pi, P_seg, P_pow;  std::vector<double> P_coef;   // upper-triangular CSC of P + value recipe
   std::vector<int> Ap, Ai, A_seg, A_pow;  std::vector<double> A_coef;   // CSC of A + value recipe coef * T[seg]^pow
-  std::vector<int> l_src;                                               // bound source per constraint row (-1: 0.0)
+  std::vector<int> l_src, u_src;                                        // bound sources per constraint row (-1: 0.0), see qp_bound_value
   std::vector<int> Kp0, Ki0;                                            // unpermuted upper CSC KKT pattern (form_KKT order)
   bool perm_from_table = false;                                         // true: the reference AMD's permutation (tabulated)
   std::vector<int> perm;                                                // perm[j] = original KKT index at position j
@@ -21,15 +22,16 @@ struct QpPlanHost {
   std::vector<int> Ltpos, LtR, LtEnd;                                   // L in the L' solve's consumption order: slot of L entry j, row index per slot, end slot per processed column
 };
 
-QpPlanHost* qp_plan_build(int order, int S);
+// Kc > 0 appends Kc corridor rows per segment (an extension): lo <= p_s(phi_j T_s) <= hi at phi_j = (j + 1) / (Kc + 1)
+QpPlanHost* qp_plan_build(int order, int S, int Kc = 0);
 
 // device view (all int arrays live in one allocation)
 struct QpPlanDev {
-  int order, S, k, nc, n, m, N, nnzP, nnzA, nnzK, nnzL;
+  int order, S, k, nc, n, m, N, nnzP, nnzA, nnzK, nnzL, Kc, m_eq;
   const int *Pp, *Pi, *P_seg, *P_pow;
   const int *Ap, *Ai, *A_seg, *A_pow;
   const double *P_coef, *A_coef;
-  const int *l_src, *perm, *Kp, *Ki, *Kkind, *Kidx, *Lp, *Li, *Rp, *Rc, *Rpos, *Ltpos, *LtR, *LtEnd;
+  const int *l_src, *u_src, *perm, *Kp, *Ki, *Kkind, *Kidx, *Lp, *Li, *Rp, *Rc, *Rpos, *Ltpos, *LtR, *LtEnd;
   const int *Arp, *Arj, *Arx, *Psp, *Psa, *Psv, *LevP, *LevC;
   int nlev, ws_warp;  // ws_warp: doubles of the one-warp-per-problem workspace (everything except the LxT copy)
   // workspace layout (offsets in doubles)
@@ -38,13 +40,30 @@ struct QpPlanDev {
 };
 
 // flattening of a host plan into one int array + one double array (what is uploaded), and the view over it
-struct QpPlanOffsets { size_t Pp, Pi, P_seg, P_pow, Ap, Ai, A_seg, A_pow, l_src, perm, Kp, Ki, Kkind, Kidx, Lp, Li, Rp, Rc, Rpos, Ltpos, LtR, LtEnd, Arp, Arj, Arx, Psp, Psa, Psv, LevP, LevC, A_coef; };
+struct QpPlanOffsets { size_t Pp, Pi, P_seg, P_pow, Ap, Ai, A_seg, A_pow, l_src, u_src, perm, Kp, Ki, Kkind, Kidx, Lp, Li, Rp, Rc, Rpos, Ltpos, LtR, LtEnd, Arp, Arj, Arx, Psp, Psa, Psv, LevP, LevC, A_coef; };
 void qp_plan_pack(const QpPlanHost& H, std::vector<int>& ints, std::vector<double>& dbls, QpPlanOffsets& off);
 void qp_plan_bind(const QpPlanHost& H, const QpPlanOffsets& off, const int* ints, const double* dbls, QpPlanDev& D);
 
 // per-batch I/O of the solve kernel
 struct QpIo {
   const double* pos; const double* bv; const double* ba; const double* bj; const double* T;
+  const double* lo; const double* hi;  // corridor boxes, B x S each (plans with Kc > 0), else nullptr
   double* coef; int* solved; int* status; int* iters;
   int B, stride;
 };
+
+// Bound source encoding of l_src / u_src: -1 -> 0.0; [0, S] -> pos_1d[src]; S+1 .. S+6 -> bound_vel / bound_acc / bound_jerk
+// [start, end]; S+7+s -> corridor lo of segment s; 2S+7+s -> corridor hi of segment s.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline double qp_bound_value(const QpIo& io, int b, int S, int src) {
+  if (src < 0) return 0.0;
+  if (src <= S) return io.pos[(size_t)b * (S + 1) + src];
+  if (src < S + 7) {
+    const int r = (src - (S + 1)) >> 1, e = (src - (S + 1)) & 1;
+    return (r == 0 ? io.bv : (r == 1 ? io.ba : io.bj))[(size_t)b * 2 + e];
+  }
+  if (src < 2 * S + 7) return io.lo[(size_t)b * S + (src - (S + 7))];
+  return io.hi[(size_t)b * S + (src - (2 * S + 7))];
+}

@@ -18,6 +18,7 @@
 #include <set>
 #include <vector>
 
+#include "fpmath.h"
 #include "qp_plan.h"
 
 // amd_perm_table.inc defines: static const int* qp_amd_table_lookup(int order, int S, int N)
@@ -35,12 +36,12 @@ struct Entry { int r, c, seg, pw; double coef; };
 
 }  // namespace
 
-QpPlanHost* qp_plan_build(int order, int S) {
+QpPlanHost* qp_plan_build(int order, int S, int Kc) {
   QpPlanHost* pl = new QpPlanHost();
   QpPlanHost& P = *pl;
   const int k = (order + 1) / 2, nc = order + 1;
-  const int n = nc * S, m = 2 * k + (k + 1) * (S - 1), N = n + m;
-  P.order = order; P.S = S; P.k = k; P.nc = nc; P.n = n; P.m = m; P.N = N;
+  const int n = nc * S, m_eq = 2 * k + (k + 1) * (S - 1), m = m_eq + Kc * S, N = n + m;
+  P.order = order; P.S = S; P.k = k; P.nc = nc; P.n = n; P.m = m; P.N = N; P.Kc = Kc; P.m_eq = m_eq;
 
   // ---- P (upper) ------------------------------------------------------------------------------------------
   std::vector<Entry> pe;
@@ -84,6 +85,14 @@ QpPlanHost* qp_plan_build(int order, int S) {
     int base = k + (k + 1) * (S - 1);
     for (int r = 0; r < k; r++) deriv_row(base + r, S - 1, r);
   }
+  // corridor rows (extension; no counterpart in minimum_control.cpp, whose rows are all equalities): the
+  // position of segment s at the interior sample time phi_j T_s, phi_j = (j + 1) / (Kc + 1), as sum_i c_i phi_j^i T_s^i —
+  // the entry is (phi_j^i) * T_s^i, evaluated exactly like that by oracle/minctrl_ref.cpp
+  for (int s = 0; s < S; s++)
+    for (int j = 0; j < Kc; j++) {
+      const double phi = (double)(j + 1) / (double)(Kc + 1);
+      for (int i = 0; i < nc; i++) ae.push_back({m_eq + s * Kc + j, nc * s + i, s, i, fpm::powi(phi, i)});
+    }
   std::sort(ae.begin(), ae.end(), [](const Entry& a, const Entry& b) { return a.c != b.c ? a.c < b.c : a.r < b.r; });
   P.Ap.assign(n + 1, 0);
   for (auto& e : ae) {
@@ -100,6 +109,9 @@ QpPlanHost* qp_plan_build(int order, int S) {
   P.l_src[eb] = S;
   for (int r = 1; r < k; r++) P.l_src[eb + r] = (S + 1) + 2 * (r - 1) + 1;
   for (int s = 0; s + 1 < S; s++) P.l_src[k + (k + 1) * s] = s + 1;
+  P.u_src = P.l_src;  // equality rows: l == u (minimum_control.cpp:98-125)
+  for (int s = 0; s < S; s++)
+    for (int j = 0; j < Kc; j++) { P.l_src[m_eq + s * Kc + j] = (S + 7) + s; P.u_src[m_eq + s * Kc + j] = (2 * S + 7) + s; }
 
   // ---- KKT = [[P + sigma I, A'], [A, -diag(1/rho)]], upper-triangular CSC, entries in the order OSQP's form_KKT
   // writes them (3rd/osqp/algebra/_common/kkt.c:254-291 _kkt_assemble_csc): column c < n holds P's column c and, when P
@@ -276,7 +288,7 @@ void qp_plan_pack(const QpPlanHost& H, std::vector<int>& ints, std::vector<doubl
   auto push = [&](const std::vector<int>& v) { size_t at = ints.size(); ints.insert(ints.end(), v.begin(), v.end()); return at; };
   o.Pp = push(H.Pp); o.Pi = push(H.Pi); o.P_seg = push(H.P_seg); o.P_pow = push(H.P_pow);
   o.Ap = push(H.Ap); o.Ai = push(H.Ai); o.A_seg = push(H.A_seg); o.A_pow = push(H.A_pow);
-  o.l_src = push(H.l_src); o.perm = push(H.perm); o.Kp = push(H.Kp); o.Ki = push(H.Ki); o.Kkind = push(H.Kkind);
+  o.l_src = push(H.l_src); o.u_src = push(H.u_src); o.perm = push(H.perm); o.Kp = push(H.Kp); o.Ki = push(H.Ki); o.Kkind = push(H.Kkind);
   o.Kidx = push(H.Kidx); o.Lp = push(H.Lp); o.Li = push(H.Li); o.Rp = push(H.Rp); o.Rc = push(H.Rc); o.Rpos = push(H.Rpos);
   o.Ltpos = push(H.Ltpos); o.LtR = push(H.LtR); o.LtEnd = push(H.LtEnd);
   o.Arp = push(H.Arp); o.Arj = push(H.Arj); o.Arx = push(H.Arx); o.Psp = push(H.Psp); o.Psa = push(H.Psa); o.Psv = push(H.Psv);
@@ -288,11 +300,11 @@ void qp_plan_pack(const QpPlanHost& H, std::vector<int>& ints, std::vector<doubl
 
 void qp_plan_bind(const QpPlanHost& H, const QpPlanOffsets& o, const int* I, const double* Dbl, QpPlanDev& D) {
   D.order = H.order; D.S = H.S; D.k = H.k; D.nc = H.nc; D.n = H.n; D.m = H.m; D.N = H.N;
-  D.nnzP = H.nnzP; D.nnzA = H.nnzA; D.nnzK = H.nnzK; D.nnzL = H.nnzL;
+  D.nnzP = H.nnzP; D.nnzA = H.nnzA; D.nnzK = H.nnzK; D.nnzL = H.nnzL; D.Kc = H.Kc; D.m_eq = H.m_eq;
   D.Pp = I + o.Pp; D.Pi = I + o.Pi; D.P_seg = I + o.P_seg; D.P_pow = I + o.P_pow;
   D.Ap = I + o.Ap; D.Ai = I + o.Ai; D.A_seg = I + o.A_seg; D.A_pow = I + o.A_pow;
   D.P_coef = Dbl; D.A_coef = Dbl + o.A_coef;
-  D.l_src = I + o.l_src; D.perm = I + o.perm; D.Kp = I + o.Kp; D.Ki = I + o.Ki; D.Kkind = I + o.Kkind; D.Kidx = I + o.Kidx;
+  D.l_src = I + o.l_src; D.u_src = I + o.u_src; D.perm = I + o.perm; D.Kp = I + o.Kp; D.Ki = I + o.Ki; D.Kkind = I + o.Kkind; D.Kidx = I + o.Kidx;
   D.Lp = I + o.Lp; D.Li = I + o.Li; D.Rp = I + o.Rp; D.Rc = I + o.Rc; D.Rpos = I + o.Rpos;
   D.Ltpos = I + o.Ltpos; D.LtR = I + o.LtR; D.LtEnd = I + o.LtEnd;
   D.Arp = I + o.Arp; D.Arj = I + o.Arj; D.Arx = I + o.Arx; D.Psp = I + o.Psp; D.Psa = I + o.Psa; D.Psv = I + o.Psv;

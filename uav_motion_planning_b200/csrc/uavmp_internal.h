@@ -112,6 +112,11 @@ struct KinoQpDev {
   int warps;                 // problems solved concurrently per round (how many workspaces fit in the overlay)
   int Sg, n;                 // segments, coefficients per axis ((order + 1) * S)
   double seg_time;
+  int time_alloc;            // 1: T_s = max(idx_{s+1} - idx_s, 1) * step (uavmp_plan_options)
+  double step;               // time_step_size: spacing of the sampled path points
+  int Kc;                    // corridor samples per segment (0: none)
+  double margin;             // corridor box = bounding box of the segment's path points +- margin
+  double* lo; double* hi;    // per-problem corridor boxes (3 B x S), Kc > 0 only
   double* pos; double* bv; double* ba; double* bj; double* T;  // per-problem inputs of qp_warp_solve_one (3 B problems)
   double* coef;              // B x 3 x n, the caller-visible layout (problem id * n)
   int* solved3; int* status3; int* iters3;                     // per problem

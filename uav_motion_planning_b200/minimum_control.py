@@ -30,7 +30,10 @@ class MinimumControl:
         self._coef_1d = None
         self.last = {}
 
-    def solve_batch(self, pos_1d, bound_vel, bound_acc, time_vec, bound_jerk=None, order=None, settings=None):
+    def solve_batch(self, pos_1d, bound_vel, bound_acc, time_vec, bound_jerk=None, order=None, settings=None,
+                    corridor_lo=None, corridor_hi=None, n_corridor=0):
+        """n_corridor > 0 (extension): per segment, the position at n_corridor interior times must stay in
+        [corridor_lo[b, s], corridor_hi[b, s]] — true inequality rows (uavmp_minctrl_solve_corridor_batch)."""
         order = self.order if order is None else order
         pos = _lib.as_f64(pos_1d)
         pos = pos.reshape(1, -1) if pos.ndim == 1 else pos
@@ -43,9 +46,15 @@ class MinimumControl:
         coef = np.zeros((B, n))
         solved, status, iters = np.zeros(B, np.int32), np.zeros(B, np.int32), np.zeros(B, np.int32)
         st = settings or self.settings
-        self.ctx.check(self.lib.uavmp_minctrl_solve_batch(
-            self.ctx.h, order, S, B, _lib.ptr(pos), _lib.ptr(bv), _lib.ptr(ba), _lib.ptr(bj), _lib.ptr(T), C.byref(st),
-            _lib.ptr(coef), _lib.ptr(solved), _lib.ptr(status), _lib.ptr(iters)))
+        if n_corridor > 0:
+            lo, hi = _lib.as_f64(corridor_lo).reshape(B, S), _lib.as_f64(corridor_hi).reshape(B, S)
+            self.ctx.check(self.lib.uavmp_minctrl_solve_corridor_batch(
+                self.ctx.h, order, S, n_corridor, B, _lib.ptr(pos), _lib.ptr(bv), _lib.ptr(ba), _lib.ptr(bj), _lib.ptr(T),
+                _lib.ptr(lo), _lib.ptr(hi), C.byref(st), _lib.ptr(coef), _lib.ptr(solved), _lib.ptr(status), _lib.ptr(iters)))
+        else:
+            self.ctx.check(self.lib.uavmp_minctrl_solve_batch(
+                self.ctx.h, order, S, B, _lib.ptr(pos), _lib.ptr(bv), _lib.ptr(ba), _lib.ptr(bj), _lib.ptr(T), C.byref(st),
+                _lib.ptr(coef), _lib.ptr(solved), _lib.ptr(status), _lib.ptr(iters)))
         self.last = dict(coef=coef, solved=solved, status=status, iters=iters)
         return self.last
 

@@ -36,14 +36,26 @@ def _info_dict(info):
                 timings={k: getattr(info.timings, k) for k, _ in _lib.Timings._fields_})
 
 
-def plan_submit(ctx, B, sp, sv, ep, ev, status, solved, coef, order=7, S=8, seg_time=1.0, settings=None, device_io=False):
-    """uavmp_plan_submit: asynchronous, returns a ticket.  Every argument is a raw pointer (int): page-locked host memory, or
-    device memory with device_io=True.  The buffers must stay alive until plan_wait(ticket) has returned."""
+def plan_options(order=7, S=8, seg_time=1.0, time_alloc=0, corridor_samples=0, corridor_margin=0.0):
+    """uavmp_plan_options (include/uavmp.h): time_alloc 1 = the searched trajectory's own timing per segment; corridor_samples
+    > 0 = box constraints around each segment's path points (+- corridor_margin) at that many interior times."""
+    return _lib.PlanOptions(order, S, float(seg_time), int(time_alloc), int(corridor_samples), float(corridor_margin))
+
+
+def plan_submit(ctx, B, sp, sv, ep, ev, status, solved, coef, order=7, S=8, seg_time=1.0, settings=None, device_io=False,
+                options=None):
+    """uavmp_plan_submit(_opt): asynchronous, returns a ticket.  Every argument is a raw pointer (int): page-locked host memory,
+    or device memory with device_io=True.  The buffers must stay alive until plan_wait(ticket) has returned."""
     vp = C.c_void_p
     t = C.c_longlong(-1)
-    ctx.check(ctx.lib.uavmp_plan_submit(ctx.h, B, vp(sp), vp(sv), vp(ep), vp(ev), order, S, float(seg_time),
-                                        C.byref(settings) if settings is not None else None,
-                                        PLAN_DEVICE_IO if device_io else 0, vp(status), vp(solved), vp(coef), C.byref(t)))
+    st = C.byref(settings) if settings is not None else None
+    fl = PLAN_DEVICE_IO if device_io else 0
+    if options is not None:
+        ctx.check(ctx.lib.uavmp_plan_submit_opt(ctx.h, B, vp(sp), vp(sv), vp(ep), vp(ev), C.byref(options), st, fl, vp(status),
+                                                vp(solved), vp(coef), C.byref(t)))
+    else:
+        ctx.check(ctx.lib.uavmp_plan_submit(ctx.h, B, vp(sp), vp(sv), vp(ep), vp(ev), order, S, float(seg_time), st, fl,
+                                            vp(status), vp(solved), vp(coef), C.byref(t)))
     return t.value
 
 
@@ -63,9 +75,11 @@ def max_in_flight(ctx):
     return ctx.lib.uavmp_plan_max_in_flight()
 
 
-def plan_batches_pipelined(ctx, batches, order=7, S=8, seg_time=1.0, settings=None):
+def plan_batches_pipelined(ctx, batches, order=7, S=8, seg_time=1.0, settings=None, options=None):
     """Host arrays in, host arrays out, every batch through uavmp_plan_submit / uavmp_plan_wait with as many batches in flight
     as the library allows (cross-batch pipelining).  `batches`: iterable of (start_pt, start_vel, end_pt, end_vel)."""
+    if options is not None:
+        order, S = options.order, options.S
     n = (order + 1) * S
     depth = max_in_flight(ctx)
     live, out = [], []
@@ -83,7 +97,7 @@ def plan_batches_pipelined(ctx, batches, order=7, S=8, seg_time=1.0, settings=No
             collect()
         t = plan_submit(ctx, B, sp.ctypes.data, sv.ctypes.data, ep.ctypes.data, ev.ctypes.data,
                         res["search_status"].ctypes.data, res["qp_solved"].ctypes.data, res["coef"].ctypes.data,
-                        order=order, S=S, seg_time=seg_time, settings=settings)
+                        order=order, S=S, seg_time=seg_time, settings=settings, options=options)
         live.append((t, (sp, sv, ep, ev), res))
     while live:
         collect()
