@@ -9,6 +9,8 @@
 over one batch of B = 4096 synthetic start->goal queries on the 50 x 50 x 10 m random-obstacle map @ 0.1 m: KinoAstar::search
 (launch-file parameters, collision_check_type 1) -> S+1 waypoints -> three 8-segment 7th-order minimum-snap QPs per query.
 --config 2: configs[2], 32 768 queries per step with collision_check_type 2 (ellipsoid only), same map.
+--config 3: configs[3], 65 536 queries per step in TOTAL (strong scaling: each of the N ranks takes 65 536 / N), fix-wall map,
+12-segment minimum snap with corridor box constraints (2 samples per segment, box = the segment's path extent +- 0.2 m).
 --config 4: configs[4], QP only: 16 384 16-segment minimum-snap problems per step, eps_abs = eps_rel swept 1e-3 .. 1e-6.
 
 Every step uses a different seeded batch.  The K timed steps are issued through the library's asynchronous entry point
@@ -43,6 +45,11 @@ WORKLOADS = {
     1: dict(tag="configs[1]", batch=4096, map=(50.0, 50.0, 10.0), map_type=0, ctype=1, order=7, S=8, seg_time=1.0,
             text="batch 4096 queries, 50x50x10 m random map @0.1 m, kino-A* + 8-seg 7th-order min-snap, per GPU",
             kino="launch-file params, collision_check_type 1 (grid + ellipsoid)"),
+    3: dict(tag="configs[3]", batch=65536, map=(50.0, 50.0, 10.0), map_type=2, ctype=1, order=7, S=12, seg_time=1.0, Kc=2, margin=0.2,
+            strong=True,
+            text="batch 65536 queries, fix-wall map (two slabs, 0.5 m gap), kino-A* + 12-seg 7th-order min-snap with corridor box "
+                 "constraints (2 samples per segment, box = segment path extent +- 0.2 m), sharded over the GPUs (strong scaling)",
+            kino="launch-file params, collision_check_type 1 (grid + ellipsoid)"),
     2: dict(tag="configs[2]", batch=32768, map=(50.0, 50.0, 10.0), map_type=0, ctype=2, order=7, S=8, seg_time=1.0,
             text="batch 32768 queries, 50x50x10 m random map @0.1 m, SE(3) ellipsoid collision (r=0.4 h=0.1), kino-A* + 8-seg "
                  "7th-order min-snap, per GPU",
@@ -52,9 +59,10 @@ WORKLOADS = {
 
 def workload_config(wl, B, n_gpus):
     """identical on both arms (the driver compares them)"""
+    corr = f", corridor rows: {wl['Kc']} samples / segment, margin {wl['margin']} m" if wl.get("Kc") else ""
     return {"workload": f"{wl['tag']}: {wl['text']}", "batch_per_gpu": B, "global_batch": B * n_gpus,
-            "map": "500x500x100 int8, random_forest seed 1", "kino": wl["kino"],
-            "qp": f"order {wl['order']}, S {wl['S']}, T_i {wl['seg_time']}, OSQP eps 1e-3, 3 axes per plan",
+            "map": "500x500x100 int8, " + ("fix_map_type 2 (wall)" if wl["map_type"] == 2 else "random_forest seed 1"), "kino": wl["kino"],
+            "qp": f"order {wl['order']}, S {wl['S']}, T_i {wl['seg_time']}, OSQP eps 1e-3, 3 axes per plan{corr}",
             "batches": "a different seeded query batch every step; steps may overlap in time (GPU: up to 6 batches in flight, "
                        "CPU: one work queue over all steps), every step's results are complete inside the timed region",
             "l2": "256 MiB flush write before every step; the per-step working set (>= 5 GB of search arenas + a different "
@@ -152,7 +160,7 @@ def cpu_plans(world, params, wl, jobs, threads):
                 return
             (sp, sv, ep, ev), q = jobs[k]
             t0 = time.perf_counter()
-            r = plan_one(o, sp[q], sv[q], ep[q], ev[q], order, S, seg)[:2]
+            r = plan_one(o, sp[q], sv[q], ep[q], ev[q], order, S, seg, n_corridor=wl.get("Kc", 0), margin=wl.get("margin", 0.0))[:2]
             busy[t] += time.perf_counter() - t0
             res.append(r)
 
@@ -232,15 +240,22 @@ def run_gpu(args, rank, world_size, local_rank, wl):
     if world_size > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = u.Context(local_rank)
-    B, K, W = args.batch or wl["batch"], args.steps, args.warmup
+    strong = bool(wl.get("strong")) and not args.batch
+    B, K, W = args.batch or (wl["batch"] // world_size if strong else wl["batch"]), args.steps, args.warmup
     order, S, seg = wl["order"], wl["S"], wl["seg_time"]
     n = (order + 1) * S
+    opts = planner.plan_options(order=order, S=S, seg_time=seg, corridor_samples=wl.get("Kc", 0), corridor_margin=wl.get("margin", 0.0))
     world = u.make_world(*wl["map"], seed=1, map_type=wl["map_type"])
     ka = u.KinoAstar(ctx)
     ka.setLaunchParams()
     ka.setParam(collision_check_type=wl["ctype"])
     ka.setGridMap(world)
-    batches = make_batches(world, B, K + W, rank)
+    if strong:  # one global batch per step, cut into contiguous shards (sharding.shard_range): rank r works on its own slice
+        from uav_motion_planning_b200.sharding import shard_range
+        lo_q, hi_q = shard_range(wl["batch"], rank, world_size)
+        batches = [tuple(a[lo_q:hi_q] for a in bt) for bt in make_batches(world, wl["batch"], K + W, 0)]
+    else:
+        batches = make_batches(world, B, K + W, rank)
     depth = planner.max_in_flight(ctx)
     lib_stream = torch.cuda.ExternalStream(ctx.stream, device=dev)  # the context's stream: device inputs are ordered after it
     side = torch.cuda.Stream(device=dev)                            # all-gathers run here, behind each batch's completion
@@ -291,8 +306,7 @@ def run_gpu(args, rank, world_size, local_rank, wl):
                 sp, sv, ep, ev = d_in[i]
                 o = ring[slot]
             t = planner.plan_submit(ctx, B, sp.data_ptr(), sv.data_ptr(), ep.data_ptr(), ev.data_ptr(), o["status"].data_ptr(),
-                                    o["solved"].data_ptr(), o["coef"].data_ptr(), order=order, S=S, seg_time=seg,
-                                    device_io=not host_io)
+                                    o["solved"].data_ptr(), o["coef"].data_ptr(), device_io=not host_io, options=opts)
             live.append(t)
             if world_size > 1:
                 if host_io:  # results land in pinned host memory: they go back up for the gather once the batch is complete
@@ -363,8 +377,8 @@ def run_gpu(args, rank, world_size, local_rank, wl):
             traffic = json.load(open(tp)).get("kino_search_kernel_dram_bytes_per_launch")
         out = {
             "metric": METRIC, "value": value, "unit": "plans/s", "n_gpus": world_size, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(wl, B, world_size),
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(wl, B, world_size),
             "execution": f"uavmp_plan_submit / uavmp_plan_wait, {depth} batches in flight; the QP of a query is solved inside the search "
                          "kernel by the CTA that finished it (one warp per 1-D problem)",
             "e2e": {"value": e2e_val, "unit": "plans/s", "h2d_bytes_per_step": B * 12 * 8,
@@ -469,7 +483,7 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", type=int, default=1, choices=[1, 2, 4], help="BASELINE.json configs[N] (default 1: the metric's)")
+    ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4], help="BASELINE.json configs[N] (default 1: the metric's)")
     ap.add_argument("--batch", type=int, default=0, help="queries per GPU per step (0: the configuration's own)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries per step in the CPU sample (0: auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -217,7 +217,8 @@ int uavmp_polytraj_eval_batch(uavmp_ctx* ctx, int B, int order, int S, const dou
 int uavmp_get_timings(uavmp_ctx* ctx, uavmp_timings* out);
 /* optional in-kernel profile of the search: SM cycles per phase (0 pop, 1 shot/path, 2 primitive evaluation, 3 dedup +
  * table probe, 4 heuristic + id scan, 5 node/hash writes, 6 ordered heap commit, 7 query setup/epilogue) summed over the
- * CTAs (entries 8..15: diagnostics: cloud staging cycles, staged / unstaged expansions, staged points, flagged primitives),
+ * CTAs (entries 8..15: diagnostics: cloud staging cycles, staged expansions, cycles of the ordered heap replay, staged points,
+ * flagged primitives, closure staging / slow key updates / deferred writes of the commit),
  * the cycles every query kept its CTA busy, and the grid size of the last launch */
 int uavmp_kino_set_profile(uavmp_ctx* ctx, int on);
 int uavmp_kino_get_profile(uavmp_ctx* ctx, unsigned long long phase_cycles[16], long long* query_cycles, int cap, int* grid);

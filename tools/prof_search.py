@@ -25,7 +25,7 @@ pr = ka.profile(B)
 c = ka.counters()
 qc = pr["query_cycles"].astype(np.float64)
 pops = r["n_pop"].astype(np.float64)
-diag = {k: pr["phase_cycles"].pop(k) for k in ("n_staged", "n_unstaged", "sum_npts", "sum_flagged_prims", "commit_closure_io", "commit_slow_updates", "commit_deferred_writes")}
+diag = {k: pr["phase_cycles"].pop(k) for k in ("n_staged", "commit_replay", "sum_npts", "sum_flagged_prims", "commit_closure_io", "commit_slow_updates", "commit_deferred_writes")}
 tot = sum(pr["phase_cycles"].values())
 clk_ghz = qc.max() / (t["search_ms"] * 1e6)  # lower bound on the SM clock: the longest query cannot outlast the kernel
 out = dict(B=B, diag=diag, search_ms=t["search_ms"], grid=pr["grid"], counters=c,

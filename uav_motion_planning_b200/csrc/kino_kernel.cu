@@ -83,7 +83,11 @@ struct PhaseB {  // successor classification / commit
   uint8_t imp[UAVMP_MAXPRIM];    // per candidate: 0 not improving, 1 improving, 2 improving and ordered with the pushes
   uint8_t inun[UAVMP_MAXPRIM];   // that node is an ancestor of a new leaf: its key was already written in order
   double gpc[UAVMP_MAXPRIM];     // g of every commit candidate
+  HeapSlot ev[UAVMP_MAXPRIM];    // per commit candidate (list2 order): what the ordered commit replays — a push {f, id, hash slot},
+                                 // a key mutation of an ancestor of a new leaf {f, id, hash slot | EV_SETKEY}, or nothing (id NONE)
+  HeapSlot evc[UAVMP_MAXPRIM];   // the same without the "nothing" records (compacted by warp 0 at the start of the replay)
 };
+#define EV_SETKEY 0x80000000u
 
 struct SearchSmem {
   union __align__(128) { PhaseA a; PhaseB b; };
@@ -122,6 +126,7 @@ struct SearchSmem {
   unsigned long long ph[16];  // per-phase SM cycles [0..7] + diagnostics [8..15] of this CTA (thread 0's clock), only when bt.phase_cycles != nullptr
   long long ph_t;
   unsigned long long phq[16];
+  float nzf[UAVMP_MAXNA], nz2[UAVMP_MAXNA];  // (float)(ua[c] + 9.81) and its square: the c-dependent part of the body axis
   int arena;                  // index of the arena this CTA took from the pool
   int npend;                  // finished queries' QP problems (3 q + axis) waiting for a round
   int pend[16];
@@ -367,12 +372,16 @@ __device__ __forceinline__ void closure_load(SearchSmem& s, const HeapSlot* H, i
   {  // level 0 = the new leaves themselves (offset 0, m entries): initialised by the whole warp
     for (int j = lane; j < m; j += 32) { HeapSlot e; e.f = 0; e.id = UAVMP_NONE; e.hs = 0; s.b.hc[j] = e; s.b.hidx[j] = (uint32_t)(len0 + 1 + j); }
   }
-  if (lane != 0) {
-    for (int j = 0; j < cnt; j++) {
+  // ancestors, level by level, one entry per lane (a level of a 256-leaf batch has up to 128 entries: copying it from its
+  // owner lane alone was a 128-trip serial loop)
+  const int depth = 32 - __clz(len0 + m);  // levels 1 .. depth-1 hold ancestors
+  for (int d = 1; d < depth; d++) {
+    const int lo_d = __shfl_sync(FULL, lo, d), cnt_d = __shfl_sync(FULL, cnt, d), off_d = __shfl_sync(FULL, c.off, d);
+    for (int j = lane; j < cnt_d; j += 32) {
       // asynchronous 16 B global -> shared copies (L2 only): all of a level's loads are in flight at once
-      if (lo + j < HTOP) s.b.hc[c.off + j] = s.htop[lo + j];
-      else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&s.b.hc[c.off + j])), "l"(H + lo + j) : "memory");
-      s.b.hidx[c.off + j] = (uint32_t)(lo + j);
+      if (lo_d + j < HTOP) s.b.hc[off_d + j] = s.htop[lo_d + j];
+      else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&s.b.hc[off_d + j])), "l"(H + lo_d + j) : "memory");
+      s.b.hidx[off_d + j] = (uint32_t)(lo_d + j);
     }
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
@@ -429,10 +438,56 @@ __device__ __forceinline__ void closure_push(SearchSmem& s, int n1, double f, ui
   __syncwarp();
 }
 
+// ---- the push through a register-resident ancestor chain -------------------------------------------------------------------
+// closure_push above reads and writes the staged ancestors in shared memory for every push (~100 dependent instructions,
+// measured ~800 cycles per push: the ordered commit was 41 % of all CTA time).  The chain of the CURRENT leaf n1 is kept in
+// registers instead: lane d caches the staged entry of ancestor n1 >> d (lane 0: the leaf itself).  A push that moves L
+// ancestors down is then one ballot plus a one-lane shuffle of the chain (lane j - 1 takes lane j's entry, lane L the new
+// node); moving on to leaf n1 + 1 changes the cached index only on the lanes d <= ctz(n1 + 1), which write their entry back to
+// the staging array (if modified) and fetch their next one.  Indices of one level only grow during a batch, so an entry that
+// left the cache is never read again before closure_flush.
+struct ChainCache {
+  HeapSlot e;  // the cached staging entry (lanes above the root: f = -inf, never moves)
+  int ix;      // its index in s.b.hc
+};
+__device__ __forceinline__ void chain_writeback(SearchSmem& s, ChainCache& cc) {
+  if (cc.e.hs & HS_DIRTY) s.b.hc[cc.ix] = cc.e;
+  cc.e.hs = 0;
+  __syncwarp();
+}
+__device__ __forceinline__ void chain_fill(const SearchSmem& s, const Closure& c, ChainCache& cc, int n1, int lane) {
+  const int a = n1 >> lane;
+  cc.e.f = -INFINITY; cc.e.id = 0; cc.e.hs = 0; cc.ix = 0;
+  if (lane == 0) cc.ix = c.off + (a - c.lo);  // the leaf's own slot, written when the chain moves on
+  else if (a >= 1) { cc.ix = c.off + (a - c.lo); cc.e = s.b.hc[cc.ix]; }
+}
+// std::push_heap of (f, id, hs) as the leaf the chain is filled for.  lm = bits 0 .. lane, a per-lane constant: with
+// cont = (ballot of "ancestor key > f") >> 1, the number L of consecutive ancestors that move down satisfies
+// lane < L <=> (cont & lm) == lm and lane == L <=> (cont & lm) == lm >> 1 — no find-first-set on the critical path.
+__device__ __forceinline__ void chain_push(ChainCache& cc, double f, uint32_t id, uint32_t hs, unsigned lm) {
+  const unsigned cont = __ballot_sync(FULL, cc.e.f > f) >> 1;
+  HeapSlot up;
+  up.f = __shfl_down_sync(FULL, cc.e.f, 1);
+  up.id = __shfl_down_sync(FULL, cc.e.id, 1);
+  up.hs = __shfl_down_sync(FULL, cc.e.hs, 1) | HS_DIRTY;
+  const unsigned cl = cont & lm;
+  if (cl == lm) cc.e = up;
+  else if (cl == (lm >> 1)) { cc.e.f = f; cc.e.id = id; cc.e.hs = hs | HS_DIRTY; }
+}
+// the chain of leaf n1 becomes the chain of leaf n1 + 1 (same tree level, same closure): ancestor n1 >> d changes on the
+// lanes d <= ctz(n1 + 1); the entries of a level are contiguous in the staging array, so the next one is the next slot
+__device__ __forceinline__ void chain_advance(SearchSmem& s, ChainCache& cc, int n1_next, int lane) {
+  if (lane < __ffs(n1_next)) {
+    s.b.hc[cc.ix] = cc.e;
+    cc.ix++;
+    cc.e = s.b.hc[cc.ix];
+  }
+}
+
 // in-place key mutation (kino_astar.cpp:251-265) of a node that may sit among the staged ancestors: look for it in the
 // closure; if it is not there, write through its live heap position
 __device__ void heap_set_key_slow(SearchSmem& s, HeapSlot* H, const HashSlot* table, uint32_t id, uint32_t hs, double f,
-                                  int lane, const Closure& c) {
+                                  int lane, const Closure c) {
   __syncwarp();
   int found = -1;
   if (c.active) {
@@ -633,6 +688,10 @@ __global__ void __launch_bounds__(KT, (KT <= 256 ? 2 : 1)) kino_search_kernel(co
   const bool prof = bt.phase_cycles != nullptr;
   const int na = P.na, K = P.K, nprim = P.nprim;
   if (tid < 16) { s.ph[tid] = 0; s.phq[tid] = 0; }
+  if (tid < UAVMP_MAXNA) {
+    const float nz = (tid < na) ? (float)(P.ua[tid] + 9.81) : 1.f;  // a3 = u + 9.81 e_z (kino_astar.cpp:724)
+    s.nzf[tid] = nz; s.nz2[tid] = nz * nz;
+  }
   if (tid == 0) {
     s.ph_t = clock64(); s.npend = 0;
     mbar_init(&s.mbar, 1);
@@ -697,7 +756,7 @@ __global__ void __launch_bounds__(KT, (KT <= 256 ? 2 : 1)) kino_search_kernel(co
       hstore(s, H, 1, hs);
       s.heap_len = 1; s.use_num = 1; s.n_pop = 0; s.status = 0; s.trunc = 0;
       s.pop_hash = 0xcbf29ce484222325ull;
-      s.cnt[3] += 1; s.cnt[4] += 1; s.cnt[6] += 1;  // hash probe, insert, heuristic of the start node
+      s.cnt[4] += 1; s.cnt[6] += 1;  // insert and heuristic of the start node (its expanded_list_.insert is not a lookup, :96)
     }
     unsigned my_occ = 0, my_cloud = 0;
     __syncthreads();
@@ -1023,7 +1082,7 @@ __global__ void __launch_bounds__(KT, (KT <= 256 ? 2 : 1)) kino_search_kernel(co
           __syncthreads();
         }
         PH_MARK(8);  // staging time
-        if (prof && tid == 0) { s.ph[staged ? 9 : 10] += 1; s.ph[11] += (unsigned long long)(staged ? s.npts : 0); s.ph[12] += (unsigned long long)nT; }
+        if (prof && tid == 0) { if (staged) s.ph[9] += 1; s.ph[11] += (unsigned long long)(staged ? s.npts : 0); s.ph[12] += (unsigned long long)nT; }
         unsigned my_hits = 0;
         (void)my_hits;
         if (staged) {
@@ -1061,26 +1120,30 @@ __global__ void __launch_bounds__(KT, (KT <= 256 ? 2 : 1)) kino_search_kernel(co
 #pragma unroll
             for (int c = 0; c < UAVMP_MAXNA; c++) fz[c] = (c < na) ? (float)s.X[i][2][c] : 1e30f;
             // two points per trip: their cull chains are independent, which roughly halves the dependent latency
+            // Float slab test without a body-axis table.  The ellipsoid is diag(r, r, h) in the body frame, so with w = d . b3:
+            // || E^-1 d ||^2 = |d|^2 / r^2 + w^2 (1/h^2 - 1/r^2), and b3 = n / |n| with n = (ux, uy, uz + 9.81) (:724-726), hence
+            //   || E^-1 d ||^2 <= v   <=>   (d . n)^2 (1/h^2 - 1/r^2) <= (v - |d|^2 / r^2) |n|^2
+            // where d . n and |n|^2 are sums of per-axis terms (registers for the unit's a and b, a 9-entry shared-memory table
+            // for c): no global table load inside the per-candidate loop.  v = 1 + slab_margin: above it the pair is a miss;
+            // v = 1 - slab_margin: below it a hit — both final, the float error is far below the margin (1 %, widened by the
+            // host for maps whose coordinates are coarse in float).  Only the shell in between takes the f64 path.
+            const float nxf = (float)P.ua[a], nyf = (float)P.ua[b];
+            const float nab2 = nxf * nxf + nyf * nyf;
+            const float kq = P.inv_h2f - P.inv_r2f, v_hi = 1.f + slab_margin, v_lo = 1.f - slab_margin;
             auto decide = [&](const float4& q, float dx, float dy, float dxy2, uint32_t cand) {
+              const float dn_ab = dx * nxf + dy * nyf;
               while (cand) {
                 const int c = __ffs(cand) - 1;
                 cand &= cand - 1;
                 if (!((mask >> c) & 1u)) continue;
-                {  // float slab test: || E^-1 d ||^2 = (|d|^2 - w^2)/r^2 + w^2/h^2, w = d . b3; slab_margin >> float error
-                  const float4 bf = __ldg(lat.b3f + (ab * na + c));
-                  const float dz = q.z - fz[c];
-                  const float w = (dx * bf.x + dy * bf.y) + dz * bf.z, w2 = w * w;
-                  const float val = ((dxy2 + dz * dz) - w2) * P.inv_r2f + w2 * P.inv_h2f;
-                  if (val > 1.f + slab_margin) continue;
-                  // clearly inside: the float error of `val` is far below the margin (1 %, widened by the host for maps
-                  // whose coordinates are coarse in float), so the exact expression is < 1 as well.  Deciding it here
-                  // keeps the f64 path (table loads, executed by one lane at a time when lanes diverge) to the thin shell
-                  // around the surface.
-                  if (val < 1.f - slab_margin) { s.state[ab * na + c] = ST_REJECT; mask &= ~(1u << c); continue; }
-                }
-                EllipsoidTest t;
-                make_test(t, P, lat, ab * na + c, px, py, s.X[i][2][c]);
-                if (point_hits(t, q)) { s.state[ab * na + c] = ST_REJECT; mask &= ~(1u << c); }
+                const float dz = q.z - fz[c];
+                const float t = dn_ab + dz * s.nzf[c];
+                const float lhs = t * t * kq, rr = (dxy2 + dz * dz) * P.inv_r2f, n2 = nab2 + s.nz2[c];
+                if (lhs > (v_hi - rr) * n2) continue;                                                               // clear miss
+                if (lhs < (v_lo - rr) * n2) { s.state[ab * na + c] = ST_REJECT; mask &= ~(1u << c); continue; }     // clear hit
+                EllipsoidTest t64;
+                make_test(t64, P, lat, ab * na + c, px, py, s.X[i][2][c]);
+                if (point_hits(t64, q)) { s.state[ab * na + c] = ST_REJECT; mask &= ~(1u << c); }
               }
             };
             if (!mask) continue;
@@ -1350,8 +1413,11 @@ __global__ void __launch_bounds__(KT, (KT <= 256 ? 2 : 1)) kino_search_kernel(co
         const int p = s.list2[e];
         const uint8_t st = s.state[p];
         bool event = false;  // does this candidate change optimal_time / count as an update?
+        HeapSlot rec;        // what the ordered commit (phase D) replays for this candidate
+        rec.f = s.b.f[p]; rec.id = UAVMP_NONE; rec.hs = 0;
         if (st == ST_NEW) {
           event = true;
+          rec.id = s.id[p]; rec.hs = s.b.hs[p];
         } else {
           const int leader = (st == ST_FOLLOW_CAND) ? (int)s.id[p] : p;
           double run = s.b.gcur[leader];  // g of the existing node (or of the new leader) before this expansion's updates
@@ -1375,12 +1441,13 @@ __global__ void __launch_bounds__(KT, (KT <= 256 ? 2 : 1)) kino_search_kernel(co
                 if (pos1 >= lo && pos1 <= hi) { in_union = true; break; }
               }
             }
-            if (in_union) s.b.inun[leader] = 1;
+            if (in_union) { s.b.inun[leader] = 1; rec.id = s.id[leader]; rec.hs = s.b.hs[leader] | EV_SETKEY; }
             s.b.imp[p] = in_union ? 2 : 1;
           } else {
             s.b.imp[p] = 0;
           }
         }
+        s.b.ev[e] = rec;
         if (event && s.b.topt[p] >= 0.0) my_ev = e;  // e grows with the trip count: the last one is this thread's maximum
       }
       my_ev = __reduce_max_sync(FULL, my_ev);
@@ -1392,52 +1459,65 @@ __global__ void __launch_bounds__(KT, (KT <= 256 ? 2 : 1)) kino_search_kernel(co
       // (through the staged ancestor closure: one push = one ballot) and the key mutations of nodes that are ancestors
       // of new leaves.  Everything else was resolved in U and is written back in D2. -------------------------------------
       if (warp == 0) {
+        const long long t_d0 = prof ? clock64() : 0;
         int pushed = 0, len = s.heap_len, batch_left = 0;
         Closure cl;
         cl.lo = cl.off = cl.lo_m1 = cl.off_m1 = cl.total = 0; cl.active = false;
+        ChainCache cc;
+        cc.e.f = 0.0; cc.e.id = 0; cc.e.hs = 0; cc.ix = 0;
+        const unsigned lm = (2u << lane) - 1u;
+        int nev = 0;  // the events, compacted (order kept)
         for (int cb = 0; cb < n2; cb += 32) {
           const bool in = cb + lane < n2;
-          const int p = in ? (int)s.list2[cb + lane] : 0;
-          const int st = in ? (int)s.state[p] : (int)ST_REJECT;
-          const bool cand = in && (st == ST_NEW || s.b.imp[p] == 2);
-          double c_f = 0.0;
-          uint32_t c_id = 0, c_hs = 0;
-          if (cand) {
-            c_f = s.b.f[p];
-            const int leader = (st == ST_NEW) ? p : ((st == ST_FOLLOW_CAND) ? (int)s.id[p] : p);
-            c_id = s.id[leader]; c_hs = s.b.hs[leader];
+          HeapSlot r;
+          r.f = 0.0; r.id = UAVMP_NONE; r.hs = 0;
+          if (in) r = s.b.ev[cb + lane];
+          const bool isev = r.id != UAVMP_NONE;
+          const unsigned m = __ballot_sync(FULL, isev);
+          if (isev) s.b.evc[nev + __popc(m & (lm >> 1))] = r;
+          nev += __popc(m);
+        }
+        __syncwarp();
+        int k = 0;
+        while (k < nev) {
+          HeapSlot ev = s.b.evc[k];
+          if (ev.hs & EV_SETKEY) {
+            const long long t0 = prof ? clock64() : 0;
+            if (cl.active) chain_writeback(s, cc);
+            heap_set_key_slow(s, H, table, ev.id, ev.hs & HS_MASK, ev.f, lane, cl);
+            if (cl.active && batch_left) chain_fill(s, cl, cc, len + 1, lane);
+            if (prof && lane == 0) s.ph[14] += (unsigned long long)(clock64() - t0);
+            k++;
+            continue;
           }
-          unsigned evm = __ballot_sync(FULL, cand);
-          while (evm) {
-            const int l = __ffs(evm) - 1;
-            evm &= evm - 1;
-            const int ste = __shfl_sync(FULL, st, l);
-            const double f = __shfl_sync(FULL, c_f, l);
-            const uint32_t nid = __shfl_sync(FULL, c_id, l), nhs = __shfl_sync(FULL, c_hs, l);
-            if (ste == ST_NEW) {
-              if (batch_left == 0) {
-                const long long t0 = prof ? clock64() : 0;
-                closure_flush(s, H, table, lane, cl);
-                batch_left = min(min(PUSH_BATCH, n_new - pushed), level_room(len));
-                closure_load(s, H, len, batch_left, lane, cl);
-                if (prof && lane == 0) s.ph[13] += (unsigned long long)(clock64() - t0);
-              }
-              closure_push(s, len + 1, f, nid, nhs, lane, cl);
-              len++;
-              pushed++;
-              batch_left--;
-            } else {
-              const long long t0 = prof ? clock64() : 0;
-              heap_set_key_slow(s, H, table, nid, nhs, f, lane, cl);
-              if (prof && lane == 0) s.ph[14] += (unsigned long long)(clock64() - t0);
-            }
+          if (batch_left == 0) {
+            const long long t0 = prof ? clock64() : 0;
+            if (cl.active) chain_writeback(s, cc);
+            closure_flush(s, H, table, lane, cl);
+            batch_left = min(min(PUSH_BATCH, n_new - pushed), level_room(len));
+            closure_load(s, H, len, batch_left, lane, cl);
+            chain_fill(s, cl, cc, len + 1, lane);
+            if (prof && lane == 0) s.ph[13] += (unsigned long long)(clock64() - t0);
+          }
+          for (;;) {  // a run of pushes inside one staged batch; the next record is fetched under the current push
+            k++;
+            HeapSlot nx;
+            nx.f = 0.0; nx.id = 0; nx.hs = EV_SETKEY;
+            if (k < nev) nx = s.b.evc[k];
+            chain_push(cc, ev.f, ev.id, ev.hs, lm);
+            len++; pushed++; batch_left--;
+            if (batch_left == 0 || (nx.hs & EV_SETKEY)) break;
+            chain_advance(s, cc, len + 1, lane);
+            ev = nx;
           }
         }
         {
           const long long t0 = prof ? clock64() : 0;
+          if (cl.active) chain_writeback(s, cc);
           closure_flush(s, H, table, lane, cl);
           if (prof && lane == 0) s.ph[13] += (unsigned long long)(clock64() - t0);
         }
+        if (prof && lane == 0) s.ph[10] += (unsigned long long)(clock64() - t_d0);  // diagnostics: the whole ordered replay
         if (lane == 0) {
           if (len > 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes + s.htop[1].id));  // the next pop's node record
           s.heap_len = len;

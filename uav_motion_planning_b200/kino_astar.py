@@ -104,7 +104,7 @@ class KinoAstar:
         self.ctx.check(self.lib.uavmp_kino_get_profile(self.ctx.h, _lib.ptr(ph), _lib.ptr(qc), 17 * B, C.byref(grid)))
         qphase = qc[B:].reshape(B, 16).copy()
         qc = qc[:B].copy()
-        names = ["pop", "shot_path", "tables_tile_grid", "cloud_ellipsoid", "dedup_probe_heuristic", "node_write", "heap_commit", "setup", "cloud_staging", "n_staged", "n_unstaged", "sum_npts", "sum_flagged_prims", "commit_closure_io", "commit_slow_updates", "commit_deferred_writes"]
+        names = ["pop", "shot_path", "tables_tile_grid", "cloud_ellipsoid", "dedup_probe_heuristic", "node_write", "heap_commit", "setup", "cloud_staging", "n_staged", "commit_replay", "sum_npts", "sum_flagged_prims", "commit_closure_io", "commit_slow_updates", "commit_deferred_writes"]
         return dict(phase_cycles=dict(zip(names, ph.tolist())), query_cycles=qc, query_phase=qphase, names=names, grid=grid.value)
 
     # -- GridMap::cloudCallback on the device (grid_map.cpp:733-785): only the cloud is uploaded -----------------
