@@ -46,7 +46,7 @@ WORKLOADS = {
             text="batch 4096 queries, 50x50x10 m random map @0.1 m, kino-A* + 8-seg 7th-order min-snap, per GPU",
             kino="launch-file params, collision_check_type 1 (grid + ellipsoid)"),
     3: dict(tag="configs[3]", batch=65536, map=(50.0, 50.0, 10.0), map_type=2, ctype=1, order=7, S=12, seg_time=1.0, Kc=2, margin=0.2,
-            strong=True,
+            strong=True, warm_batch=4096,
             text="batch 65536 queries, fix-wall map (two slabs, 0.5 m gap), kino-A* + 12-seg 7th-order min-snap with corridor box "
                  "constraints (2 samples per segment, box = segment path extent +- 0.2 m), sharded over the GPUs (strong scaling)",
             kino="launch-file params, collision_check_type 1 (grid + ellipsoid)"),
@@ -63,6 +63,7 @@ def workload_config(wl, B, n_gpus):
     return {"workload": f"{wl['tag']}: {wl['text']}", "batch_per_gpu": B, "global_batch": B * n_gpus,
             "map": "500x500x100 int8, " + ("fix_map_type 2 (wall)" if wl["map_type"] == 2 else "random_forest seed 1"), "kino": wl["kino"],
             "qp": f"order {wl['order']}, S {wl['S']}, T_i {wl['seg_time']}, OSQP eps 1e-3, 3 axes per plan{corr}",
+            "warmup_batch": wl.get("warm_batch"),
             "batches": "a different seeded query batch every step; steps may overlap in time (GPU: up to 6 batches in flight, "
                        "CPU: one work queue over all steps), every step's results are complete inside the timed region",
             "l2": "256 MiB flush write before every step; the per-step working set (>= 5 GB of search arenas + a different "
@@ -256,6 +257,11 @@ def run_gpu(args, rank, world_size, local_rank, wl):
         batches = [tuple(a[lo_q:hi_q] for a in bt) for bt in make_batches(world, wl["batch"], K + W, 0)]
     else:
         batches = make_batches(world, B, K + W, rank)
+    if wl.get("warm_batch") and not args.batch:
+        # the W warm-up steps of this configuration use a smaller batch (its full batch is minutes of work: wall-crossing queries
+        # exhaust the 100 000-node pool); the K timed steps are full size
+        wb = max(1, wl["warm_batch"] // world_size)
+        batches = [tuple(a[:wb] for a in bt) if i < W else bt for i, bt in enumerate(batches)]
     depth = planner.max_in_flight(ctx)
     lib_stream = torch.cuda.ExternalStream(ctx.stream, device=dev)  # the context's stream: device inputs are ordered after it
     side = torch.cuda.Stream(device=dev)                            # all-gathers run here, behind each batch's completion
@@ -305,7 +311,7 @@ def run_gpu(args, rank, world_size, local_rank, wl):
             else:
                 sp, sv, ep, ev = d_in[i]
                 o = ring[slot]
-            t = planner.plan_submit(ctx, B, sp.data_ptr(), sv.data_ptr(), ep.data_ptr(), ev.data_ptr(), o["status"].data_ptr(),
+            t = planner.plan_submit(ctx, int(sp.shape[0]), sp.data_ptr(), sv.data_ptr(), ep.data_ptr(), ev.data_ptr(), o["status"].data_ptr(),
                                     o["solved"].data_ptr(), o["coef"].data_ptr(), device_io=not host_io, options=opts)
             live.append(t)
             if world_size > 1:
@@ -480,7 +486,7 @@ def run_qp_sweep(args, rank, world_size, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4], help="BASELINE.json configs[N] (default 1: the metric's)")

@@ -73,12 +73,13 @@ static int host_qp_solve_warp_impl(int reversed, int order, int S, int Kc, int B
   QpPlanDev D;
   qp_plan_pack(*H, ints, dbls, off);
   qp_plan_bind(*H, off, ints.data(), dbls.data(), D);
+  D.Sidx = H->Sidx.data(); D.Sch = H->Sch.data();
   QpIo io;
   io.pos = pos; io.bv = bv; io.ba = ba; io.bj = bj ? bj : ba; io.T = T; io.lo = lo; io.hi = hi;
   io.coef = coef; io.solved = solved; io.status = status; io.iters = iters; io.B = B; io.stride = 0;
   for (int b = 0; b < B; b++) {
     std::vector<double> w((size_t)D.ws_warp, fpm::from_bits(0x7ff8000000000000ull));  // poisoned
-    if (reversed) rev::qp_warp_solve_one(D, io, *st, w.data(), b); else fwd::qp_warp_solve_one(D, io, *st, w.data(), b);
+    if (reversed) rev::qp_warp_solve_one(D, io, *st, w.data(), b, H->Sidx.data()); else fwd::qp_warp_solve_one(D, io, *st, w.data(), b, H->Sidx.data());
   }
   delete H;
   return 0;

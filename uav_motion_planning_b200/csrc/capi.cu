@@ -457,7 +457,9 @@ static int plan_issue(uavmp_ctx* ctx, PlanSlot& sl, int B, const double* sp, con
   }
   // in-kernel QP: how many warp workspaces fit in the shared memory the search gives up between two queries
   const int ws_bytes = plan->ws_warp * (int)sizeof(double);
-  int warps = std::min(8, kino_qp_overlay_bytes() / ws_bytes);
+  const int idx_bytes = plan->n_sidx * (int)sizeof(unsigned short);  // the solves' index block, staged once per round
+  int warps = plan->n_sidx > 0 ? std::min(8, (kino_qp_overlay_bytes() - idx_bytes) / ws_bytes) : 0;
+  if (warps < 0) warps = 0;
   if (getenv("UAVMP_NO_FUSE")) warps = 0;
   if (warps == 0) { r = ensure_bytes(ctx, (void**)&sl.d_qp_out, &sl.qp_out_bytes, nB * n * sizeof(double)); if (r) return r; }
 
@@ -489,7 +491,7 @@ static int plan_issue(uavmp_ctx* ctx, PlanSlot& sl, int B, const double* sp, con
     qp.time_alloc = opt.time_alloc; qp.step = ctx->kp.time_step_size; qp.Kc = Kc; qp.margin = opt.corridor_margin; qp.lo = lo; qp.hi = hi;
     qp.pos = pos; qp.bv = bv; qp.ba = ba; qp.bj = bj; qp.T = T;
     qp.coef = d_coef; qp.solved3 = d_solved3; qp.status3 = d_stat3; qp.iters3 = d_it3; qp.qp_solved = d_solved;
-    r = kino_launch_search(ctx, sl, B, d_sp, d_sv, d_ep, d_ev, true, false, &qp, plan, settings);
+    r = kino_launch_search(ctx, sl, B, d_sp, d_sv, d_ep, d_ev, true, ctx->profile_phases && &sl == &ctx->slots[0], &qp, plan, settings);
     if (r) return r;
     sl.launches_qp = 0;  // the QP runs inside the search kernel
   } else {

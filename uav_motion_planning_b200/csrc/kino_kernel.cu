@@ -116,7 +116,7 @@ struct SearchSmem {
   unsigned long long pop_hash;
   unsigned long long cnt[8];
   uint32_t cur_id, cur_parent, epoch;
-  int heap_len, use_num, n_pop, n1, n2, n_new, status, flag, q, trunc;
+  int heap_len, sift_len, use_num, n_pop, n1, n2, n_new, status, flag, q, trunc;
   int wsum[KT / 32];
   // ---- everything above is per-query scratch: between two queries the in-kernel QP overlays it with its workspaces.
   // ---- everything below survives a QP round.
@@ -613,6 +613,10 @@ __device__ __forceinline__ void qp_round(SearchSmem& s, unsigned char* smem_raw,
   const int warp = tid >> 5, lane = tid & 31;
   const int cnt = min(s.npend, qp.warps);
   __syncthreads();  // every thread has left the scratch area and has read npend
+  // the index block of the triangular solves (uint16), shared by the round's warps, behind their workspaces
+  unsigned short* sx = reinterpret_cast<unsigned short*>(reinterpret_cast<double*>(smem_raw) + (size_t)qp.warps * pl.ws_warp);
+  for (int i = tid; i < pl.n_sidx / 2; i += KT) reinterpret_cast<uint32_t*>(sx)[i] = reinterpret_cast<const uint32_t*>(pl.Sidx)[i];
+  __syncthreads();
   if (warp < cnt) {
     const int b = s.pend[s.npend - 1 - warp];
     const int q = b / 3, ax = b - 3 * q;
@@ -640,7 +644,7 @@ __device__ __forceinline__ void qp_round(SearchSmem& s, unsigned char* smem_raw,
     QpIo io;
     io.pos = qp.pos; io.bv = qp.bv; io.ba = qp.ba; io.bj = qp.bj; io.T = qp.T; io.lo = qp.lo; io.hi = qp.hi;
     io.coef = qp.coef; io.solved = qp.solved3; io.status = qp.status3; io.iters = qp.iters3; io.B = 3 * bt.B; io.stride = 0;
-    qp_warp_solve_one(pl, io, S, reinterpret_cast<double*>(smem_raw) + (size_t)warp * pl.ws_warp, b);
+    qp_warp_solve_one(pl, io, S, reinterpret_cast<double*>(smem_raw) + (size_t)warp * pl.ws_warp, b, sx);
     if (lane == 0 && !qp.solved3[b]) atomicAnd(qp.qp_solved + q, 0);
   }
   __syncthreads();
@@ -772,15 +776,15 @@ __global__ void __launch_bounds__(KT, (KT <= 256 ? 2 : 1)) kino_search_kernel(co
         if (len0 == 0) {
           if (lane == 0) s.status = UAVMP_NO_PATH_FOUND;  // open list exhausted (:270-271)
         } else {
-          HeapSlot top;
-          int len = len0;
-          // the popped node's record is only needed after the sift-down: lanes 16..24 fetch its nine words under it
+          // Only the IDENTITY of the popped node is needed to start the expansion: the top of the open list and its record
+          // (prefetched at the end of the previous commit).  The sift-down that restores the heap — a chain of dependent L2
+          // round trips — is deferred to the start of phase A0, where it runs on this warp under the TMA flight of the flags
+          // box and the other warps' table computation; nobody reads the open list before the classification (phase B).
+          const HeapSlot top = s.htop[1];
+          const int len = len0 - 1;
           unsigned long long nw = 0;
-          const uint32_t top_id = s.htop[1].id;
           if (lane >= 16 && lane < 16 + (int)(sizeof(KinoNode) / 8))
-            nw = reinterpret_cast<const unsigned long long*>(nodes + top_id)[lane - 16];
-          __syncwarp();
-          heap_pop_warp(s, H, table, len, top, lane);
+            nw = reinterpret_cast<const unsigned long long*>(nodes + top.id)[lane - 16];
           KinoNode nd;
           nd.px = __longlong_as_double((long long)__shfl_sync(FULL, nw, 16)); nd.py = __longlong_as_double((long long)__shfl_sync(FULL, nw, 17));
           nd.pz = __longlong_as_double((long long)__shfl_sync(FULL, nw, 18)); nd.vx = __longlong_as_double((long long)__shfl_sync(FULL, nw, 19));
@@ -789,6 +793,7 @@ __global__ void __launch_bounds__(KT, (KT <= 256 ? 2 : 1)) kino_search_kernel(co
           nd.parent = (uint32_t)(__shfl_sync(FULL, nw, 23) & 0xffffffffull);
           if (lane == 0) {
           s.heap_len = len;
+          s.sift_len = len0;
           nodes[top.id].closed = 1;
           table[top.hs].closed = 1;
           s.cur_id = top.id; s.cur_parent = nd.parent;
@@ -899,6 +904,12 @@ __global__ void __launch_bounds__(KT, (KT <= 256 ? 2 : 1)) kino_search_kernel(co
         if (s.status) break;
       }
 
+      // ---- the deferred half of the pop: std::pop_heap's sift-down (see the pop phase), concurrent with A0 ----------------
+      if (warp == 0) {
+        int len = s.sift_len;
+        HeapSlot top_unused;
+        heap_pop_warp(s, H, table, len, top_unused, lane);
+      }
       // ---- A0. separable tables: every checkpoint / end-state coordinate is (c + t v) + h u per axis, and u comes
       // from a tensor lattice, so there are only K * 3 * na distinct coordinates (StateTransit, :651-670) -----------
       if (warp == KT / 32 - 1) {
@@ -1526,27 +1537,30 @@ __global__ void __launch_bounds__(KT, (KT <= 256 ? 2 : 1)) kino_search_kernel(co
           s.cnt[3] += n1; s.cnt[4] += n_new; s.cnt[5] += s.n_upd; s.cnt[6] += n_new + s.n_upd;
         }
       }
-      __syncthreads();
-      const long long t_d2 = (prof && tid == 0) ? clock64() : 0;
-      // ---- D2. the recorded mutations, in parallel: node state, g in the hash slot, and the cached heap key ------
-      for (int e = tid; e < n1; e += KT) {
-        const int p = s.list1[e];
-        const uint8_t st = s.state[p];
-        if (st != ST_NEW && st != ST_OPEN_CAND && st != ST_OPEN_NOCAND) continue;  // leaders only
-        const int we = s.b.winm[p];
-        if (we < 0) continue;
-        const int w = s.list2[we];
-        const int a = w / (na * na), b = (w / na) % na, c = w % na;
-        KinoNode* nd = nodes + s.id[p];
-        nd->px = s.EX[0][a]; nd->py = s.EX[1][b]; nd->pz = s.EX[2][c];
-        nd->vx = s.EV[0][a]; nd->vy = s.EV[1][b]; nd->vz = s.EV[2][c];
-        const double g = s.cg + ginc_of(P, w);
-        nd->g = g; nd->parent = s.cur_id; nd->input = (uint16_t)w;
-        table[s.b.hs[p]].g = g;
-        if (st != ST_NEW && !s.b.inun[p]) hstore_key(s, H, (int)s.b.hpos[p] + 1, s.b.f[w]);
+      else {
+        // ---- D2 (warps 1 .. 7, concurrently with the ordered replay on warp 0): the recorded mutations that cannot move
+        // during the expansion — node state, g in the hash slot, and the cached heap key of nodes that are NOT ancestors of a
+        // new leaf (the replay never reads or writes their slots) ------------------------------------------------------------
+        const long long t_d2 = (prof && tid == 32) ? clock64() : 0;
+        for (int e = tid - 32; e < n1; e += KT - 32) {
+          const int p = s.list1[e];
+          const uint8_t st = s.state[p];
+          if (st != ST_NEW && st != ST_OPEN_CAND && st != ST_OPEN_NOCAND) continue;  // leaders only
+          const int we = s.b.winm[p];
+          if (we < 0) continue;
+          const int w = s.list2[we];
+          const int a = w / (na * na), b = (w / na) % na, c = w % na;
+          KinoNode* nd = nodes + s.id[p];
+          nd->px = s.EX[0][a]; nd->py = s.EX[1][b]; nd->pz = s.EX[2][c];
+          nd->vx = s.EV[0][a]; nd->vy = s.EV[1][b]; nd->vz = s.EV[2][c];
+          const double g = s.cg + ginc_of(P, w);
+          nd->g = g; nd->parent = s.cur_id; nd->input = (uint16_t)w;
+          table[s.b.hs[p]].g = g;
+          if (st != ST_NEW && !s.b.inun[p]) hstore_key(s, H, (int)s.b.hpos[p] + 1, s.b.f[w]);
+        }
+        if (prof && tid == 32) s.ph[15] += (unsigned long long)(clock64() - t_d2);
       }
       __syncthreads();
-      if (prof && tid == 0) s.ph[15] += (unsigned long long)(clock64() - t_d2);
       PH_MARK(6);
     }  // main loop
 

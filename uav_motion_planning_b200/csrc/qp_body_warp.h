@@ -29,6 +29,7 @@ QPW_HD double qpw_max(double v) {
   return v;
 }
 QPW_HD int qpw_any(int v) { return __any_sync(0xffffffffu, v); }
+#define QPW_DEVICE_WARP 1
 #else
 #define QPW_HD static inline
 #define QPW_LANE 0
@@ -106,34 +107,125 @@ QPW_HD int qw_factor(const QpPlanDev& pl, double* w, double sigma) {
   return positive;
 }
 
-// xz <- K^-1 xz (QDLDL_solve between the two permutations)
-QPW_HD void qw_kkt_solve(const QpPlanDev& pl, double* w) {
+// xz <- K^-1 xz (QDLDL_solve between the two permutations).  `sx` = the plan's uint16 index block (pl.sx_* offsets), staged in
+// shared memory by the kernels.  Both triangular solves run level by level with one row / column per lane:
+//   forward  (QDLDL_Lsolve: for i: for j in col i: x[Li[j]] -= Lx[j] * x[i]): row r receives its subtractions in the order of
+//            increasing column i, each as x[r] = x[r] - Lx * x[i] — exactly the sequence of the column-oriented loop, so the row
+//            form below performs the same operations on the same values (x[i] is final once every row of the levels before it
+//            is done);
+//   backward (QDLDL_Ltsolve: for i = N-1..0: for j in col i: x[i] -= Lx[j] * x[Li[j]]): column i's own loop.
+// The dots stay sequential per lane (summation order is part of the contract); their loads are hoisted four entries ahead of
+// the dependent subtract chain.
+QPW_HD void qw_tri_dot(const double* w_lx, const double* w_bp, const unsigned short* ix_a, const unsigned short* ix_b, int p0, int p1,
+                       double& val) {
+  int p = p0;
+  for (; p + 4 <= p1; p += 4) {
+    const double a0 = w_lx[ix_a ? ix_a[p] : p], a1 = w_lx[ix_a ? ix_a[p + 1] : p + 1], a2 = w_lx[ix_a ? ix_a[p + 2] : p + 2],
+                 a3 = w_lx[ix_a ? ix_a[p + 3] : p + 3];
+    const double b0 = w_bp[ix_b[p]], b1 = w_bp[ix_b[p + 1]], b2 = w_bp[ix_b[p + 2]], b3 = w_bp[ix_b[p + 3]];
+    val = val - a0 * b0; val = val - a1 * b1; val = val - a2 * b2; val = val - a3 * b3;
+  }
+  for (; p < p1; p++) val = val - w_lx[ix_a ? ix_a[p] : p] * w_bp[ix_b[p]];
+}
+// One triangular solve from the lane schedule (qp_symbolic.cpp: QpPlanHost::Sch).  A chunk holds the rows (columns) of one
+// dependency level: every lane forms ONE product Lx * x (all of a level's products in a single step), then each row's leader lane
+// subtracts its row's products in their sequential order, pulling them from the lanes to its right with shuffles — the summation
+// order per element is the reference's (QDLDL_Lsolve / QDLDL_Ltsolve), only the loads and multiplications run side by side.
+// (The in-lane loops of the first version cost ~15 dependent instructions per L entry on a warp that had two or three rows to
+// work on: 85 % of the kernel, profiles/r02_reading.md.)  The schedule is read from global memory one chunk ahead.
+#if defined(QPW_DEVICE_WARP)
+QPW_HD void qw_tri_sched(const unsigned int* sch, int c0, int c1, const double* lx, double* bp) {
+  const int lane = QPW_LANE;
+  uint2 rec = __ldg(reinterpret_cast<const uint2*>(sch) + (size_t)c0 * 32 + lane);
+  for (int c = c0; c < c1; c++) {
+    uint2 nxt = rec;
+    if (c + 1 < c1) nxt = __ldg(reinterpret_cast<const uint2*>(sch) + (size_t)(c + 1) * 32 + lane);
+    const unsigned elx = rec.x & 0xffffu, esrc = rec.x >> 16, row = rec.y & 0xffffu;
+    const int len = (int)((rec.y >> 16) & 0xffu), maxlen = (int)(rec.y >> 24);
+    double prod = 0.0;
+    if (elx != 0xffffu) prod = lx[elx] * bp[esrc];
+    double val = 0.0;
+    if (len) val = bp[row];
+    int k = 0;
+    for (; k + 4 <= maxlen; k += 4) {
+      const double p0 = __shfl_down_sync(0xffffffffu, prod, k), p1 = __shfl_down_sync(0xffffffffu, prod, k + 1),
+                   p2 = __shfl_down_sync(0xffffffffu, prod, k + 2), p3 = __shfl_down_sync(0xffffffffu, prod, k + 3);
+      if (k < len) val = val - p0;
+      if (k + 1 < len) val = val - p1;
+      if (k + 2 < len) val = val - p2;
+      if (k + 3 < len) val = val - p3;
+    }
+    for (; k < maxlen; k++) {
+      const double p0 = __shfl_down_sync(0xffffffffu, prod, k);
+      if (k < len) val = val - p0;
+    }
+    if (len) bp[row] = val;
+    QPW_SYNC();
+    rec = nxt;
+  }
+}
+#else
+QPW_HD void qw_tri_sched(const unsigned int* sch, int c0, int c1, const double* lx, double* bp) {  // the 32 lanes, one after the other
+  for (int c = c0; c < c1; c++) {
+    const unsigned int* rec = sch + (size_t)c * 64;
+    double prod[32], out[32];
+    for (int l = 0; l < 32; l++) {
+      const unsigned elx = rec[2 * l] & 0xffffu, esrc = rec[2 * l] >> 16;
+      prod[l] = (elx != 0xffffu) ? lx[elx] * bp[esrc] : 0.0;
+    }
+#if defined(QPW_REVERSED)
+    for (int l = 31; l >= 0; l--) {
+#else
+    for (int l = 0; l < 32; l++) {
+#endif
+      const int len = (int)((rec[2 * l + 1] >> 16) & 0xffu);
+      if (!len) continue;
+      double val = bp[rec[2 * l + 1] & 0xffffu];
+      for (int k = 0; k < len; k++) val = val - prod[l + k];
+      out[l] = val;
+    }
+    for (int l = 0; l < 32; l++) if ((rec[2 * l + 1] >> 16) & 0xffu) bp[rec[2 * l + 1] & 0xffffu] = out[l];
+  }
+}
+#endif
+
+QPW_HD void qw_kkt_solve(const QpPlanDev& pl, double* w, const unsigned short* sx) {
   const int N = pl.N;
-  QPW_PFOR(j, 0, N) WW(pl.o_bp, j) = WW(pl.o_xz, QPW_LDG(pl.perm + j));
+  const unsigned short *perm = sx + pl.sx_perm, *Lrp = sx + pl.sx_Lrp, *Lrc = sx + pl.sx_Lrc, *Lrx = sx + pl.sx_Lrx,
+                       *LevFP = sx + pl.sx_LevFP, *LevFR = sx + pl.sx_LevFR, *Lp = sx + pl.sx_Lp, *Li = sx + pl.sx_Li,
+                       *LevP = sx + pl.sx_LevP, *LevC = sx + pl.sx_LevC;
+  double* bp = w + pl.o_bp;
+  const double* lx = w + pl.o_Lx;
+  QPW_PFOR(j, 0, N) bp[j] = WW(pl.o_xz, perm[j]);
   QPW_SYNC();
-  for (int i = 0; i < N; i++) {  // forward: column i scatters into distinct rows, one entry per lane
-    const int j0 = QPW_LDG(pl.Lp + i), j1 = QPW_LDG(pl.Lp + i + 1);
-    if (j1 == j0) continue;
-    const double val = WW(pl.o_bp, i);
+  if (pl.sch_n > 0) {
+    qw_tri_sched(pl.Sch, 0, pl.sch_nf, lx, bp);
+    QPW_PFOR(i, 0, N) bp[i] = bp[i] * WW(pl.o_Ddinv, i);
     QPW_SYNC();
-    QPW_PFOR(j, j0, j1) {
-      const int r = QPW_LDG(pl.Li + j);
-      WW(pl.o_bp, r) = WW(pl.o_bp, r) - WW(pl.o_Lx, j) * val;
+    qw_tri_sched(pl.Sch, pl.sch_nf, pl.sch_n, lx, bp);
+  } else {  // a row with more than 32 entries: level by level with one row / column per lane
+    for (int lv = 0; lv < pl.nlevf; lv++) {
+      QPW_PFOR(ri, LevFP[lv], LevFP[lv + 1]) {
+        const int r = LevFR[ri];
+        double val = bp[r];
+        qw_tri_dot(lx, bp, Lrx, Lrc, Lrp[r], Lrp[r + 1], val);
+        bp[r] = val;
+      }
+      QPW_SYNC();
     }
+    QPW_PFOR(i, 0, N) bp[i] = bp[i] * WW(pl.o_Ddinv, i);
     QPW_SYNC();
-  }
-  QPW_PFOR(i, 0, N) WW(pl.o_bp, i) = WW(pl.o_bp, i) * WW(pl.o_Ddinv, i);
-  QPW_SYNC();
-  for (int lv = 0; lv < pl.nlev; lv++) {  // backward: the columns of one level only read finished entries
-    QPW_PFOR(ci, QPW_LDG(pl.LevP + lv), QPW_LDG(pl.LevP + lv + 1)) {
-      const int i = QPW_LDG(pl.LevC + ci);
-      double val = WW(pl.o_bp, i);
-      for (int j = QPW_LDG(pl.Lp + i); j < QPW_LDG(pl.Lp + i + 1); j++) val -= WW(pl.o_Lx, j) * WW(pl.o_bp, QPW_LDG(pl.Li + j));
-      WW(pl.o_bp, i) = val;
+    for (int lv = 0; lv < pl.nlev; lv++) {
+      QPW_PFOR(ci, LevP[lv], LevP[lv + 1]) {
+        const int i = LevC[ci];
+        double val = bp[i];
+        qw_tri_dot(lx, bp, nullptr, Li, Lp[i], Lp[i + 1], val);
+        bp[i] = val;
+      }
+      QPW_SYNC();
     }
-    QPW_SYNC();
   }
-  QPW_PFOR(j, 0, N) WW(pl.o_xz, QPW_LDG(pl.perm + j)) = WW(pl.o_bp, j);
+  QPW_PFOR(j, 0, N) WW(pl.o_xz, perm[j]) = bp[j];
   QPW_SYNC();
 }
 
@@ -282,7 +374,7 @@ QPW_HD void qw_set_rho(const QpPlanDev& pl, double* w, double rho_) {
 }
 
 // one problem per warp: assembly -> osqp_setup -> osqp_solve -> store_solution.  `w` = this warp's workspace (pl.ws_warp doubles)
-QPW_HD void qp_warp_solve_one(const QpPlanDev& pl, const QpIo& io, const uavmp_osqp_settings& S, double* w, int b) {
+QPW_HD void qp_warp_solve_one(const QpPlanDev& pl, const QpIo& io, const uavmp_osqp_settings& S, double* w, int b, const unsigned short* sx) {
   const int n = pl.n, m = pl.m, Sg = pl.S;
   // ---- assembly (minimum_control.cpp:5-125) ----------------------------------------------------------------------------
   const double* T = io.T + (size_t)b * Sg;
@@ -384,7 +476,7 @@ QPW_HD void qp_warp_solve_one(const QpPlanDev& pl, const QpIo& io, const uavmp_o
         WW(pl.o_tm, i) = rhs;
       }
       QPW_SYNC();
-      qw_kkt_solve(pl, w);
+      qw_kkt_solve(pl, w, sx);
       QPW_PFOR(i, 0, n) {  // update_x
         const double xp = WW(pl.o_xprev, i);
         const double xn = alpha * WW(pl.o_xz, i) + one_m_alpha * xp;
@@ -460,6 +552,7 @@ QPW_HD void qp_warp_solve_one(const QpPlanDev& pl, const QpIo& io, const uavmp_o
 #undef QPW_SYNC
 #undef QPW_LDG
 #undef QPW_LANE0
+#undef QPW_DEVICE_WARP
 #undef QW_INFTY
 #undef QW_MIN_SCALING
 #undef QW_MAX_SCALING

@@ -40,6 +40,8 @@ struct QpPlan {
   QpPlanDev dev;
   int* d_ints = nullptr;
   double* d_dbls = nullptr;
+  unsigned short* d_sidx = nullptr;
+  unsigned int* d_sch = nullptr;
 };
 
 namespace {
@@ -54,10 +56,14 @@ __global__ void __launch_bounds__(QP_TPB) qp_solve_kernel(QpPlanDev pl, QpIo io,
 // ---- K2w: one warp per problem, workspace in shared memory (qp_body_warp.h) ------------------------------------------------------
 __global__ void qp_solve_warp_kernel(QpPlanDev pl, QpIo io, uavmp_osqp_settings S, int warps_per_cta) {
   extern __shared__ __align__(16) double qpw_sm[];
+  // the index block of the triangular solves, shared by the CTA's warps, behind their workspaces
+  unsigned short* sx = reinterpret_cast<unsigned short*>(qpw_sm + (size_t)warps_per_cta * pl.ws_warp);
+  for (int i = threadIdx.x; i < pl.n_sidx / 2; i += blockDim.x) reinterpret_cast<uint32_t*>(sx)[i] = reinterpret_cast<const uint32_t*>(pl.Sidx)[i];
+  __syncthreads();
   const int warp = threadIdx.x >> 5;
   const int b = blockIdx.x * warps_per_cta + warp;
   if (b >= io.B) return;  // whole warps leave together
-  qp_warp_solve_one(pl, io, S, qpw_sm + (size_t)warp * pl.ws_warp, b);
+  qp_warp_solve_one(pl, io, S, qpw_sm + (size_t)warp * pl.ws_warp, b, sx);
 }
 
 // warps per CTA of the warp-per-problem kernels: as many problems as ~100 KB of shared memory hold (2 CTAs / SM); 0 = does not fit
@@ -68,8 +74,9 @@ static int qpw_warps_per_cta(const QpPlanDev& pl, int B) {
   // on wall time.
   if (B > 6000 && !getenv("UAVMP_QP_WARP")) return 0;
   const size_t per = (size_t)pl.ws_warp * sizeof(double);
-  if (per > 200 * 1024) return 0;
-  int w = (int)((100 * 1024) / per);
+  const size_t idx = (size_t)pl.n_sidx * sizeof(unsigned short);
+  if (pl.n_sidx == 0 || per + idx > 200 * 1024) return 0;
+  int w = (int)((100 * 1024 - idx) / per);
   if (w < 1) w = 1;
   if (w > 8) w = 8;
   return w;
@@ -143,8 +150,18 @@ static QpPlan* get_plan(uavmp_ctx* ctx, int order, int S, int Kc) {
   if (cudaMalloc(&p->d_dbls, dbl.size() * sizeof(double)) != cudaSuccess) return nullptr;
   cudaMemcpyAsync(p->d_ints, ints.data(), ints.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
   cudaMemcpyAsync(p->d_dbls, dbl.data(), dbl.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  if (!H.Sidx.empty()) {
+    if (cudaMalloc(&p->d_sidx, H.Sidx.size() * sizeof(unsigned short)) != cudaSuccess) return nullptr;
+    cudaMemcpyAsync(p->d_sidx, H.Sidx.data(), H.Sidx.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, ctx->stream);
+  }
+  if (!H.Sch.empty()) {
+    if (cudaMalloc(&p->d_sch, H.Sch.size() * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+    cudaMemcpyAsync(p->d_sch, H.Sch.data(), H.Sch.size() * sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->stream);
+  }
   cudaStreamSynchronize(ctx->stream);
   qp_plan_bind(H, off, p->d_ints, p->d_dbls, p->dev);
+  p->dev.Sidx = p->d_sidx;
+  p->dev.Sch = p->d_sch;
   ctx->qp_plans.push_back(p);
   return p;
 }
@@ -153,6 +170,8 @@ void qp_free_plans(uavmp_ctx* ctx) {
   for (QpPlan* p : ctx->qp_plans) {
     if (p->d_ints) cudaFree(p->d_ints);
     if (p->d_dbls) cudaFree(p->d_dbls);
+    if (p->d_sidx) cudaFree(p->d_sidx);
+    if (p->d_sch) cudaFree(p->d_sch);
     delete p->host;
     delete p;
   }
@@ -190,7 +209,7 @@ int qp_solve_batch_dev(uavmp_ctx* ctx, cudaStream_t stream, QpScratch& scr, int*
   if (launches) *launches = 1;
   if (const int wpc = qpw_warps_per_cta(p->dev, B)) {
     // one warp per problem, everything in shared memory: no global workspace at all
-    const size_t smem = (size_t)wpc * p->dev.ws_warp * sizeof(double);
+    const size_t smem = (size_t)wpc * p->dev.ws_warp * sizeof(double) + (size_t)p->dev.n_sidx * sizeof(unsigned short);
     if (smem > 48 * 1024) cudaFuncSetAttribute(qp_solve_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     qp_solve_warp_kernel<<<(B + wpc - 1) / wpc, 32 * wpc, smem, stream>>>(p->dev, io, *st, wpc);
     UAVMP_CUDA(ctx, cudaGetLastError());

@@ -20,6 +20,13 @@ struct QpPlanHost {
   std::vector<int> Psp, Psa, Psv;                                       // per element i of P*v: (slot in Px, index into v) in the CSC loop's order
   std::vector<int> LevP, LevC; int nlev = 0;                            // L' solve: columns with entries grouped by elimination-tree level
   std::vector<int> Ltpos, LtR, LtEnd;                                   // L in the L' solve's consumption order: slot of L entry j, row index per slot, end slot per processed column
+  // warp-per-problem triangular solves: L by rows (entries of a row by increasing column = the order the column-oriented
+  // QDLDL_Lsolve subtracts them from that row), rows grouped by dependency level; all of it packed as uint16 in `Sidx`
+  std::vector<int> Lrp, Lrc, Lrx, LevFP, LevFR; int nlevf = 0;
+  // lane schedule of the triangular solves (see qw_tri_sched): per chunk 32 records {lx slot:16 | source index:16, row:16 | len:8 | maxlen:8};
+  // chunks [0, sch_nf) = forward solve, [sch_nf, sch_n) = backward solve; empty when a row has more than 32 entries
+  std::vector<unsigned int> Sch; int sch_nf = 0, sch_n = 0;
+  std::vector<unsigned short> Sidx; int sx_Lrp = 0, sx_Lrc = 0, sx_Lrx = 0, sx_LevFP = 0, sx_LevFR = 0, sx_Lp = 0, sx_Li = 0, sx_LevP = 0, sx_LevC = 0, sx_perm = 0;
 };
 
 // Kc > 0 appends Kc corridor rows per segment (an extension): lo <= p_s(phi_j T_s) <= hi at phi_j = (j + 1) / (Kc + 1)
@@ -34,6 +41,9 @@ struct QpPlanDev {
   const int *l_src, *u_src, *perm, *Kp, *Ki, *Kkind, *Kidx, *Lp, *Li, *Rp, *Rc, *Rpos, *Ltpos, *LtR, *LtEnd;
   const int *Arp, *Arj, *Arx, *Psp, *Psa, *Psv, *LevP, *LevC;
   int nlev, ws_warp;  // ws_warp: doubles of the one-warp-per-problem workspace (everything except the LxT copy)
+  // the index block of the warp-per-problem triangular solves (uint16, `n_sidx` entries; staged in shared memory by the kernels)
+  const unsigned int* Sch; int sch_nf, sch_n;  // lane schedule of the triangular solves (global memory, 2 words per lane per chunk)
+  const unsigned short* Sidx; int n_sidx, nlevf, sx_Lrp, sx_Lrc, sx_Lrx, sx_LevFP, sx_LevFR, sx_Lp, sx_Li, sx_LevP, sx_LevC, sx_perm;
   // workspace layout (offsets in doubles)
   int o_Px, o_Ax, o_q, o_l, o_u, o_D, o_Dinv, o_E, o_Einv, o_rho, o_rhoinv, o_Lx, o_LxT, o_Dd, o_Ddinv, o_yw, o_x, o_xprev,
       o_dx, o_Pxv, o_Aty, o_z, o_zprev, o_y, o_dy, o_Axv, o_xz, o_bp, o_tn, o_tm, ws_doubles;
@@ -43,6 +53,7 @@ struct QpPlanDev {
 struct QpPlanOffsets { size_t Pp, Pi, P_seg, P_pow, Ap, Ai, A_seg, A_pow, l_src, u_src, perm, Kp, Ki, Kkind, Kidx, Lp, Li, Rp, Rc, Rpos, Ltpos, LtR, LtEnd, Arp, Arj, Arx, Psp, Psa, Psv, LevP, LevC, A_coef; };
 void qp_plan_pack(const QpPlanHost& H, std::vector<int>& ints, std::vector<double>& dbls, QpPlanOffsets& off);
 void qp_plan_bind(const QpPlanHost& H, const QpPlanOffsets& off, const int* ints, const double* dbls, QpPlanDev& D);
+// D.Sidx / D.Sch are NOT set by qp_plan_bind: point them at copies of H.Sidx / H.Sch in the memory space the solver runs in
 
 // per-batch I/O of the solve kernel
 struct QpIo {

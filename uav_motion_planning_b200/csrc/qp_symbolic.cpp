@@ -280,6 +280,83 @@ QpPlanHost* qp_plan_build(int order, int S, int Kc) {
       P.LevP[l] = (int)P.LevC.size();
     }
   }
+  {  // L by rows + forward-solve levels + the packed uint16 index block of the warp-per-problem solves
+    const int nnzL = P.nnzL;
+    P.Lrp.assign(N + 1, 0);
+    for (int j = 0; j < nnzL; j++) P.Lrp[P.Li[j] + 1]++;
+    for (int r = 0; r < N; r++) P.Lrp[r + 1] += P.Lrp[r];
+    P.Lrc.assign(nnzL, 0); P.Lrx.assign(nnzL, 0);
+    std::vector<int> nxt(P.Lrp.begin(), P.Lrp.end() - 1);
+    for (int i = 0; i < N; i++)  // columns ascending: every row receives its entries by increasing column
+      for (int j = P.Lp[i]; j < P.Lp[i + 1]; j++) { const int r = P.Li[j]; P.Lrc[nxt[r]] = i; P.Lrx[nxt[r]] = j; nxt[r]++; }
+    std::vector<int> lev(N, 0);
+    int mx = 0;
+    for (int r = 0; r < N; r++) {  // row r needs x[i] for every column i < r it has an entry in
+      int l = 0;
+      for (int p = P.Lrp[r]; p < P.Lrp[r + 1]; p++) l = std::max(l, lev[P.Lrc[p]] + 1);
+      lev[r] = l; mx = std::max(mx, l);
+    }
+    P.nlevf = mx;  // level 0 (rows without entries) needs no work
+    P.LevFP.assign(mx + 1, 0);
+    P.LevFR.clear();
+    for (int l = 1; l <= mx; l++) {
+      for (int r = 0; r < N; r++) if (lev[r] == l) P.LevFR.push_back(r);
+      P.LevFP[l] = (int)P.LevFR.size();
+    }
+    auto put = [&](const std::vector<int>& v) { int at = (int)P.Sidx.size(); for (int x : v) P.Sidx.push_back((unsigned short)x); return at; };
+    P.Sidx.clear();
+    if (N < 65536 && nnzL < 65536) {
+      P.sx_Lrp = put(P.Lrp); P.sx_Lrc = put(P.Lrc); P.sx_Lrx = put(P.Lrx); P.sx_LevFP = put(P.LevFP); P.sx_LevFR = put(P.LevFR);
+      P.sx_Lp = put(P.Lp); P.sx_Li = put(P.Li); P.sx_LevP = put(P.LevP); P.sx_LevC = put(P.LevC); P.sx_perm = put(P.perm);
+      if (P.Sidx.size() & 1) P.Sidx.push_back(0);
+    }
+    // ---- lane schedule: the rows (forward) / columns (backward) of one dependency level are packed into chunks of 32 lanes, a
+    // row's entries on consecutive lanes starting at its leader lane, in the order the sequential solve consumes them
+    struct Item { int dst; std::vector<std::pair<int, int>> ent; };  // destination index, (Lx slot, source index) in order
+    auto pack = [&](const std::vector<std::vector<Item>>& levels) {
+      for (const auto& lv : levels) {
+        std::vector<unsigned int> rec(64, 0);
+        int used = 0;
+        auto flush = [&]() {
+          int mx = 0;
+          for (int l = 0; l < 32; l++) mx = std::max(mx, (int)((rec[2 * l + 1] >> 16) & 0xff));
+          for (int l = 0; l < 32; l++) rec[2 * l + 1] |= (unsigned)mx << 24;
+          P.Sch.insert(P.Sch.end(), rec.begin(), rec.end());
+          rec.assign(64, 0); used = 0;
+        };
+        for (int l = 0; l < 32; l++) { rec[2 * l] = 0xffffu; }
+        for (const Item& it : lv) {
+          const int len = (int)it.ent.size();
+          if (len == 0) continue;
+          if (used + len > 32) { flush(); for (int l = 0; l < 32; l++) rec[2 * l] = 0xffffu; }
+          for (int k = 0; k < len; k++) rec[2 * (used + k)] = (unsigned)it.ent[k].first | ((unsigned)it.ent[k].second << 16);
+          rec[2 * used + 1] = (unsigned)it.dst | ((unsigned)len << 16);
+          used += len;
+        }
+        if (used) flush();
+      }
+    };
+    bool ok = N < 65535 && nnzL < 65535;
+    for (int r = 0; r < N && ok; r++) if (P.Lrp[r + 1] - P.Lrp[r] > 32 || P.Lp[r + 1] - P.Lp[r] > 32) ok = false;
+    P.Sch.clear(); P.sch_nf = P.sch_n = 0;
+    if (ok) {
+      std::vector<std::vector<Item>> fl(P.nlevf), bl(P.nlev);
+      for (int l = 0; l < P.nlevf; l++)
+        for (int q = P.LevFP[l]; q < P.LevFP[l + 1]; q++) {
+          Item it; it.dst = P.LevFR[q];
+          for (int e = P.Lrp[it.dst]; e < P.Lrp[it.dst + 1]; e++) it.ent.push_back({P.Lrx[e], P.Lrc[e]});
+          fl[l].push_back(it);
+        }
+      for (int l = 0; l < P.nlev; l++)
+        for (int q = P.LevP[l]; q < P.LevP[l + 1]; q++) {
+          Item it; it.dst = P.LevC[q];
+          for (int j = P.Lp[it.dst]; j < P.Lp[it.dst + 1]; j++) it.ent.push_back({j, P.Li[j]});
+          bl[l].push_back(it);
+        }
+      pack(fl); P.sch_nf = (int)P.Sch.size() / 64;
+      pack(bl); P.sch_n = (int)P.Sch.size() / 64;
+    }
+  }
   return pl;
 }
 
@@ -309,6 +386,10 @@ void qp_plan_bind(const QpPlanHost& H, const QpPlanOffsets& o, const int* I, con
   D.Ltpos = I + o.Ltpos; D.LtR = I + o.LtR; D.LtEnd = I + o.LtEnd;
   D.Arp = I + o.Arp; D.Arj = I + o.Arj; D.Arx = I + o.Arx; D.Psp = I + o.Psp; D.Psa = I + o.Psa; D.Psv = I + o.Psv;
   D.LevP = I + o.LevP; D.LevC = I + o.LevC; D.nlev = H.nlev;
+  D.Sidx = nullptr; D.n_sidx = (int)H.Sidx.size(); D.nlevf = H.nlevf;
+  D.Sch = nullptr; D.sch_nf = H.sch_nf; D.sch_n = H.sch_n;
+  D.sx_Lrp = H.sx_Lrp; D.sx_Lrc = H.sx_Lrc; D.sx_Lrx = H.sx_Lrx; D.sx_LevFP = H.sx_LevFP; D.sx_LevFR = H.sx_LevFR;
+  D.sx_Lp = H.sx_Lp; D.sx_Li = H.sx_Li; D.sx_LevP = H.sx_LevP; D.sx_LevC = H.sx_LevC; D.sx_perm = H.sx_perm;
   // workspace layout (offsets in doubles; element e of problem b lives at ws[e * stride + b])
   int at = 0;
   auto take = [&](int len) { int r = at; at += len; return r; };
