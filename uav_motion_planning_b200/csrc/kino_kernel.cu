@@ -1373,6 +1373,20 @@ __global__ void __launch_bounds__(KT, (KT <= 256 ? 2 : 1)) kino_search_kernel(co
         __syncthreads();
         break;
       }
+      // The ordered replay (phase D) will stage the ancestors of the new leaves l0+1 .. l0+n_new: pull their sectors towards L2 now,
+      // under the heuristic.  The arenas' open lists (1.6 MB each, 296 of them) do not stay in L2 between expansions.
+      if (n_new > 0) {
+        const int l0 = s.heap_len, m = min(n_new, PUSH_BATCH);
+        for (int t = tid; t < m; t += KT) {  // levels 1 .. 5 of every leaf (32 B sectors: two slots each)
+          const int leaf = l0 + 1 + t;
+#pragma unroll
+          for (int d = 1; d <= 5; d++) if ((leaf >> d) >= HTOP) asm volatile("prefetch.global.L2 [%0];" ::"l"(H + (leaf >> d)));
+        }
+        if (tid < 32 && ((l0 + 1) >> (6 + tid)) >= HTOP) {  // the levels above are shared by (almost) all leaves of the batch
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(H + ((l0 + 1) >> (6 + tid))));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(H + ((l0 + m) >> (6 + tid))));
+        }
+      }
       // ---- B3. heuristic for every candidate (:232,:259) ----------------------------------------------
       for (int e = tid; e < n2; e += KT) {
         const int p = s.list2[e];

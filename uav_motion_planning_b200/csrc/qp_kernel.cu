@@ -66,20 +66,18 @@ __global__ void qp_solve_warp_kernel(QpPlanDev pl, QpIo io, uavmp_osqp_settings 
   qp_warp_solve_one(pl, io, S, qpw_sm + (size_t)warp * pl.ws_warp, b, sx);
 }
 
-// warps per CTA of the warp-per-problem kernels: as many problems as ~100 KB of shared memory hold (2 CTAs / SM); 0 = does not fit
+// warps per CTA of the warp-per-problem kernel: whatever keeps the most problems resident per SM — one big CTA (up to 227 KB of
+// shared memory) or two of up to 113 KB; 0 = a problem's workspace does not fit (or UAVMP_QP_THREAD asks for the thread kernel)
 static int qpw_warps_per_cta(const QpPlanDev& pl, int B) {
   if (getenv("UAVMP_QP_THREAD")) return 0;
-  // Measured on B200 (order 7, S 8): a problem takes ~7.6 ms on a warp and ~50 ms on a thread, but 12 288 threads run at once
-  // while only ~1 200 warps do (shared memory).  A stand-alone batch takes the warp kernel while it is small enough to win
-  // on wall time.
-  if (B > 6000 && !getenv("UAVMP_QP_WARP")) return 0;
+  (void)B;
   const size_t per = (size_t)pl.ws_warp * sizeof(double);
   const size_t idx = (size_t)pl.n_sidx * sizeof(unsigned short);
-  if (pl.n_sidx == 0 || per + idx > 200 * 1024) return 0;
-  int w = (int)((100 * 1024 - idx) / per);
-  if (w < 1) w = 1;
-  if (w > 8) w = 8;
-  return w;
+  if (pl.n_sidx == 0 || per + idx > 226 * 1024) return 0;
+  int w1 = (int)((226 * 1024 - idx) / per), w2 = (per + idx <= 112 * 1024) ? (int)((112 * 1024 - idx) / per) : 0;
+  if (w1 > 16) w1 = 16;
+  if (w2 > 8) w2 = 8;
+  return (2 * w2 >= w1) ? w2 : w1;
 }
 
 // ---- pipeline glue: waypoints from the searched paths, outputs back to per-plan layout --------------------------------------
