@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
-TAG = sys.argv[1] if len(sys.argv) > 1 else "r01"
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r02"
 
 
 def raw(rep):
@@ -64,8 +64,8 @@ def tobytes(u, v):
 
 
 def kernels():
-    reps = [("kino_search_kernel (4 096 queries: the bench workload, tools/ncu_search.py 4096)", "prof_search.ncu-rep"),
-            ("QP kernel (12 288 problems, order 7, S 8, tools/ncu_qp.py)", "prof_qp.ncu-rep")]
+    reps = [("kino_search_kernel (search + in-kernel QP of 4 096 queries: one launch of the bench workload, tools/ncu_plan.py 4096)", "prof_search.ncu-rep"),
+            ("qp_solve_warp_kernel (2 400 problems, order 7, S 8, tools/ncu_qp.py)", "prof_qp.ncu-rep")]
     with open(os.path.join(P, f"{TAG}_ncu_metrics.md"), "w") as f:
         f.write(f"# {TAG} — `ncu --set full --clock-control none --import-source on`, one launch per kernel (1 x B200)\n\n"
                 "`.ncu-rep` files stay in gpurun_out/ (scratch); read with `ncu -i … --page raw --csv`. Durations under ncu are not bench values.\n\n")
@@ -82,7 +82,7 @@ def kernels():
             if "kino" in name:
                 rd, wr = tobytes(*d["dram__bytes_read.sum"]), tobytes(*d["dram__bytes_write.sum"])
                 json.dump({"kino_search_kernel_dram_bytes_per_launch": rd + wr, "dram_bytes_read": rd, "dram_bytes_write": wr,
-                           "source": "ncu --set full --clock-control none -k regex:kino_search -c 1 python tools/ncu_search.py 4096",
+                           "source": "ncu --set full --clock-control none -k regex:kino_search -s 1 -c 1 python tools/ncu_plan.py 4096 (search + in-kernel QP)",
                            "gpu_time_duration_ms_under_ncu": float(d["gpu__time_duration.sum"][1]),
                            "l2_hit_pct": float(d["lts__t_sector_hit_rate.pct"][1])}, open(os.path.join(P, "traffic.json"), "w"), indent=1)
 
@@ -111,7 +111,9 @@ if __name__ == "__main__":
     kernels()
     phases()
     for src, dst in (("bench.log", f"{TAG}_bench_1gpu.json"), ("bench_ref.log", f"{TAG}_bench_reference_arm.json"),
-                     ("bench_2gpu.log", f"{TAG}_bench_2gpu.log")):
+                     ("bench_2gpu.log", f"{TAG}_bench_2gpu.json"), ("bench_c2.log", f"{TAG}_bench_config2.json"),
+                     ("bench_c3.log", f"{TAG}_bench_config3_1gpu.json"), ("bench_c3_2gpu.log", f"{TAG}_bench_config3_2gpu.json"),
+                     ("bench_c4.log", f"{TAG}_bench_config4.json"), ("prof_plan.log", f"{TAG}_prof_plan_B4096.json")):
         if os.path.exists(os.path.join(G, src)):
             shutil.copy(os.path.join(G, src), os.path.join(P, dst))
     print("profiles refreshed")
