@@ -134,30 +134,30 @@ QPW_HD void qw_tri_dot(const double* w_lx, const double* w_bp, const unsigned sh
 // (The in-lane loops of the first version cost ~15 dependent instructions per L entry on a warp that had two or three rows to
 // work on: 85 % of the kernel, profiles/r02_reading.md.)  The schedule is read from global memory one chunk ahead.
 #if defined(QPW_DEVICE_WARP)
-QPW_HD void qw_tri_sched(const unsigned int* sch, int c0, int c1, const double* lx, double* bp) {
+// pb: 64 doubles of this warp's workspace (16 B aligned).  Every lane parks its product there; a leader (always an even lane)
+// then reads its row's products two per load and subtracts them in order.  (Pulling them with shuffles cost two SHFL per
+// entry plus the lane arithmetic: the chain was 80 % of the solve's instructions.)
+QPW_HD void qw_tri_sched(const unsigned int* sch, int c0, int c1, const double* lx, double* bp, double* pb) {
   const int lane = QPW_LANE;
   uint2 rec = __ldg(reinterpret_cast<const uint2*>(sch) + (size_t)c0 * 32 + lane);
+  const double2* mine = reinterpret_cast<const double2*>(pb + (lane & ~1));
   for (int c = c0; c < c1; c++) {
     uint2 nxt = rec;
     if (c + 1 < c1) nxt = __ldg(reinterpret_cast<const uint2*>(sch) + (size_t)(c + 1) * 32 + lane);
     const unsigned elx = rec.x & 0xffffu, esrc = rec.x >> 16, row = rec.y & 0xffffu;
-    const int len = (int)((rec.y >> 16) & 0xffu), maxlen = (int)(rec.y >> 24);
+    const int len = (int)((rec.y >> 16) & 0xffu), maxlen = (int)(rec.y >> 24);  // maxlen: a multiple of 4
     double prod = 0.0;
     if (elx != 0xffffu) prod = lx[elx] * bp[esrc];
+    pb[lane] = prod;
     double val = 0.0;
     if (len) val = bp[row];
-    int k = 0;
-    for (; k + 4 <= maxlen; k += 4) {
-      const double p0 = __shfl_down_sync(0xffffffffu, prod, k), p1 = __shfl_down_sync(0xffffffffu, prod, k + 1),
-                   p2 = __shfl_down_sync(0xffffffffu, prod, k + 2), p3 = __shfl_down_sync(0xffffffffu, prod, k + 3);
-      if (k < len) val = val - p0;
-      if (k + 1 < len) val = val - p1;
-      if (k + 2 < len) val = val - p2;
-      if (k + 3 < len) val = val - p3;
-    }
-    for (; k < maxlen; k++) {
-      const double p0 = __shfl_down_sync(0xffffffffu, prod, k);
-      if (k < len) val = val - p0;
+    QPW_SYNC();
+    for (int k = 0; k < maxlen; k += 4) {
+      const double2 p01 = mine[(k >> 1)], p23 = mine[(k >> 1) + 1];
+      if (k < len) val = val - p01.x;
+      if (k + 1 < len) val = val - p01.y;
+      if (k + 2 < len) val = val - p23.x;
+      if (k + 3 < len) val = val - p23.y;
     }
     if (len) bp[row] = val;
     QPW_SYNC();
@@ -165,7 +165,7 @@ QPW_HD void qw_tri_sched(const unsigned int* sch, int c0, int c1, const double* 
   }
 }
 #else
-QPW_HD void qw_tri_sched(const unsigned int* sch, int c0, int c1, const double* lx, double* bp) {  // the 32 lanes, one after the other
+QPW_HD void qw_tri_sched(const unsigned int* sch, int c0, int c1, const double* lx, double* bp, double*) {  // the 32 lanes, one after the other
   for (int c = c0; c < c1; c++) {
     const unsigned int* rec = sch + (size_t)c * 64;
     double prod[32], out[32];
@@ -199,10 +199,10 @@ QPW_HD void qw_kkt_solve(const QpPlanDev& pl, double* w, const unsigned short* s
   QPW_PFOR(j, 0, N) bp[j] = WW(pl.o_xz, perm[j]);
   QPW_SYNC();
   if (pl.sch_n > 0) {
-    qw_tri_sched(pl.Sch, 0, pl.sch_nf, lx, bp);
+    qw_tri_sched(pl.Sch, 0, pl.sch_nf, lx, bp, w + pl.o_pb);
     QPW_PFOR(i, 0, N) bp[i] = bp[i] * WW(pl.o_Ddinv, i);
     QPW_SYNC();
-    qw_tri_sched(pl.Sch, pl.sch_nf, pl.sch_n, lx, bp);
+    qw_tri_sched(pl.Sch, pl.sch_nf, pl.sch_n, lx, bp, w + pl.o_pb);
   } else {  // a row with more than 32 entries: level by level with one row / column per lane
     for (int lv = 0; lv < pl.nlevf; lv++) {
       QPW_PFOR(ri, LevFP[lv], LevFP[lv + 1]) {

@@ -46,7 +46,7 @@ struct QpPlanDev {
   const unsigned short* Sidx; int n_sidx, nlevf, sx_Lrp, sx_Lrc, sx_Lrx, sx_LevFP, sx_LevFR, sx_Lp, sx_Li, sx_LevP, sx_LevC, sx_perm;
   // workspace layout (offsets in doubles)
   int o_Px, o_Ax, o_q, o_l, o_u, o_D, o_Dinv, o_E, o_Einv, o_rho, o_rhoinv, o_Lx, o_LxT, o_Dd, o_Ddinv, o_yw, o_x, o_xprev,
-      o_dx, o_Pxv, o_Aty, o_z, o_zprev, o_y, o_dy, o_Axv, o_xz, o_bp, o_tn, o_tm, ws_doubles;
+      o_dx, o_Pxv, o_Aty, o_z, o_zprev, o_y, o_dy, o_Axv, o_xz, o_bp, o_tn, o_tm, o_pb, ws_doubles;
 };
 
 // flattening of a host plan into one int array + one double array (what is uploaded), and the view over it

@@ -320,6 +320,7 @@ QpPlanHost* qp_plan_build(int order, int S, int Kc) {
         auto flush = [&]() {
           int mx = 0;
           for (int l = 0; l < 32; l++) mx = std::max(mx, (int)((rec[2 * l + 1] >> 16) & 0xff));
+          mx = (mx + 3) & ~3;  // the chain loop runs four entries per trip
           for (int l = 0; l < 32; l++) rec[2 * l + 1] |= (unsigned)mx << 24;
           P.Sch.insert(P.Sch.end(), rec.begin(), rec.end());
           rec.assign(64, 0); used = 0;
@@ -328,6 +329,7 @@ QpPlanHost* qp_plan_build(int order, int S, int Kc) {
         for (const Item& it : lv) {
           const int len = (int)it.ent.size();
           if (len == 0) continue;
+          used += used & 1;  // leaders sit on even lanes: the leader reads its row's products two at a time (16 B aligned)
           if (used + len > 32) { flush(); for (int l = 0; l < 32; l++) rec[2 * l] = 0xffffu; }
           for (int k = 0; k < len; k++) rec[2 * (used + k)] = (unsigned)it.ent[k].first | ((unsigned)it.ent[k].second << 16);
           rec[2 * used + 1] = (unsigned)it.dst | ((unsigned)len << 16);
@@ -400,6 +402,7 @@ void qp_plan_bind(const QpPlanHost& H, const QpPlanOffsets& o, const int* I, con
   D.o_x = take(n); D.o_xprev = take(n); D.o_dx = take(n); D.o_Pxv = take(n); D.o_Aty = take(n);
   D.o_z = take(m); D.o_zprev = take(m); D.o_y = take(m); D.o_dy = take(m); D.o_Axv = take(m);
   D.o_xz = take(N); D.o_bp = take(N); D.o_tn = take(n); D.o_tm = take(m);
+  at = (at + 1) & ~1; D.o_pb = take(64);  // the products of one schedule chunk (warp kernel; 16 B aligned)
   D.ws_warp = at;              // the warp-per-problem kernel keeps everything up to here in shared memory
   D.o_LxT = take(H.nnzL);      // thread-per-problem kernel only: L in the L' solve's consumption order
   D.ws_doubles = at;
