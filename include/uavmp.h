@@ -136,6 +136,20 @@ int uavmp_kino_get_counters(uavmp_ctx* ctx, uavmp_kino_counters* out);
 /* capacity of the per-query path staging, in sampled points (default 1024; a longer path fails its batch with UAVMP_ECAP) */
 int uavmp_kino_set_path_cap(uavmp_ctx* ctx, int points);
 
+/* ---- the other grid front-end: batched Astar::search ------------------------------ */
+/* replaces path_searching::Astar::setParam / search (src/planner/path_searching/src/a_star.cpp:6-11,48-154,
+ * include/path_searching/a_star.h:142-147) on the map given to uavmp_map_set: 26-connected grid A* whose nodes are keyed by their
+ * exact position, diagonal heuristic, in-place g updates, libstdc++ heap order.  lambda_heu / allocated_node_num: the ROS
+ * parameters astar/lambda_heu, astar/allocated_node_num (astar/resolution is overwritten by the grid map's, a_star.cpp:31);
+ * path_cap_nodes: capacity of a returned path (a longer one fails the call with UAVMP_ECAP). */
+int uavmp_astar_set_params(uavmp_ctx* ctx, double lambda_heu, int allocated_node_num, int path_cap_nodes);
+/* start_pt / end_pt: B x 3.  status 1 REACH_END | 2 NO_PATH_FOUND; use_node_num = use_node_num_ at return; path_offsets: B + 1 prefix
+ * sums of path node counts (start ... last popped node, retrievePath a_star.cpp:180-190); pop_hash / n_pop (nullable): digest and
+ * length of the ordered expansion sequence.  Returns the total number of path nodes or a negative error. */
+long long uavmp_astar_search_batch(uavmp_ctx* ctx, int B, const double* start_pt, const double* end_pt, int* status,
+                                   int* use_node_num, long long* path_offsets, uint64_t* pop_hash, int* n_pop);
+int uavmp_astar_get_paths(uavmp_ctx* ctx, double* path_xyz, long long cap_points);
+
 /* ---- hot path (b): batched MinimumControl::solve ---------------------------------------------------- */
 /* order: 5 (minimum jerk, the reference) or 7 (minimum snap, extension §9.3).  S segments.
  * pos_1d: B x (S+1) waypoints; bound_vel / bound_acc (/ bound_jerk, order 7 only, else NULL): B x 2 start,end

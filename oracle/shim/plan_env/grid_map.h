@@ -6,6 +6,10 @@
 // Every position passed to isInMap is folded into `lookup_digest`: the sequence of map lookups of a search is a fingerprint
 // of its ordered expansion sequence (each expansion starts by testing the popped node's own position, t = 0).
 #pragma once
+// <math.h> / <stdlib.h> (the C++ wrappers): in the reference build they arrive through ROS / PCL / OpenCV, and with them the
+// global-namespace overloads of abs() that a_star.cpp:77-79 relies on (`abs(double)` without std::)
+#include <math.h>
+#include <stdlib.h>
 #include <Eigen/Eigen>
 #include <cmath>
 #include <cstdint>

@@ -215,3 +215,55 @@ def kkt_solve(P_triu_csc, A_csc, sigma, rho, rhs):
     if rc:
         raise RuntimeError(f"kkt solve failed ({rc})")
     return sol
+
+
+# ---- grid A* ---------------------------------------------------------------------------------------------------------
+class AstarResult(C.Structure):
+    _fields_ = [("status", C.c_int), ("use_node_num", C.c_int), ("n_pop", C.c_int), ("n_path", C.c_int),
+                ("pop_hash", C.c_uint64), ("lookup_digest", C.c_uint64), ("n_in_map_calls", C.c_longlong)]
+
+
+class RefAstarResult(C.Structure):
+    _fields_ = [("status", C.c_int), ("use_node_num", C.c_int), ("n_path", C.c_int), ("pad", C.c_int),
+                ("lookup_digest", C.c_uint64), ("n_in_map_calls", C.c_longlong)]
+
+
+def astar_search(world, start_pt, end_pt, lambda_heu=1.0, allocated_node_num=100000, path_cap=8192):
+    """oracle/astar_ref.cpp: the restated path_searching::Astar, a fresh object per query."""
+    lib = load()
+    occ = np.ascontiguousarray(world.occ, np.int8)
+    origin, msz = _f(world.origin), _f(world.map_size)
+    sp, ep = _f(start_pt), _f(end_pt)
+    res = AstarResult()
+    path = np.zeros((path_cap, 3))
+    lib.oracle_astar_search.argtypes = [C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double,
+                                        C.c_void_p, C.c_void_p, C.POINTER(AstarResult), C.c_void_p, C.c_int]
+    lib.oracle_astar_search(lambda_heu, allocated_node_num, occ.ctypes.data, *world.dims, _p(origin), _p(msz), world.resolution, _p(sp),
+                            _p(ep), C.byref(res), path.ctypes.data, path_cap)
+    return dict(status=res.status, use_node_num=res.use_node_num, n_pop=res.n_pop, n_path=res.n_path, pop_hash=res.pop_hash,
+                lookup_digest=res.lookup_digest, n_in_map_calls=res.n_in_map_calls, path=path[:min(res.n_path, path_cap)].copy())
+
+
+_astar_ref = None
+
+
+def have_astar_ref():
+    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libastar_ref.so"))
+
+
+def astar_search_reference(world, start_pt, end_pt, lambda_heu=1.0, allocated_node_num=100000, path_cap=8192):
+    """oracle/_ref/libastar_ref.so: the reference's a_star.cpp compiled unmodified against the header shims."""
+    global _astar_ref
+    if _astar_ref is None:
+        _astar_ref = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libastar_ref.so"))
+        _astar_ref.refastar_search.argtypes = [C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                               C.c_double, C.c_void_p, C.c_void_p, C.POINTER(RefAstarResult), C.c_void_p, C.c_int]
+    occ = np.ascontiguousarray(world.occ, np.int8)
+    origin, msz = _f(world.origin), _f(world.map_size)
+    sp, ep = _f(start_pt), _f(end_pt)
+    res = RefAstarResult()
+    path = np.zeros((path_cap, 3))
+    _astar_ref.refastar_search(lambda_heu, allocated_node_num, occ.ctypes.data, *world.dims, _p(origin), _p(msz), world.resolution,
+                               _p(sp), _p(ep), C.byref(res), path.ctypes.data, path_cap)
+    return dict(status=res.status, use_node_num=res.use_node_num, n_path=res.n_path, lookup_digest=res.lookup_digest,
+                n_in_map_calls=res.n_in_map_calls, path=path[:min(res.n_path, path_cap)].copy())

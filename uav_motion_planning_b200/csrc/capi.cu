@@ -164,6 +164,7 @@ void uavmp_ctx_destroy(uavmp_ctx* ctx) {
     cudaStreamDestroy(sl.stream);
   }
   qp_free_plans(ctx);
+  astar_destroy(ctx);
   for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->ev[i]);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -355,6 +356,29 @@ int uavmp_fpmath_eval(uavmp_ctx* ctx, int op, int n_pow, const double* x, double
   if (!ctx || !x || !y || n <= 0) return UAVMP_EINVAL;
   cudaSetDevice(ctx->device);
   return kino_fpmath_eval(ctx, op, n_pow, x, y, n);
+}
+
+// ---- grid A* ---------------------------------------------------------------------------------------------
+int uavmp_astar_set_params(uavmp_ctx* ctx, double lambda_heu, int allocated_node_num, int path_cap_nodes) {
+  if (!ctx || allocated_node_num < 2 || path_cap_nodes < 2 || !(lambda_heu >= 0.0)) return UAVMP_EINVAL;
+  cudaSetDevice(ctx->device);
+  ctx->astar_lambda = lambda_heu; ctx->astar_allocated = allocated_node_num; ctx->astar_path_cap = path_cap_nodes;
+  return UAVMP_OK;
+}
+
+long long uavmp_astar_search_batch(uavmp_ctx* ctx, int B, const double* start_pt, const double* end_pt, int* status,
+                                   int* use_node_num, long long* path_offsets, uint64_t* pop_hash, int* n_pop) {
+  if (!ctx || B <= 0 || !start_pt || !end_pt || !status) return UAVMP_EINVAL;
+  cudaSetDevice(ctx->device);
+  if (!ctx->have_map) return uavmp_fail(ctx, UAVMP_ESTATE, "uavmp_map_set has not been called");
+  drain_all(ctx);
+  return astar_search_batch(ctx, B, start_pt, end_pt, status, use_node_num, path_offsets, pop_hash, n_pop);
+}
+
+int uavmp_astar_get_paths(uavmp_ctx* ctx, double* path_xyz, long long cap_points) {
+  if (!ctx || !path_xyz) return UAVMP_EINVAL;
+  cudaSetDevice(ctx->device);
+  return astar_get_paths(ctx, path_xyz, cap_points);
 }
 
 // ---- hot path (b) --------------------------------------------------------------------------------------

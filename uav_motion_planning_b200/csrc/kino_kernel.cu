@@ -412,34 +412,8 @@ __device__ __forceinline__ int level_room(int len) {
   return (2 << depth) - x;              // leaves x .. 2^(depth+1) - 1
 }
 
-// std::push_heap of (f, id) as 1-based leaf n1, ancestors read from the closure
-__device__ __forceinline__ void closure_push(SearchSmem& s, int n1, double f, uint32_t id, uint32_t hs, int lane,
-                                             const Closure& c) {
-  const int a = n1 >> lane;
-  const bool valid = (lane >= 1) && (a >= 1);
-  HeapSlot e;
-  e.f = 0; e.id = 0; e.hs = 0;
-  if (valid) e = s.b.hc[c.off + (a - c.lo)];
-  const bool gt = valid && (e.f > f);
-  const unsigned m = __ballot_sync(FULL, gt);
-  const unsigned cont = m >> 1;            // bit j: level j+1 moves down
-  const int L = __ffs(~cont) - 1;          // number of consecutive moves
-  if (lane >= 1 && lane <= L) {
-    const int tgt = n1 >> (lane - 1);
-    e.hs |= HS_DIRTY;
-    s.b.hc[c.off_m1 + (tgt - c.lo_m1)] = e;
-  }
-  const int lo_L = __shfl_sync(FULL, c.lo, L), off_L = __shfl_sync(FULL, c.off, L);
-  if (lane == 0) {
-    const int tgt = n1 >> L;
-    HeapSlot ne; ne.f = f; ne.id = id; ne.hs = hs | HS_DIRTY;
-    s.b.hc[off_L + (tgt - lo_L)] = ne;
-  }
-  __syncwarp();
-}
-
 // ---- the push through a register-resident ancestor chain -------------------------------------------------------------------
-// closure_push above reads and writes the staged ancestors in shared memory for every push (~100 dependent instructions,
+// Round 1's push read and wrote the staged ancestors in shared memory for every push (~100 dependent instructions,
 // measured ~800 cycles per push: the ordered commit was 41 % of all CTA time).  The chain of the CURRENT leaf n1 is kept in
 // registers instead: lane d caches the staged entry of ancestor n1 >> d (lane 0: the leaf itself).  A push that moves L
 // ancestors down is then one ballot plus a one-lane shuffle of the chain (lane j - 1 takes lane j's entry, lane L the new

@@ -125,6 +125,7 @@ struct KinoQpDev {
 
 // ---- host-side context -----------------------------------------------------------------------------
 struct QpPlan;  // qp_kernel.cu
+struct AstarState;  // astar_kernel.cu
 
 #define UAVMP_NSLOT 7  // slot 0: the synchronous entry points; 1..6: batches in flight (uavmp_plan_submit) — the tail of a batch
                        // spans ~3 batch times
@@ -221,6 +222,11 @@ struct uavmp_ctx {
   double* d_qp_out = nullptr; size_t qp_out_bytes = 0;
   int* d_qp_int = nullptr; size_t qp_int_bytes = 0;
 
+  // batched grid A* (astar_kernel.cu): parameters of Astar::setParam (a_star.cpp:6-11) and the lazily built device state
+  AstarState* astar = nullptr;
+  int astar_allocated = 100000, astar_path_cap = 4096;
+  double astar_lambda = 1.0;
+
   // timings of the last completed call
   cudaEvent_t ev[8];
   uavmp_timings tm;
@@ -249,3 +255,9 @@ int kino_launch_search(uavmp_ctx* ctx, PlanSlot& sl, int B, const double* d_star
                        const double* d_end_pt, const double* d_end_vel, bool sort_order, bool profile,
                        const KinoQpDev* qp, const QpPlanDev* plan, const uavmp_osqp_settings* settings);
 int kino_pack_paths(uavmp_ctx* ctx, PlanSlot& sl, int B);
+
+// astar_kernel.cu
+long long astar_search_batch(uavmp_ctx* ctx, int B, const double* start_pt, const double* end_pt, int* status, int* use_node_num,
+                             long long* path_offsets, uint64_t* pop_hash, int* n_pop);
+int astar_get_paths(uavmp_ctx* ctx, double* path_xyz, long long cap_points);
+void astar_destroy(uavmp_ctx* ctx);
