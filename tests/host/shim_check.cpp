@@ -1,4 +1,5 @@
 // compile-and-link check of the C++ shims against the Eigen stand-in (tests/test_shims.py); calls nothing that needs a GPU
+#include <uavmp/a_star.hpp>
 #include <uavmp/kino_astar.hpp>
 #include <uavmp/minimum_control.hpp>
 extern "C" int shim_check() {
@@ -9,6 +10,8 @@ extern "C" int shim_check() {
     ka.setParam(p);
     uavmp::MinimumControl mc(ka.context(), 5);
     (void)mc;
+    uavmp::Astar as(ka.context());
+    as.setParam(1.0, 100000);
     return 1;  // a GPU is present
   } catch (const std::exception&) {
     return 0;
