@@ -150,6 +150,28 @@ long long uavmp_astar_search_batch(uavmp_ctx* ctx, int B, const double* start_pt
                                    int* use_node_num, long long* path_offsets, uint64_t* pop_hash, int* n_pop);
 int uavmp_astar_get_paths(uavmp_ctx* ctx, double* path_xyz, long long cap_points);
 
+/* ---- the sampling front-end: batched RRTStar::search (the reference's QP front-end, test_minimum_jerk.cpp:40-75) -- */
+/* replaces path_searching::RRTStar::setParam / search / getOptimalPath (src/planner/path_searching/src/rrt_star.cpp:5-11,304-429,
+ * :299-302; include/path_searching/rrt_star.h:84-93) and the kd-tree it calls (src/kdtree/kdtree.cpp).  The reference draws every sample
+ * from a fresh std::random_device (one 32-bit value seeds a std::mt19937_64 per sample, rrt_star.cpp:104-116) and stops on wall-clock time;
+ * the deterministic form here: the 32-bit seed of query q's sample i is uavmp_rrt_sample_seed(query_seed[q], i), and
+ * `rrt_star/max_tolerance_time` is `sample_budget`, a number of drawn samples (the search returns REACH_END at the first accepted sample
+ * i with i + 1 >= sample_budget once the goal is connected, else after max_tree_node_num samples).  With that, the tree (every node's
+ * position, parent and g_cost) is the one the reference's own code builds from the same seeds (oracle/_ref/librrt_ref.so).
+ * max_tree_node_num / step_length / search_radius / collision_check_resolution: the ROS parameters of the same names. */
+int uavmp_rrt_set_params(uavmp_ctx* ctx, int max_tree_node_num, double step_length, double search_radius,
+                         double collision_check_resolution, double sample_budget, int path_cap_nodes);
+uint32_t uavmp_rrt_sample_seed(uint64_t query_seed, long long i);
+/* start_pt / end_pt: B x 3; query_seed: B.  status 1 REACH_END | 2 NO_PATH_FOUND; use_node_num = use_node_num_; n_samples = samples drawn;
+ * goal_g_cost = the goal node's g_cost (1 << 30 if never connected); tree_digest: order-free digest over (index, position, g_cost, parent)
+ * of every node; path_offsets: B + 1 prefix sums over getOptimalPath() — which the reference only fills when a LATER sample improves on the
+ * first feasible cost (rrt_star.cpp:396-404), so it may be empty with status 1.  Nullable outputs: all but status.  Returns the total number
+ * of path points or a negative error. */
+long long uavmp_rrt_search_batch(uavmp_ctx* ctx, int B, const double* start_pt, const double* end_pt, const uint64_t* query_seed,
+                                 int* status, int* use_node_num, long long* n_samples, double* goal_g_cost, uint64_t* tree_digest,
+                                 long long* path_offsets);
+int uavmp_rrt_get_paths(uavmp_ctx* ctx, double* path_xyz, long long cap_points);
+
 /* ---- hot path (b): batched MinimumControl::solve ---------------------------------------------------- */
 /* order: 5 (minimum jerk, the reference) or 7 (minimum snap, extension §9.3).  S segments.
  * pos_1d: B x (S+1) waypoints; bound_vel / bound_acc (/ bound_jerk, order 7 only, else NULL): B x 2 start,end

@@ -3,6 +3,9 @@
 // one "local_cloud" message; publishers swallow their messages.
 #pragma once
 #include <boost/make_shared.hpp>
+#include <algorithm>  // roscpp pulls these in for the reference sources (rrt_star.cpp uses std::queue, assert, std::remove bare)
+#include <cassert>
+#include <queue>
 #include <functional>
 #include <iostream>
 #include <map>
@@ -12,9 +15,11 @@
 
 namespace ros {
 struct Duration { double s; double toSec() const { return s; } };
+// the driver of a search whose termination depends on the clock (RRTStar::search, rrt_star.cpp:413-418) installs a deterministic one
+inline double (*&time_hook())() { static double (*h)() = nullptr; return h; }
 struct Time {
   double t = 0;
-  static Time now() { return Time(); }
+  static Time now() { Time x; if (time_hook()) x.t = time_hook()(); return x; }
   Duration operator-(const Time& o) const { return Duration{t - o.t}; }
 };
 struct Publisher {

@@ -2,6 +2,7 @@
 #include <uavmp/a_star.hpp>
 #include <uavmp/kino_astar.hpp>
 #include <uavmp/minimum_control.hpp>
+#include <uavmp/rrt_star.hpp>
 extern "C" int shim_check() {
   uavmp_kino_params p;
   uavmp_kino_params_launch(&p);
@@ -12,6 +13,8 @@ extern "C" int shim_check() {
     (void)mc;
     uavmp::Astar as(ka.context());
     as.setParam(1.0, 100000);
+    uavmp::RRTStar rs(ka.context());
+    rs.setParam();
     return 1;  // a GPU is present
   } catch (const std::exception&) {
     return 0;

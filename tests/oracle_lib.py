@@ -267,3 +267,51 @@ def astar_search_reference(world, start_pt, end_pt, lambda_heu=1.0, allocated_no
                                _p(sp), _p(ep), C.byref(res), path.ctypes.data, path_cap)
     return dict(status=res.status, use_node_num=res.use_node_num, n_path=res.n_path, lookup_digest=res.lookup_digest,
                 n_in_map_calls=res.n_in_map_calls, path=path[:min(res.n_path, path_cap)].copy())
+
+
+# ---- RRT* (second half) ----------------------------------------------------------------------------------
+class RrtResult(C.Structure):
+    _fields_ = [("status", C.c_int), ("use_node_num", C.c_int), ("n_opt_path", C.c_int), ("reach_goal", C.c_int),
+                ("n_samples", C.c_longlong), ("tree_digest", C.c_uint64), ("goal_g_cost", C.c_double), ("n_kd_visits", C.c_longlong)]
+
+
+_RRT_ARGS = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+             C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.POINTER(RrtResult), C.c_void_p, C.c_int]
+_rrt_ref = None
+
+
+def have_rrt_ref():
+    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "librrt_ref.so"))
+
+
+def _rrt_call(fn, world, start_pt, end_pt, query_seed, max_tree_node_num, step_length, search_radius, collision_check_resolution,
+              sample_budget, path_cap):
+    occ = np.ascontiguousarray(world.occ, np.int8)
+    origin, msz = _f(world.origin), _f(world.map_size)
+    sp, ep = _f(start_pt), _f(end_pt)
+    res = RrtResult()
+    path = np.zeros((path_cap, 3))
+    fn.argtypes = _RRT_ARGS
+    fn(max_tree_node_num, step_length, search_radius, collision_check_resolution, float(sample_budget), int(query_seed), occ.ctypes.data,
+       *world.dims, _p(origin), _p(msz), world.resolution, _p(sp), _p(ep), C.byref(res), path.ctypes.data, path_cap)
+    return dict(status=res.status, use_node_num=res.use_node_num, n_opt_path=res.n_opt_path, reach_goal=res.reach_goal,
+                n_samples=res.n_samples, tree_digest=res.tree_digest, goal_g_cost=res.goal_g_cost,
+                opt_path=path[:min(res.n_opt_path, path_cap)].copy())
+
+
+def rrt_search(world, start_pt, end_pt, query_seed, max_tree_node_num=100000, step_length=0.5, search_radius=0.5,
+               collision_check_resolution=0.05, sample_budget=2.0, path_cap=8192):
+    """oracle/rrt_star_ref.cpp: the restated path_searching::RRTStar with the seeded sample stream and a sample budget for
+    `max_tolerance_time`; defaults = rrt_star.cpp:7-11."""
+    return _rrt_call(load().oracle_rrt_search, world, start_pt, end_pt, query_seed, max_tree_node_num, step_length, search_radius,
+                     collision_check_resolution, sample_budget, path_cap)
+
+
+def rrt_search_reference(world, start_pt, end_pt, query_seed, max_tree_node_num=100000, step_length=0.5, search_radius=0.5,
+                         collision_check_resolution=0.05, sample_budget=2.0, path_cap=8192):
+    """oracle/_ref/librrt_ref.so: the reference's rrt_star.cpp + kdtree.cpp compiled unmodified (shims pin the RNG and the clock)."""
+    global _rrt_ref
+    if _rrt_ref is None:
+        _rrt_ref = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "librrt_ref.so"))
+    return _rrt_call(_rrt_ref.refrrt_search, world, start_pt, end_pt, query_seed, max_tree_node_num, step_length, search_radius,
+                     collision_check_resolution, sample_budget, path_cap)

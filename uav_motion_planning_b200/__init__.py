@@ -6,6 +6,7 @@ reference's two classes (KinoAstar, MinimumControl).  The CUDA library is the on
 from ._lib import Context, KinoParams, OsqpSettings, UavmpError, load  # noqa: F401
 from .kino_astar import NO_PATH_FOUND, REACH_END, KinoAstar  # noqa: F401
 from .a_star import Astar  # noqa: F401
+from .rrt_star import RRTStar  # noqa: F401
 from .mapgen import make_world, sample_queries  # noqa: F401
 
 try:  # lands with the QP kernel

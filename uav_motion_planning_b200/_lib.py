@@ -70,6 +70,7 @@ SYMBOLS = [
     "uavmp_plan_submit", "uavmp_plan_wait", "uavmp_plan_stream_wait", "uavmp_plan_max_in_flight",
     "uavmp_kino_set_path_cap", "uavmp_minctrl_solve_corridor_batch", "uavmp_plan_options_default", "uavmp_plan_submit_opt",
     "uavmp_astar_set_params", "uavmp_astar_search_batch", "uavmp_astar_get_paths",
+    "uavmp_rrt_set_params", "uavmp_rrt_sample_seed", "uavmp_rrt_search_batch", "uavmp_rrt_get_paths",
 ]
 
 WORLDGEN_SYMBOLS = ["uavmp_mapgen_params_default", "uavmp_mapgen_cloud", "uavmp_grid_inflate_host"]
@@ -170,6 +171,12 @@ def load():
     lib.uavmp_astar_search_batch.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]
     lib.uavmp_astar_search_batch.restype = C.c_longlong
     lib.uavmp_astar_get_paths.argtypes = [vp, vp, C.c_longlong]
+    lib.uavmp_rrt_set_params.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
+    lib.uavmp_rrt_sample_seed.argtypes = [C.c_uint64, C.c_longlong]
+    lib.uavmp_rrt_sample_seed.restype = C.c_uint32
+    lib.uavmp_rrt_search_batch.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.uavmp_rrt_search_batch.restype = C.c_longlong
+    lib.uavmp_rrt_get_paths.argtypes = [vp, vp, C.c_longlong]
     lib.uavmp_kino_set_profile.argtypes = [vp, C.c_int]
     lib.uavmp_kino_get_profile.argtypes = [vp, vp, vp, C.c_int, ip]
     _lib = lib

@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -130,7 +131,8 @@ __device__ uint32_t aheap_pop(AHeap* H, ANode* nodes, int& len) {
   return top;
 }
 
-__global__ void __launch_bounds__(AW * 32) astar_search_kernel(AParams P, const int8_t* __restrict__ occ, const AArena* arenas, ABatch bt) {
+template <int MINB>
+__global__ void __launch_bounds__(AW * 32, MINB) astar_search_kernel(AParams P, const int8_t* __restrict__ occ, const AArena* arenas, ABatch bt) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const AArena ar = arenas[blockIdx.x * AW + warp];
   ANode* nodes = ar.nodes;
@@ -282,6 +284,7 @@ __global__ void __launch_bounds__(AW * 32) astar_search_kernel(AParams P, const 
 
 // =====================================================================================================
 struct AstarState {
+  int ctas = 4;
   int allocated = 0, n_arenas = 0, table_bits = 0;
   void* mem = nullptr;
   AArena* d_arenas = nullptr;
@@ -317,7 +320,9 @@ static int astar_ensure(uavmp_ctx* ctx, int B) {
                  sz_tab = up(((size_t)1 << bits) * sizeof(ASlot)), per = sz_nodes + sz_heap + sz_tab + 256;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    int want = ctx->sm_count * 4 * AW;  // four CTAs of AW warps per SM
+    const char* env = getenv("UAVMP_ASTAR_CTAS");  // experiment knob: resident CTAs per SM (4 or 8)
+    a.ctas = (env && atoi(env) == 8) ? 8 : 4;
+    int want = ctx->sm_count * a.ctas * AW;  // four CTAs of AW warps per SM
     const long long fit = (long long)((free_b / 2) / per);
     if (fit < AW) return uavmp_fail(ctx, UAVMP_ENOMEM, "not enough device memory for A* arenas of %d nodes", allocated);
     if (want > fit) want = (int)(fit / AW) * AW;
@@ -391,7 +396,8 @@ long long astar_search_batch(uavmp_ctx* ctx, int B, const double* start_pt, cons
   bt.status = a.d_status; bt.use_num = a.d_use; bt.n_pop = a.d_npop; bt.pop_hash = a.d_hash; bt.n_path = a.d_npath;
   bt.path_stage = a.d_path_stage; bt.path_cap = a.path_cap; bt.next_query = a.d_misc + 1; bt.error_flag = a.d_misc;
   const int grid = std::min(a.n_arenas / AW, (B + AW - 1) / AW);
-  astar_search_kernel<<<grid, AW * 32, 0, st>>>(P, ctx->d_occ, a.d_arenas, bt);
+  if (a.ctas == 8) astar_search_kernel<8><<<grid, AW * 32, 0, st>>>(P, ctx->d_occ, a.d_arenas, bt);
+  else astar_search_kernel<4><<<grid, AW * 32, 0, st>>>(P, ctx->d_occ, a.d_arenas, bt);
   UAVMP_CUDA(ctx, cudaGetLastError());
   k_astar_offsets<<<1, 1, 0, st>>>(a.d_npath, B, a.d_offsets);
   long long total = 0;

@@ -165,6 +165,7 @@ void uavmp_ctx_destroy(uavmp_ctx* ctx) {
   }
   qp_free_plans(ctx);
   astar_destroy(ctx);
+  rrt_destroy(ctx);
   for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->ev[i]);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -379,6 +380,35 @@ int uavmp_astar_get_paths(uavmp_ctx* ctx, double* path_xyz, long long cap_points
   if (!ctx || !path_xyz) return UAVMP_EINVAL;
   cudaSetDevice(ctx->device);
   return astar_get_paths(ctx, path_xyz, cap_points);
+}
+
+int uavmp_rrt_set_params(uavmp_ctx* ctx, int max_tree_node_num, double step_length, double search_radius,
+                         double collision_check_resolution, double sample_budget, int path_cap_nodes) {
+  if (!ctx || max_tree_node_num < 1 || path_cap_nodes < 2 || !(step_length > 0.0) || !(search_radius > 0.0) ||
+      !(collision_check_resolution > 0.0) || !(sample_budget >= 0.0))
+    return UAVMP_EINVAL;
+  cudaSetDevice(ctx->device);
+  ctx->rrt_max_nodes = max_tree_node_num; ctx->rrt_step = step_length; ctx->rrt_radius = search_radius;
+  ctx->rrt_ccres = collision_check_resolution; ctx->rrt_budget = sample_budget; ctx->rrt_path_cap = path_cap_nodes;
+  return UAVMP_OK;
+}
+
+uint32_t uavmp_rrt_sample_seed(uint64_t query_seed, long long i) { return rrt_sample_seed_host(query_seed, i); }
+
+long long uavmp_rrt_search_batch(uavmp_ctx* ctx, int B, const double* start_pt, const double* end_pt, const uint64_t* query_seed,
+                                 int* status, int* use_node_num, long long* n_samples, double* goal_g_cost, uint64_t* tree_digest,
+                                 long long* path_offsets) {
+  if (!ctx || B <= 0 || !start_pt || !end_pt || !query_seed || !status) return UAVMP_EINVAL;
+  cudaSetDevice(ctx->device);
+  if (!ctx->have_map) return uavmp_fail(ctx, UAVMP_ESTATE, "uavmp_map_set has not been called");
+  drain_all(ctx);
+  return rrt_search_batch(ctx, B, start_pt, end_pt, query_seed, status, use_node_num, n_samples, goal_g_cost, tree_digest, path_offsets);
+}
+
+int uavmp_rrt_get_paths(uavmp_ctx* ctx, double* path_xyz, long long cap_points) {
+  if (!ctx || !path_xyz) return UAVMP_EINVAL;
+  cudaSetDevice(ctx->device);
+  return rrt_get_paths(ctx, path_xyz, cap_points);
 }
 
 // ---- hot path (b) --------------------------------------------------------------------------------------

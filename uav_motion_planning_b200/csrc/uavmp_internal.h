@@ -126,6 +126,7 @@ struct KinoQpDev {
 // ---- host-side context -----------------------------------------------------------------------------
 struct QpPlan;  // qp_kernel.cu
 struct AstarState;  // astar_kernel.cu
+struct RrtState;    // rrt_kernel.cu
 
 #define UAVMP_NSLOT 7  // slot 0: the synchronous entry points; 1..6: batches in flight (uavmp_plan_submit) — the tail of a batch
                        // spans ~3 batch times
@@ -226,6 +227,10 @@ struct uavmp_ctx {
   AstarState* astar = nullptr;
   int astar_allocated = 100000, astar_path_cap = 4096;
   double astar_lambda = 1.0;
+  // batched RRT* (rrt_kernel.cu): parameters of RRTStar::setParam (rrt_star.cpp:7-11; the time budget is a budget of drawn samples)
+  RrtState* rrt = nullptr;
+  int rrt_max_nodes = 100000, rrt_path_cap = 4096;
+  double rrt_step = 0.5, rrt_radius = 0.5, rrt_ccres = 0.05, rrt_budget = 100000.0;
 
   // timings of the last completed call
   cudaEvent_t ev[8];
@@ -261,3 +266,9 @@ long long astar_search_batch(uavmp_ctx* ctx, int B, const double* start_pt, cons
                              long long* path_offsets, uint64_t* pop_hash, int* n_pop);
 int astar_get_paths(uavmp_ctx* ctx, double* path_xyz, long long cap_points);
 void astar_destroy(uavmp_ctx* ctx);
+// rrt_kernel.cu
+long long rrt_search_batch(uavmp_ctx* ctx, int B, const double* start_pt, const double* end_pt, const uint64_t* query_seed, int* status,
+                           int* use_node_num, long long* n_samples, double* goal_g_cost, uint64_t* tree_digest, long long* path_offsets);
+int rrt_get_paths(uavmp_ctx* ctx, double* path_xyz, long long cap_points);
+void rrt_destroy(uavmp_ctx* ctx);
+uint32_t rrt_sample_seed_host(unsigned long long query_seed, long long i);
