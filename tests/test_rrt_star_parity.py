@@ -83,3 +83,37 @@ def test_reference_class_call_and_batch_properties(gpu_ctx):
     path = []
     st = r.search(sp[has[0]], ep[has[0]], path, query_seed=int(seeds[has[0]]))
     assert st == 1 and not path and np.array_equal(np.array(r.getOptimalPath()), got["paths"][off[has[0]]:off[has[0] + 1]])
+
+
+def test_rrt_star_to_minimum_jerk_like_the_reference_node(gpu_ctx):
+    """test_minimum_jerk.cpp:40-75: RRT* -> every optimal-path point a waypoint, T = 1 -> MinimumControl::solve per axis.  The QPs are
+    bit-identical to the reference's OSQP while S <= 40 (tabulated AMD order) and within 1e-5 beyond."""
+    from uav_motion_planning_b200 import planner
+    world = u.make_world(20, 20, 5, seed=1)
+    rrt, mc = u.RRTStar(gpu_ctx), u.MinimumControl(gpu_ctx)
+    rrt.setParam(max_tree_node_num=6000, sample_budget=6000)
+    rrt.setGridMap(world)
+    sp, _, ep, _ = u.sample_queries(world, 64, seed=8, min_dist=4.0)
+    seeds = np.arange(64, dtype=np.uint64) + np.uint64(123)
+    r, plans = planner.rrt_minimum_jerk_batch(rrt, mc, sp, ep, seeds)
+    done = [q for q in range(64) if plans[q] is not None]
+    assert len(done) >= 8 and all((r["status"][q] == 1) for q in done)
+    n_exact = 0
+    for q in done[:10]:
+        S = plans[q]["S"]
+        path = r["paths"][r["path_offsets"][q]:r["path_offsets"][q + 1]]
+        assert len(path) == S + 1
+        for ax in range(3):
+            ok, coef, info = oracle_lib.minctrl_solve(5, S, path[:, ax], np.zeros(2), np.zeros(2), np.ones(S))
+            assert bool(plans[q]["solved"][ax]) == bool(ok)
+            if not ok:
+                continue
+            got = plans[q]["coef"][ax]
+            if S <= 40:
+                assert np.array_equal(got.view(np.uint64), coef.view(np.uint64)) and plans[q]["iters"][ax] == info["iter"]
+                n_exact += 1
+            else:
+                assert np.abs(got - coef).max() <= 1e-5 * max(1.0, np.abs(coef).max())
+            # the spline interpolates the waypoints (position continuity rows of getConstraintMatrix)
+            assert abs(got[0] - path[0, ax]) < 2e-2 and abs(got[6 * (S - 1):].sum() - path[-1, ax]) < 2e-2   # eps_abs = eps_rel = 1e-3
+    assert n_exact >= 3

@@ -95,8 +95,13 @@ __device__ void aheap_push(AHeap* H, ANode* nodes, int& len, double f, uint32_t 
   nodes[id].hpos = (uint32_t)hole;
 }
 // std::pop_heap + pop_back (bits/stl_heap.h __adjust_heap: the hole walks to a leaf taking the smaller child, the right one on
-// ties; a lone left child moves up; the former last element is then pushed up from the hole)
-__device__ uint32_t aheap_pop(AHeap* H, ANode* nodes, int& len) {
+// ties; a lone left child moves up; the former last element is then pushed up from the hole).
+// Called by the WHOLE warp: the walk down is a chain of dependent loads, so the warp fetches three levels below the hole per round
+// trip (lane j < 14 loads the (j + 2)-th entry of the hole's binary subtree: children 2h, 2h+1, grandchildren 4h .. 4h+3, great-
+// grandchildren 8h .. 8h+7 — each level one contiguous, aligned block) and then every lane walks those levels from the shuffled
+// values; only lane 0 stores.  Same comparisons on the same values as the one-level loop, a third of the round trips (measured: +3 %
+// on an 8 192-query batch, whose time is the tail of its longest queries — profiles/r02_reading.md).
+__device__ uint32_t aheap_pop(AHeap* H, ANode* nodes, int& len, int lane) {
   const uint32_t top = H[1].id;
   const int old_len = len;
   len = old_len - 1;
@@ -105,29 +110,44 @@ __device__ uint32_t aheap_pop(AHeap* H, ANode* nodes, int& len) {
   const AHeap value = H[old_len];
   int hole = 1;
   while (2 * hole + 1 <= n) {
-    const AHeap l = H[2 * hole], r = H[2 * hole + 1];
-    const bool right = !(r.f > l.f);
-    const AHeap pick = right ? r : l;
-    H[hole] = pick;
-    nodes[pick.id].hpos = (uint32_t)hole;
-    hole = 2 * hole + (right ? 1 : 0);
+    // subtree entry j + 2 (1-based, root = hole): depth d = floor(log2(j + 2)), index hole * 2^d + (j + 2 - 2^d)
+    const int r1 = lane + 2, d = 31 - __clz(r1), idx = (hole << d) + (r1 - (1 << d));
+    AHeap e; e.f = 0; e.id = 0; e.pad = 0;
+    if (lane < 14 && idx <= n) e = H[idx];
+    int rel = 1, h = hole;  // position inside the fetched subtree / absolute index of the hole; invariant: 2 h + 1 <= n
+    for (int lv = 0; lv < 3; lv++) {
+      const double fl = __shfl_sync(AFULL, e.f, 2 * rel - 2), fr = __shfl_sync(AFULL, e.f, 2 * rel - 1);
+      const uint32_t il = __shfl_sync(AFULL, e.id, 2 * rel - 2), ir = __shfl_sync(AFULL, e.id, 2 * rel - 1);
+      const bool right = !(fr > fl);
+      if (lane == 0) {
+        AHeap pick; pick.f = right ? fr : fl; pick.id = right ? ir : il; pick.pad = 0;
+        H[h] = pick;
+        nodes[pick.id].hpos = (uint32_t)h;
+      }
+      rel = 2 * rel + (right ? 1 : 0);
+      h = 2 * h + (right ? 1 : 0);
+      if (2 * h + 1 > n) break;
+    }
+    hole = h;
   }
-  if (2 * hole == n) {
-    const AHeap l = H[n];
-    H[hole] = l;
-    nodes[l.id].hpos = (uint32_t)hole;
-    hole = n;
+  if (lane == 0) {
+    if (2 * hole == n) {
+      const AHeap l = H[n];
+      H[hole] = l;
+      nodes[l.id].hpos = (uint32_t)hole;
+      hole = n;
+    }
+    while (hole > 1) {
+      const int parent = hole >> 1;
+      const AHeap pe = H[parent];
+      if (!(pe.f > value.f)) break;
+      H[hole] = pe;
+      nodes[pe.id].hpos = (uint32_t)hole;
+      hole = parent;
+    }
+    H[hole] = value;
+    nodes[value.id].hpos = (uint32_t)hole;
   }
-  while (hole > 1) {
-    const int parent = hole >> 1;
-    const AHeap pe = H[parent];
-    if (!(pe.f > value.f)) break;
-    H[hole] = pe;
-    nodes[pe.id].hpos = (uint32_t)hole;
-    hole = parent;
-  }
-  H[hole] = value;
-  nodes[value.id].hpos = (uint32_t)hole;
   return top;
 }
 
@@ -177,15 +197,9 @@ __global__ void __launch_bounds__(AW * 32, MINB) astar_search_kernel(AParams P, 
 
     while (!status) {
       // ---- pop (:71-75) ------------------------------------------------------------------------------------------------
-      uint32_t cur = 0;
-      if (lane == 0) {
-        if (len == 0) status = UAVMP_NO_PATH_FOUND;  // open list empty (:150-153)
-        else { cur = aheap_pop(H, nodes, len); nodes[cur].closed = 1; }
-      }
-      status = __shfl_sync(AFULL, status, 0);
-      if (status) break;
-      cur = __shfl_sync(AFULL, cur, 0);
-      len = __shfl_sync(AFULL, len, 0);
+      if (len == 0) { status = UAVMP_NO_PATH_FOUND; break; }  // open list empty (:150-153); len is warp-uniform
+      const uint32_t cur = aheap_pop(H, nodes, len, lane);
+      if (lane == 0) nodes[cur].closed = 1;
       __syncwarp();
       const ANode cn = nodes[cur];
       n_pop++;
@@ -239,6 +253,14 @@ __global__ void __launch_bounds__(AW * 32, MINB) astar_search_kernel(AParams P, 
       }
       // ---- ordered replay (lane 0), lattice order == lane order ---------------------------------------------------------
       unsigned evm = __ballot_sync(AFULL, verdict != 0);
+      if (evm) {  // the pushes of this expansion append leaves len + 1 .. : pull their parents / grandparents / great-grandparents
+                  // into L1 in one round trip (a push usually stops within a level or two of its leaf) instead of one miss per push
+        const int leaf = len + 1 + (lane & 15);
+        const int a1 = (lane < 16) ? (leaf >> 1) : (leaf >> 2), a3 = leaf >> 3;
+        double sink = (a1 >= 1) ? H[a1].f : 0.0;
+        if (lane < 16 && a3 >= 1) sink += H[a3].f;
+        asm volatile("" ::"d"(sink));
+      }
       while (evm && !status) {
         const int l = __ffs(evm) - 1;
         evm &= evm - 1;

@@ -111,3 +111,32 @@ def plan_batch_dev(ctx, B, d_sp, d_sv, d_ep, d_ev, d_status, d_solved, d_coef, o
     ctx.check(ctx.lib.uavmp_plan_batch_dev(ctx.h, B, vp(d_sp), vp(d_sv), vp(d_ep), vp(d_ev), order, S, float(seg_time),
                                            C.byref(settings) if settings is not None else None, vp(d_status),
                                            vp(d_solved), vp(d_coef)))
+
+
+def rrt_minimum_jerk_batch(rrt, optimizer, start_pt, end_pt, query_seed, start_vel=None, seg_time=1.0):
+    """The reference's own front-end → optimiser flow (test_minimum_jerk.cpp:40-75 GoalCallback), batched: RRTStar::search, then — for
+    every query that returned REACH_END with a non-empty getOptimalPath() — EVERY point of the optimal path is a waypoint,
+    `time_vec(i) = 1.0` for every segment (:65-71), end velocity / both accelerations zero (:31-37), and MinimumControl::solve runs once
+    per axis.  The number of segments differs per query, so the QPs are solved in groups of equal S (one uavmp_minctrl_solve_batch
+    call per group, 3 problems per query).  Returns a list with one entry per query: None, or dict(S, coef[3, 6 S], solved[3], iters[3])."""
+    sp, ep = (_lib.as_f64(a).reshape(-1, 3) for a in (start_pt, end_pt))
+    B = sp.shape[0]
+    sv = np.zeros((B, 3)) if start_vel is None else _lib.as_f64(start_vel).reshape(B, 3)
+    r = rrt.search_batch(sp, ep, query_seed)
+    off = r["path_offsets"]
+    groups = {}
+    for q in range(B):
+        n = int(off[q + 1] - off[q])
+        if r["status"][q] == 1 and n >= 2:
+            groups.setdefault(n - 1, []).append(q)
+    out = [None] * B
+    for S, qs in sorted(groups.items()):
+        pos = np.stack([r["paths"][off[q]:off[q + 1]] for q in qs])            # [nq, S + 1, 3]
+        pos_1d = np.ascontiguousarray(pos.transpose(0, 2, 1)).reshape(-1, S + 1)  # problem 3 i + axis
+        bv = np.zeros((len(qs) * 3, 2))
+        bv[:, 0] = sv[qs].reshape(-1)
+        res = optimizer.solve_batch(pos_1d, bv, np.zeros_like(bv), np.full((len(qs) * 3, S), float(seg_time)), order=5)
+        for i, q in enumerate(qs):
+            out[q] = dict(S=S, coef=res["coef"][3 * i:3 * i + 3].copy(), solved=res["solved"][3 * i:3 * i + 3].copy(),
+                          iters=res["iters"][3 * i:3 * i + 3].copy())
+    return r, out
