@@ -71,3 +71,24 @@ def test_big_map_batch(gpu_ctx):
         o0, o1 = off[q], off[q + 1]
         assert (ref["status"], ref["use_node_num"], ref["pop_hash"]) == (got["status"][q], got["use_node_num"][q], int(got["pop_hash"][q]))
         assert np.array_equal(ref["path"].view(np.uint64), got["paths"][o0:o1].view(np.uint64))
+
+
+def test_golden_vectors_of_the_reference_build(gpu_ctx):
+    """tests/golden/astar_golden.json: outputs of the reference's own a_star.cpp build (make_f4_golden.py)"""
+    import hashlib
+    import json
+    import os
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "astar_golden.json")))["cases"]
+    for case in cases:
+        world = u.make_world(*case["dims"], seed=case["map_seed"])
+        a = u.Astar(gpu_ctx)
+        a.setParam(**case["params"])
+        a.setGridMap(world)
+        sp = np.array([q["start_pt"] for q in case["queries"]])
+        ep = np.array([q["end_pt"] for q in case["queries"]])
+        got = a.search_batch(sp, ep)
+        for i, q in enumerate(case["queries"]):
+            o0, o1 = got["path_offsets"][i], got["path_offsets"][i + 1]
+            assert (q["status"], q["use_node_num"], q["n_path"]) == (got["status"][i], got["use_node_num"][i], o1 - o0), (case["name"], i)
+            assert hashlib.sha256(np.ascontiguousarray(got["paths"][o0:o1]).tobytes()).hexdigest() == q["path_sha256"], (case["name"], i)
+    u.Astar(gpu_ctx).setParam(lambda_heu=1.0, allocated_node_num=100000)  # back to the defaults for the shared context

@@ -117,3 +117,26 @@ def test_rrt_star_to_minimum_jerk_like_the_reference_node(gpu_ctx):
             # the spline interpolates the waypoints (position continuity rows of getConstraintMatrix)
             assert abs(got[0] - path[0, ax]) < 2e-2 and abs(got[6 * (S - 1):].sum() - path[-1, ax]) < 2e-2   # eps_abs = eps_rel = 1e-3
     assert n_exact >= 3
+
+
+def test_golden_vectors_of_the_reference_build(gpu_ctx):
+    """tests/golden/rrt_star_golden.json: outputs of the reference's own rrt_star.cpp + kdtree.cpp build (make_f4_golden.py)"""
+    import hashlib
+    import json
+    import os
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "rrt_star_golden.json")))["cases"]
+    for case in cases:
+        world = u.make_world(*case["dims"], seed=case["map_seed"])
+        r = u.RRTStar(gpu_ctx)
+        r.setParam(**case["params"])
+        r.setGridMap(world)
+        sp = np.array([q["start_pt"] for q in case["queries"]])
+        ep = np.array([q["end_pt"] for q in case["queries"]])
+        seeds = np.array([q["query_seed"] for q in case["queries"]], np.uint64)
+        got = r.search_batch(sp, ep, seeds)
+        for i, q in enumerate(case["queries"]):
+            o0, o1 = got["path_offsets"][i], got["path_offsets"][i + 1]
+            assert (q["status"], q["use_node_num"], q["n_samples"], q["tree_digest"], q["n_opt_path"]) == \
+                (got["status"][i], got["use_node_num"][i], got["n_samples"][i], str(int(got["tree_digest"][i])), o1 - o0), (case["name"], i)
+            assert q["goal_g_cost_bits"] == str(got["goal_g_cost"][i:i + 1].view(np.uint64)[0]), (case["name"], i)
+            assert hashlib.sha256(np.ascontiguousarray(got["paths"][o0:o1]).tobytes()).hexdigest() == q["opt_path_sha256"], (case["name"], i)
