@@ -46,3 +46,36 @@ def evaluate_batch(ctx, coef, times, t, deriv=0):
     ctx.check(ctx.lib.uavmp_polytraj_eval_batch(ctx.h, B, nc - 1, S, _lib.ptr(coef), _lib.ptr(times), len(t), _lib.ptr(t), deriv,
                                                 _lib.ptr(out)))
     return out
+
+
+# ---- quadrotor_msgs/PolynomialTrajectory: the wire layout between the optimiser and traj_server (host-side, no GPU) -------------------
+ACTION_ADD, ACTION_ABORT, ACTION_WARN_START, ACTION_WARN_FINAL, ACTION_WARN_IMPOSSIBLE = 1, 2, 3, 4, 5  # PolynomialTrajectory.msg:7-11
+
+
+def to_polynomial_trajectory(coef, times, trajectory_id=1, stamp=0.0, start_yaw=0.0, final_yaw=0.0, action=ACTION_ADD):
+    """One plan of uavmp_plan_batch / MinimumControl (coef [3, n] or [3, S, order+1], segment-major, ascending power, local time) as the
+    fields of simulator/utils/quadrotor_msgs/msg/PolynomialTrajectory.msg: coef_x[i * (num_order + 1) + j] is the t^j coefficient of
+    segment i — exactly the indexing poly_traj_server.cpp:68-78 (trajCallback) reads back."""
+    times = np.asarray(times, float).reshape(-1)
+    S = len(times)
+    c = np.asarray(coef, float).reshape(3, S, -1)
+    order = c.shape[2] - 1
+    return dict(header=dict(stamp=float(stamp), frame_id="world"), trajectory_id=int(trajectory_id), action=int(action), num_order=order,
+                num_segment=S, start_yaw=float(start_yaw), final_yaw=float(final_yaw), coef_x=c[0].reshape(-1).tolist(),
+                coef_y=c[1].reshape(-1).tolist(), coef_z=c[2].reshape(-1).tolist(), time=times.tolist(), mag_coeff=1.0,
+                order=[order] * S, debug_info="")
+
+
+def from_polynomial_trajectory(msg, ctx=None):
+    """trajCallback (poly_traj_server.cpp:57-81): per segment i the num_order + 1 coefficients of each axis and time[i] go to
+    PolyTraj::addSegment, then init().  Returns (coef [3, S, order+1], times [S]) and, when a context is given, the PolyTraj mirror."""
+    n, S = msg["num_order"] + 1, msg["num_segment"]
+    coef = np.stack([np.asarray(msg[k], float)[:S * n].reshape(S, n) for k in ("coef_x", "coef_y", "coef_z")])
+    times = np.asarray(msg["time"], float)[:S]
+    if ctx is None:
+        return coef, times
+    pt = PolyTraj(ctx)
+    for i in range(S):
+        pt.addSegment(coef[0, i], coef[1, i], coef[2, i], times[i])
+    pt.init()
+    return coef, times, pt
