@@ -51,16 +51,38 @@ def test_against_reference_osqp(order, S, eps):
 
 
 def test_fallback_ordering_outside_the_table():
-    """S = 41 is not tabulated: the plan falls back to its own minimum-degree order; agreement is then to rounding."""
+    """Order 7, S = 41 is not tabulated: the plan falls back to its own minimum-degree order; agreement is then to rounding."""
     S, rng = 41, np.random.default_rng(41)
     pos = np.cumsum(rng.normal(size=(2, S + 1)), axis=1)
     z = np.zeros((2, 2))
-    got = host_qp.solve_batch(5, pos, z, z, np.ones((2, S)))
+    got = host_qp.solve_batch(7, pos, z, z, np.ones((2, S)), bj=z)
     if oracle_lib.have_ref():
         for b in range(2):
-            ok, coef, info = oracle_lib.minctrl_solve(5, S, pos[b], z[b], z[b], np.ones(S))
+            ok, coef, info = oracle_lib.minctrl_solve(7, S, pos[b], z[b], z[b], np.ones(S), bound_jerk=z[b])
             assert ok == got["solved"][b]
             assert np.abs(coef - got["coef"][b]).max() / np.abs(coef).max() < 1e-4
+
+
+@pytest.mark.parametrize("S", [41, 56, 64, 80])
+def test_long_minimum_jerk_chains_like_the_rrt_star_front_end(S):
+    """The reference's own flow makes every RRT* optimal-path point a waypoint (test_minimum_jerk.cpp:44-71): 20 - 70 segments of order 5.
+    AMD orders are tabulated up to S = 80 for order 5, so thread body, warp body (both loop orders) and the reference's OSQP agree bit
+    for bit there too, adaptive-rho updates included."""
+    rng = np.random.default_rng(S)
+    B = 2
+    pos = np.cumsum(rng.normal(0, 0.5, (B, S + 1)), axis=1)
+    bv = np.zeros((B, 2)); bv[:, 0] = rng.normal(0, 1, B)
+    ba = np.zeros((B, 2))
+    T = np.ones((B, S)) if S != 64 else rng.uniform(0.5, 2.0, (B, S))
+    r = host_qp.solve_batch(5, pos, bv, ba, T)
+    rw = host_qp.solve_batch_warp(5, pos, bv, ba, T)
+    rr = host_qp.solve_batch_warp(5, pos, bv, ba, T, reversed_loops=True)
+    assert np.array_equal(r["coef"].view(np.uint64), rw["coef"].view(np.uint64)) and np.array_equal(rw["coef"].view(np.uint64), rr["coef"].view(np.uint64))
+    if oracle_lib.have_ref():
+        for b in range(B):
+            ok, coef, info = oracle_lib.minctrl_solve(5, S, pos[b], bv[b], ba[b], T[b])
+            assert ok == r["solved"][b] and info["iter"] == r["iters"][b] == rw["iters"][b]
+            assert np.array_equal(coef.view(np.uint64), r["coef"][b].view(np.uint64))
 
 
 def test_max_iter_status():

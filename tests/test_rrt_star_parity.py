@@ -87,7 +87,7 @@ def test_reference_class_call_and_batch_properties(gpu_ctx):
 
 def test_rrt_star_to_minimum_jerk_like_the_reference_node(gpu_ctx):
     """test_minimum_jerk.cpp:40-75: RRT* -> every optimal-path point a waypoint, T = 1 -> MinimumControl::solve per axis.  The QPs are
-    bit-identical to the reference's OSQP while S <= 40 (tabulated AMD order) and within 1e-5 beyond."""
+    bit-identical to the reference's OSQP while S <= 80 (AMD order tabulated for order 5) and within 1e-5 beyond."""
     from uav_motion_planning_b200 import planner
     world = u.make_world(20, 20, 5, seed=1)
     rrt, mc = u.RRTStar(gpu_ctx), u.MinimumControl(gpu_ctx)
@@ -109,7 +109,7 @@ def test_rrt_star_to_minimum_jerk_like_the_reference_node(gpu_ctx):
             if not ok:
                 continue
             got = plans[q]["coef"][ax]
-            if S <= 40:
+            if S <= 80:
                 assert np.array_equal(got.view(np.uint64), coef.view(np.uint64)) and plans[q]["iters"][ax] == info["iter"]
                 n_exact += 1
             else:

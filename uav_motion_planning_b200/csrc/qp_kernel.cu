@@ -15,8 +15,8 @@
 // index lists (uniform, read-only loads) while its own numbers live in a batch-interleaved workspace:
 // element e of problem b is ws[e * stride + b].  A warp therefore touches 32 consecutive doubles per access
 // (fully coalesced 256 B) and never diverges on structure — only on the data-dependent iteration count.
-// The fill-reducing order is the one the reference's own AMD returns for this pattern (csrc/amd_perm_table.inc, order 5 / 7,
-// S <= 40), so the ADMM iterates are bit-identical to the reference's OSQP; other (order, S) fall back to a plain
+// The fill-reducing order is the one the reference's own AMD returns for this pattern (csrc/amd_perm_table.inc: order 5 with
+// S <= 80, order 7 with S <= 40), so the ADMM iterates are bit-identical to the reference's OSQP; other (order, S) fall back to a plain
 // minimum-degree order and agree to rounding only (the parity gate there is 1e-5 relative + identical status / iterations).
 //
 // Three executions of the same restatement: qp_solve_kernel (one thread per problem, batch-interleaved workspace),
