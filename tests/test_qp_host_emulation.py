@@ -123,11 +123,11 @@ def test_warp_body_equals_thread_body_on_random_problems():
         for rev in (False, True):
             w = host_qp.solve_batch_warp(order, pos, bv, ba, T, bj, reversed_loops=rev)
             assert np.array_equal(a["coef"], w["coef"]) and np.array_equal(a["iters"], w["iters"]) and np.array_equal(a["status"], w["status"])
-    # max_iter below the first check and the fallback ordering (S = 41 is not tabulated)
+    # max_iter below the first check and the fallback ordering (order 7, S = 41 is not tabulated)
     pos = np.cumsum(rng.normal(size=(2, 42)), axis=1)
     z = np.zeros((2, 2))
-    a = host_qp.solve_batch(5, pos, z, z, np.ones((2, 41)), settings=default_settings(max_iter=10))
-    w = host_qp.solve_batch_warp(5, pos, z, z, np.ones((2, 41)), settings=default_settings(max_iter=10), reversed_loops=True)
+    a = host_qp.solve_batch(7, pos, z, z, np.ones((2, 41)), z, settings=default_settings(max_iter=10))
+    w = host_qp.solve_batch_warp(7, pos, z, z, np.ones((2, 41)), z, settings=default_settings(max_iter=10), reversed_loops=True)
     assert np.array_equal(a["coef"], w["coef"]) and np.array_equal(a["status"], w["status"])
 
 
